@@ -1,0 +1,182 @@
+/*
+ * cpppd.h — C ABI of the B200-native Chambolle-Pock PPD LP solver core (libcpppd.so).
+ *
+ * This is the drop-in boundary for the hot path of martinResearch/PySparseLP:
+ * everything the reference does inside
+ *     pysparselp/ChambollePockPPD.py:122-343   (preconditioners, main loop, stats block)
+ * happens behind these entry points, on the GPU, in IEEE fp64.  The host side
+ * (pysparselp_b200/ChambollePockPPD.py) keeps the reference's Python signature and
+ * calls this library through ctypes; see INTEGRATION.md for the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer in cpppd_problem is a HOST pointer that stays
+ *     owned by the caller and is only read during cpppd_create();
+ *   - every function returns 0 on success and a negative cpppd_status on failure; a
+ *     human readable message is available from cpppd_last_error(); CUDA errors are
+ *     sticky on the handle; nothing throws across the boundary;
+ *   - one host thread drives one handle; all work of a handle is issued on one CUDA
+ *     stream (the one given at creation, or an internal one) and is asynchronous
+ *     unless the function says it synchronises;
+ *   - there is NO CPU fallback: without a CUDA device cpppd_create() fails.
+ *
+ * Problem statement (reference ChambollePockPPD.py:55-65 after the one-sided
+ * conversion of :74-88, which stays in Python):
+ *     min c.x   s.t.  A[0:m_eq] x = b[0:m_eq],   A[m_eq:m] x <= b[m_eq:m],   lb <= x <= ub
+ * with A = [A_eq ; A_ineq] stacked row-wise in CSR (entry order inside a row is
+ * preserved: it defines the floating-point summation order).
+ */
+#ifndef CPPPD_H
+#define CPPPD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPPPD_ABI_VERSION 1
+
+typedef struct cpppd_solver *cpppd_handle;
+
+typedef enum {
+  CPPPD_OK = 0,
+  CPPPD_ERR_INVALID = -1,  /* bad argument / malformed CSR */
+  CPPPD_ERR_CUDA = -2,     /* CUDA runtime error (sticky) */
+  CPPPD_ERR_NOMEM = -3,    /* allocation failed */
+  CPPPD_ERR_NODEVICE = -4, /* no CUDA device: there is no CPU path */
+  CPPPD_ERR_COMM = -5,     /* NCCL / multi-GPU exchange error */
+  CPPPD_ERR_STATE = -6     /* call sequence violated (e.g. stats before a primal step) */
+} cpppd_status;
+
+/* Device buffer provider.  The Python front passes callbacks that hand out
+ * torch.uint8 CUDA tensors (PyTorch is only the buffer allocator); NULL means
+ * cudaMalloc/cudaFree.  Returned pointers must be 256-byte aligned device memory
+ * on the problem's device. */
+typedef void *(*cpppd_alloc_fn)(size_t bytes, void *user);
+typedef void (*cpppd_free_fn)(void *ptr, void *user);
+
+enum {
+  CPPPD_FLAG_NONE = 0,
+  /* compress matrix values through a dictionary when they take few distinct values
+   * (bit-exact: the dictionary holds the original doubles) */
+  CPPPD_FLAG_VALUE_DICT = 1u << 0,
+  /* replace constant vectors (b, sigma, lb, ub) by scalars inside the kernels */
+  CPPPD_FLAG_CONST_VECTORS = 1u << 1,
+  /* do not capture the inner iterations into CUDA graphs */
+  CPPPD_FLAG_NO_GRAPH = 1u << 2
+};
+
+typedef struct {
+  int32_t abi_version;  /* must be CPPPD_ABI_VERSION */
+  int32_t device;       /* CUDA device ordinal */
+  int64_t n;            /* variables (columns) */
+  int64_t m_eq;         /* equality rows: rows [0, m_eq) of the stacked matrix */
+  int64_t m_ineq;       /* inequality rows: rows [m_eq, m_eq + m_ineq) */
+  int64_t nnz;          /* stored entries (explicit zeros count, as in scipy) */
+  const void *indptr;   /* m+1 row pointers, int32 or int64 */
+  const void *indices;  /* nnz column indices, int32 or int64 */
+  const double *values; /* nnz values */
+  int32_t indptr_bits;  /* 32 or 64 */
+  int32_t index_bits;   /* 32 or 64 */
+  const double *c;      /* n   costs                           (ChambollePockPPD.py:198)   */
+  const double *b;      /* m   right-hand sides [b_eq; b_ineq] (:235,:240)                 */
+  const double *lb;     /* n   lower bounds, -inf allowed      (:221)                      */
+  const double *ub;     /* n   upper bounds, +inf allowed      (:222)                      */
+  const double *x0;     /* n   initial point or NULL for zeros (:91-94)                    */
+  double alpha;         /* preconditioner exponent             (:133,:143,:160,:171)       */
+  double theta;         /* extrapolation                       (:226)                      */
+  double one_plus_theta;/* (1 + theta) as evaluated by the host language (:226)            */
+  void *stream;         /* cudaStream_t to issue on, or NULL for an internal stream        */
+  uint32_t flags;       /* CPPPD_FLAG_* */
+  int32_t sort_window;  /* SELL sigma: rows are sorted by length inside windows of this many
+                           rows (<=1: keep the original order) */
+  cpppd_alloc_fn alloc; /* may be NULL */
+  cpppd_free_fn free;   /* may be NULL */
+  void *alloc_user;
+} cpppd_problem;
+
+/* The numbers the reference's stats block produces (ChambollePockPPD.py:242-291). */
+typedef struct {
+  int64_t niter;                       /* iteration index the block belongs to                */
+  double energy1;                      /* c.x + y.(Ax - b)          (:248,:267,:271)          */
+  double energy2;                      /* c.x4 + y.(A x4 - b)       (:260-263,:268,:272)      */
+  double max_violated_equality;        /* max |A_eq xbar - b_eq|    (:269), 0 without eq rows */
+  double max_violated_inequality;      /* max (A_ineq xr - b_ineq)  (:283), -inf without rows */
+  double energy_rounded;               /* c.xr                      (:278)                    */
+  double max_violated_equality_rounded;/* max |A_eq xr - b_eq|      (:280-282)                */
+  double best_integer_energy;          /* running minimum over feasible xr (:289-291)         */
+  double frac_zero_xbar;               /* mean(xbar == 0)           (:308)                    */
+  int32_t feasible;                    /* exact test of :284                                   */
+  int32_t improved;                    /* xr became the best integer solution at this block   */
+  int32_t have_best_integer;           /* a best integer solution exists                       */
+  int32_t reserved;
+} cpppd_stats;
+
+typedef struct {
+  int64_t n, m_eq, m_ineq, nnz;
+  int64_t a_padded_entries;  /* entries stored for A   in SELL-32 (>= nnz) */
+  int64_t at_padded_entries; /* entries stored for A^T in SELL-32 (>= nnz) */
+  int64_t device_bytes;      /* resident device memory of the solver state */
+  int64_t bytes_per_iteration_algorithmic; /* 2*nnz*12 + P(m+1) + P(n+1) + 8(8n+5m) */
+  int64_t bytes_per_iteration_actual;      /* what the kernels of this handle really stream    */
+  int32_t value_bytes;       /* bytes per stored matrix value (8, or 1/2 with a dictionary)    */
+  int32_t const_vector_mask; /* bit0 b, bit1 sigma, bit2 lb, bit3 ub folded to scalars         */
+  int32_t sm_count;
+  int32_t world_size;
+  int64_t row_begin, row_end;/* rows of the stacked matrix owned by this rank                   */
+} cpppd_info;
+
+typedef enum {
+  CPPPD_VEC_X = 0,       /* n  primal iterate x                         */
+  CPPPD_VEC_XBAR = 1,    /* n  extrapolated point (x3 in the reference) */
+  CPPPD_VEC_Y = 2,       /* m  duals [y_eq; y_ineq]                     */
+  CPPPD_VEC_T = 3,       /* n  diag_t   (:153)                          */
+  CPPPD_VEC_SIGMA = 4,   /* m  [diag_sigma_eq; diag_sigma_ineq] (:164,:175) */
+  CPPPD_VEC_BEST_INTEGER = 5, /* n, valid when stats.have_best_integer  */
+  CPPPD_VEC_D = 6        /* n  d = c + A^T y of the last stats step (:198-217) */
+} cpppd_vector;
+
+/* -- lifetime ------------------------------------------------------------------ */
+/* Upload the LP, build A and A^T in SELL-32 on the device, compute diag_t and the
+ * sigmas (ChambollePockPPD.py:122-179), set x = x0, y = 0.  Synchronises. */
+int cpppd_create(const cpppd_problem *problem, cpppd_handle *out);
+int cpppd_destroy(cpppd_handle h);
+/* Message of the last failure on this handle (or of the last failed cpppd_create
+ * on this thread when h is NULL). */
+const char *cpppd_last_error(cpppd_handle h);
+int cpppd_abi_version(void);
+
+/* -- the iteration (ChambollePockPPD.py:195-343) ----------------------------------- */
+/* k full iterations: [x,xbar <- primal(y)] ; [y <- dual(xbar)], asynchronous. */
+int cpppd_iterate(cpppd_handle h, int64_t k);
+/* First half of an iteration (:198-240): x, xbar from the current y.  With keep_d != 0
+ * the vector d = c + A^T y is also stored (needed by a following cpppd_stats_step).
+ * Asynchronous. */
+int cpppd_primal_step(cpppd_handle h, int32_t keep_d);
+/* The stats block (:248-291), evaluated between the two halves of an iteration, i.e.
+ * with the new x / xbar and the still unmodified y.  Requires the preceding
+ * cpppd_primal_step(keep_d = 1).  Updates the best integer solution on the device and
+ * starts the copy of the result to the host.  Asynchronous. */
+int cpppd_stats_step(cpppd_handle h, int32_t force_integer);
+/* Second half (:333-343): y from xbar; increments the iteration counter. */
+int cpppd_dual_step(cpppd_handle h);
+/* Wait for everything issued so far. */
+int cpppd_sync(cpppd_handle h);
+/* Wait, then return the stats of the last cpppd_stats_step. */
+int cpppd_read_stats(cpppd_handle h, cpppd_stats *out);
+/* Run k iterations bracketed by CUDA events on the solver's stream; returns the
+ * elapsed device time in milliseconds.  Synchronises. */
+int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms);
+
+/* -- state access (synchronising copies to/from HOST memory) ------------------------- */
+int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst);
+int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src); /* X, XBAR, Y only */
+int cpppd_get_info(cpppd_handle h, cpppd_info *out);
+int64_t cpppd_iteration_count(cpppd_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPPPD_H */

@@ -1,0 +1,380 @@
+"""Chambolle-Pock diagonally preconditioned primal-dual LP solver — B200 front end.
+
+Drop-in for the reference's ``pysparselp/ChambollePockPPD.py:36-346``: same function name,
+positional arguments, defaults, callback protocol and ``(x, best_integer_solution)``
+return.  The Python here only prepares the operator ([A_eq; A_ineq] in CSR, one-sided
+inequality rows as in ``:70-88``) and drives the schedule; every floating point operation
+of the solver (preconditioners ``:122-179``, the loop ``:195-343``, the stats block
+``:242-291``) runs in hand-written CUDA behind the C ABI of ``include/cpppd.h``.
+PyTorch is used for one thing: handing out device buffers (``torch.uint8`` tensors) and
+the current CUDA stream.  There is no CPU fallback.
+
+Extra keyword-only arguments (defaults keep the reference behaviour):
+``device`` (CUDA ordinal or torch.device), ``verbose`` (print the reference's per-block
+line), ``flags`` (CPPPD_FLAG_* bit mask), ``return_solver`` (also return the live
+``CpPpdSolver`` for inspection).
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _cabi
+
+
+def _as_f64(v, size, name):
+    a = np.ascontiguousarray(v, dtype=np.float64).ravel()
+    if a.size != size:
+        raise ValueError("%s has %d entries, expected %d" % (name, a.size, size))
+    return a
+
+
+def one_sided_rows(a_ineq, b_lower, b_upper):
+    """``b_lower <= A x <= b_upper``  ->  ``A' x <= b'``  (reference ``:74-88``).
+
+    Rows of ``A'``: those with a finite upper bound (original order), then the negation of
+    those with a finite lower bound (original order).  Deviation from the reference: when
+    only one side has finite entries the reference keeps / negates the whole matrix without
+    dropping the unbounded rows and then fails its own shape assertion (``:141``); here the
+    unbounded rows are dropped, which is what the two-sided branch does and is a no-op
+    whenever the reference does not crash.
+    """
+    if a_ineq is None or b_lower is None:
+        return a_ineq, b_upper
+    b_lower = np.asarray(b_lower, dtype=np.float64)
+    b_upper = np.asarray(b_upper, dtype=np.float64)
+    up = np.flatnonzero(b_upper != np.inf)
+    lo = np.flatnonzero(b_lower != -np.inf)
+    m = a_ineq.shape[0]
+    if up.size and lo.size:
+        a = sp.vstack((a_ineq[up, :], -a_ineq[lo, :])).tocsr()
+    elif lo.size:
+        a = -a_ineq if lo.size == m else -a_ineq[lo, :]
+    else:
+        a = a_ineq if up.size == m else a_ineq[up, :]
+    return a, np.concatenate((b_upper[up], -b_lower[lo]))
+
+
+class _TorchBuffers:
+    """Device buffer provider for libcpppd: every buffer is a ``torch.uint8`` CUDA tensor."""
+
+    def __init__(self, device):
+        import torch
+
+        self.torch = torch
+        self.device = device
+        self.live = {}
+        self.alloc_cb = _cabi.ALLOC_FN(self._alloc)
+        self.free_cb = _cabi.FREE_FN(self._free)
+
+    def _alloc(self, nbytes, _user):
+        try:
+            t = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+        except Exception:  # out of memory -> NULL -> CPPPD_ERR_NOMEM
+            return None
+        self.live[t.data_ptr()] = t
+        return t.data_ptr()
+
+    def _free(self, ptr, _user):
+        self.live.pop(ptr, None)
+
+
+class CpPpdSolver:
+    """Live solver state on one GPU (thin wrapper over a ``cpppd_handle``)."""
+
+    def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
+                 sort_window=1):
+        import torch
+
+        self.lib = _cabi.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pysparselp_b200 needs a CUDA device (B200); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        a = sp.csr_matrix(a) if not sp.isspmatrix_csr(a) else a
+        m, n = a.shape
+        self.n, self.m, self.m_eq = n, m, int(m_eq)
+        c = _as_f64(c, n, "c")
+        lb = _as_f64(lb, n, "lb")
+        ub = _as_f64(ub, n, "ub")
+        b = _as_f64(b, m, "b")
+        x0 = None if x0 is None else _as_f64(x0, n, "x0")
+        data = np.ascontiguousarray(a.data, dtype=np.float64)
+        indices = np.ascontiguousarray(a.indices)
+        if indices.dtype != np.int32:
+            indices = indices.astype(np.int32)
+        indptr = np.ascontiguousarray(a.indptr)
+        if indptr.dtype not in (np.int32, np.int64):
+            indptr = indptr.astype(np.int64)
+        self._keep = (c, lb, ub, b, x0, data, indices, indptr)
+        self._buffers = _TorchBuffers(dev)
+        p = _cabi.Problem()
+        p.abi_version = _cabi.ABI_VERSION
+        p.device = dev.index
+        p.n, p.m_eq, p.m_ineq, p.nnz = n, int(m_eq), m - int(m_eq), int(indptr[-1]) if m else 0
+        p.indptr = indptr.ctypes.data
+        p.indices = indices.ctypes.data
+        p.values = data.ctypes.data
+        p.indptr_bits = 32 if indptr.dtype == np.int32 else 64
+        p.index_bits = 32
+        p.c, p.b, p.lb, p.ub = c.ctypes.data, b.ctypes.data, lb.ctypes.data, ub.ctypes.data
+        p.x0 = None if x0 is None else x0.ctypes.data
+        p.alpha, p.theta = float(alpha), float(theta)
+        p.one_plus_theta = float(1 + theta)
+        p.stream = torch.cuda.current_stream(dev).cuda_stream or None
+        p.flags = int(flags)
+        p.sort_window = int(sort_window)
+        p.alloc = self._buffers.alloc_cb
+        p.free = self._buffers.free_cb
+        p.alloc_user = None
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib, None, self.lib.cpppd_create(C.byref(p), C.byref(handle)))
+        self.handle = handle
+        self._keep = None  # host arrays are only read during create
+
+    # -- schedule ---------------------------------------------------------------------------
+    def _call(self, fn, *args):
+        return _cabi.check(self.lib, self.handle, fn(self.handle, *args))
+
+    def iterate(self, k):
+        self._call(self.lib.cpppd_iterate, int(k))
+
+    def primal_step(self, keep_d=False):
+        self._call(self.lib.cpppd_primal_step, int(bool(keep_d)))
+
+    def stats_step(self, force_integer=False):
+        self._call(self.lib.cpppd_stats_step, int(bool(force_integer)))
+
+    def dual_step(self):
+        self._call(self.lib.cpppd_dual_step)
+
+    def sync(self):
+        self._call(self.lib.cpppd_sync)
+
+    def read_stats(self):
+        s = _cabi.Stats()
+        self._call(self.lib.cpppd_read_stats, C.byref(s))
+        return s.as_dict()
+
+    def read_stats_or_none(self):
+        """Stats of the last stats step, or None when none was issued yet."""
+        try:
+            return self.read_stats()
+        except _cabi.CpppdError as e:
+            if e.code == -6:
+                return None
+            raise
+
+    def time_iterations(self, k):
+        ms = C.c_float()
+        self._call(self.lib.cpppd_time_iterations, int(k), C.byref(ms))
+        return ms.value
+
+    # -- state ------------------------------------------------------------------------------
+    def _get(self, which, size):
+        out = np.empty(size, dtype=np.float64)
+        self._call(self.lib.cpppd_get_vector, which, out.ctypes.data)
+        return out
+
+    def _set(self, which, v, size):
+        v = _as_f64(v, size, "vector")
+        self._call(self.lib.cpppd_set_vector, which, v.ctypes.data)
+
+    def get_x(self):
+        return self._get(_cabi.VEC_X, self.n)
+
+    def get_xbar(self):
+        return self._get(_cabi.VEC_XBAR, self.n)
+
+    def get_y(self):
+        return self._get(_cabi.VEC_Y, self.m)
+
+    def get_d(self):
+        return self._get(_cabi.VEC_D, self.n)
+
+    def get_preconditioners(self):
+        return self._get(_cabi.VEC_T, self.n), self._get(_cabi.VEC_SIGMA, self.m)
+
+    def get_best_integer(self):
+        return self._get(_cabi.VEC_BEST_INTEGER, self.n)
+
+    def set_x(self, v):
+        self._set(_cabi.VEC_X, v, self.n)
+
+    def set_xbar(self, v):
+        self._set(_cabi.VEC_XBAR, v, self.n)
+
+    def set_y(self, v):
+        self._set(_cabi.VEC_Y, v, self.m)
+
+    def info(self):
+        i = _cabi.Info()
+        self._call(self.lib.cpppd_get_info, C.byref(i))
+        return i.as_dict()
+
+    @property
+    def niter(self):
+        return int(self.lib.cpppd_iteration_count(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cpppd_destroy(self.handle)
+            self.handle = None
+            self._buffers.live.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def stack_operator(a_eq, beq, a_ineq, b_ineq, n):
+    """[A_eq; A_ineq] as one CSR (entry order inside rows untouched) and [b_eq; b_ineq]."""
+    has_eq = a_eq is not None and a_eq.shape[0] > 0
+    has_ineq = a_ineq is not None and a_ineq.shape[0] > 0
+    for a in (a_eq, a_ineq):
+        if a is not None:
+            if not sp.issparse(a):
+                raise ValueError("constraint matrices must be scipy sparse matrices")
+            if a.shape[1] != n:
+                raise ValueError("constraint matrix has %d columns, expected %d" % (a.shape[1], n))
+    if has_eq and has_ineq:
+        a_eq, a_ineq = sp.csr_matrix(a_eq), sp.csr_matrix(a_ineq)
+        wide = np.int64 if (a_eq.nnz + a_ineq.nnz) >= 2**31 - 1 else np.int32
+        indptr = np.concatenate((a_eq.indptr.astype(wide), a_ineq.indptr[1:].astype(wide) + wide(a_eq.nnz)))
+        a = sp.csr_matrix((np.concatenate((a_eq.data, a_ineq.data)).astype(np.float64, copy=False),
+                           np.concatenate((a_eq.indices, a_ineq.indices)), indptr),
+                          shape=(a_eq.shape[0] + a_ineq.shape[0], n))
+        return a, np.concatenate((np.ravel(beq), np.ravel(b_ineq))).astype(np.float64), a_eq.shape[0]
+    if has_eq:
+        return sp.csr_matrix(a_eq), np.asarray(beq, dtype=np.float64), a_eq.shape[0]
+    if has_ineq:
+        return sp.csr_matrix(a_ineq), np.asarray(b_ineq, dtype=np.float64), 0
+    return None, None, 0
+
+
+def chambolle_pock_ppd(
+    c,
+    a_eq,
+    beq,
+    a_ineq,
+    b_lower,
+    b_upper,
+    lb,
+    ub,
+    x0=None,
+    alpha=1,
+    theta=1,
+    nb_max_iter=100,
+    callback_func=None,
+    max_time=None,
+    save_problem=False,
+    force_integer=False,
+    nb_iter_plot=10,
+    *,
+    device=None,
+    verbose=False,
+    flags=0,
+    return_solver=False,
+):
+    """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
+
+    Semantics kept from the reference (file:line in ``pysparselp/ChambollePockPPD.py``):
+
+    * the stats block runs when ``niter % nb_iter_plot == 0`` — including iteration 0 and
+      when ``callback_func`` is None (``:242``); it sees the x / xbar of this iteration and
+      the y of the previous one;
+    * ``max_time`` is only tested there, after the primal half of the iteration and before
+      the stats, the callback and the dual half (``:243-247``) — on time-out the returned x
+      already contains that primal step and the callback of that iteration is not made;
+    * ``callback_func(niter, x, energy1, energy2, elapsed, max_violated_equality,
+      max_violated_inequality)`` (``:319-329``) receives a fresh host array;
+      ``max_violated_inequality`` is evaluated at x (``:283``), ``max_violated_equality`` at
+      the extrapolated point (``:269``);
+    * returns ``(x, best_integer_solution)`` (``:344-346``); with neither equality nor
+      inequality rows the reference returns the bare closed-form x (``:147-151``), so does this.
+    """
+    start = time.perf_counter()
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    n = c.size
+    lb = _as_f64(lb, n, "lb")  # the reference asserts these sizes (:95-96)
+    ub = _as_f64(ub, n, "ub")
+    if a_eq is not None and a_eq.shape[0] == 0:  # :70-72
+        a_eq, beq = None, None
+    a_ineq, b_ineq = one_sided_rows(a_ineq, b_lower, b_upper)
+    if a_eq is not None and a_eq.shape[0] != np.size(beq):
+        raise ValueError("a_eq has %d rows but beq has %d entries" % (a_eq.shape[0], np.size(beq)))
+    if a_ineq is not None and a_ineq.shape[0] != np.size(b_ineq):
+        raise ValueError("a_ineq has %d rows but its bounds have %d entries" % (a_ineq.shape[0], np.size(b_ineq)))
+    if save_problem:  # :99-112
+        import pickle
+
+        with open("LP_problem2.pkl", "wb") as f:
+            pickle.dump({"c": c, "a_eq": a_eq, "beq": beq, "a_ineq": a_ineq, "b_ineq": b_ineq,
+                         "lb": lb, "ub": ub}, f)
+    if a_eq is None and a_ineq is None:  # :147-151
+        x = np.zeros_like(lb)
+        x[c > 0] = lb[c > 0]
+        x[c < 0] = ub[c < 0]
+        return x
+    a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, n)
+    if a is None:  # only empty blocks were given
+        x = np.zeros_like(lb)
+        x[c > 0] = lb[c > 0]
+        x[c < 0] = ub[c < 0]
+        return x
+
+    solver = CpPpdSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, device=device, flags=flags)
+    try:
+        nb_iter_plot = int(nb_iter_plot)
+        if nb_iter_plot < 1:
+            raise ValueError("nb_iter_plot must be >= 1")
+        niter = 0
+        while niter < nb_max_iter:
+            # iteration `niter` is a stats iteration (niter % nb_iter_plot == 0 by construction)
+            solver.primal_step(keep_d=True)
+            if max_time is not None:
+                solver.sync()
+            elapsed = time.perf_counter() - start
+            if max_time is not None and elapsed > max_time:
+                break
+            solver.stats_step(force_integer)
+            st = solver.read_stats()
+            if verbose:
+                print("iter%d: energy1= %r energy2=%r elapsed %r second max violated inequality:%r "
+                      "max violated equality:%r x3 has %r %% of zeros" % (
+                          niter, st["energy1"], st["energy2"], elapsed, st["max_violated_inequality"],
+                          st["max_violated_equality"], 100 * st["frac_zero_xbar"]))
+            if callback_func is not None:
+                callback_func(niter, solver.get_x(), st["energy1"], st["energy2"], elapsed,
+                              st["max_violated_equality"], st["max_violated_inequality"])
+            solver.dual_step()
+            niter += 1
+            k = min(nb_iter_plot - 1, nb_max_iter - niter)
+            if k > 0:
+                solver.iterate(k)
+                niter += k
+        x = solver.get_x()
+        last = solver.read_stats_or_none()
+        best = solver.get_best_integer() if last is not None and last["have_best_integer"] else None
+    except BaseException:
+        solver.close()
+        raise
+    if return_solver:
+        return x[:n], best, solver
+    solver.close()
+    return x[:n], best
+

@@ -1,0 +1,120 @@
+"""ctypes binding of ``libcpppd.so`` (C ABI declared in ``include/cpppd.h``).
+
+The library is built in-tree by ``pysparselp_b200/build.py`` (``nvcc`` for sm_100a) and
+is the ONLY compute path: if it is missing or no CUDA device is present, loading /
+``cpppd_create`` fails loudly — there is no CPU fallback in the product.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
+
+ABI_VERSION = 1
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
+FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+
+FLAG_VALUE_DICT = 1 << 0
+FLAG_CONST_VECTORS = 1 << 1
+FLAG_NO_GRAPH = 1 << 2
+
+VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
+
+
+class Problem(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32),
+        ("n", C.c_int64), ("m_eq", C.c_int64), ("m_ineq", C.c_int64), ("nnz", C.c_int64),
+        ("indptr", C.c_void_p), ("indices", C.c_void_p), ("values", C.c_void_p),
+        ("indptr_bits", C.c_int32), ("index_bits", C.c_int32),
+        ("c", C.c_void_p), ("b", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p), ("x0", C.c_void_p),
+        ("alpha", C.c_double), ("theta", C.c_double), ("one_plus_theta", C.c_double),
+        ("stream", C.c_void_p), ("flags", C.c_uint32), ("sort_window", C.c_int32),
+        ("alloc", ALLOC_FN), ("free", FREE_FN), ("alloc_user", C.c_void_p),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("niter", C.c_int64), ("energy1", C.c_double), ("energy2", C.c_double),
+        ("max_violated_equality", C.c_double), ("max_violated_inequality", C.c_double),
+        ("energy_rounded", C.c_double), ("max_violated_equality_rounded", C.c_double),
+        ("best_integer_energy", C.c_double), ("frac_zero_xbar", C.c_double),
+        ("feasible", C.c_int32), ("improved", C.c_int32), ("have_best_integer", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("m_eq", C.c_int64), ("m_ineq", C.c_int64), ("nnz", C.c_int64),
+        ("a_padded_entries", C.c_int64), ("at_padded_entries", C.c_int64), ("device_bytes", C.c_int64),
+        ("bytes_per_iteration_algorithmic", C.c_int64), ("bytes_per_iteration_actual", C.c_int64),
+        ("value_bytes", C.c_int32), ("const_vector_mask", C.c_int32), ("sm_count", C.c_int32),
+        ("world_size", C.c_int32), ("row_begin", C.c_int64), ("row_end", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/cpppd.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "cpppd_abi_version": (C.c_int, []),
+    "cpppd_create": (C.c_int, [C.POINTER(Problem), C.POINTER(C.c_void_p)]),
+    "cpppd_destroy": (C.c_int, [C.c_void_p]),
+    "cpppd_last_error": (C.c_char_p, [C.c_void_p]),
+    "cpppd_iterate": (C.c_int, [C.c_void_p, C.c_int64]),
+    "cpppd_primal_step": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cpppd_stats_step": (C.c_int, [C.c_void_p, C.c_int32]),
+    "cpppd_dual_step": (C.c_int, [C.c_void_p]),
+    "cpppd_sync": (C.c_int, [C.c_void_p]),
+    "cpppd_read_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "cpppd_time_iterations": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float)]),
+    "cpppd_get_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "cpppd_set_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "cpppd_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "cpppd_iteration_count": (C.c_int64, [C.c_void_p]),
+}
+
+_lib = None
+
+
+class CpppdError(RuntimeError):
+    """A libcpppd entry point returned a negative status."""
+
+    def __init__(self, code, message):
+        super().__init__("libcpppd error %d: %s" % (code, message))
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen the in-tree library and type every symbol; raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
+        raise RuntimeError(
+            "%s is not built — run `python -m pysparselp_b200.build` (needs nvcc). "
+            "This package has no CPU fallback." % path)
+    lib = C.CDLL(path)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.cpppd_abi_version() != ABI_VERSION:
+        raise RuntimeError("libcpppd ABI %d != binding ABI %d: rebuild" % (lib.cpppd_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(lib, handle, code):
+    if code < 0:
+        msg = lib.cpppd_last_error(handle)
+        raise CpppdError(code, msg.decode("utf-8", "replace") if msg else "")
+    return code

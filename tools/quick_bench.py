@@ -1,0 +1,35 @@
+"""Scratch timing of the inner loop on one GPU (not the bench contract; see bench.py)."""
+import argparse, json, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from pysparselp_b200 import generators
+from pysparselp_b200.ChambollePockPPD import CpPpdSolver, stack_operator, one_sided_rows
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, default=1024)
+ap.add_argument("--kind", default="potts")
+ap.add_argument("--iters", type=int, default=50)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--flags", type=int, default=0)
+a = ap.parse_args()
+t0 = time.time()
+if a.kind == "potts":
+    lp = generators.potts_lp(a.size)
+elif a.kind == "random":
+    lp, _ = generators.random_sparse_lp(a.size, 2 * a.size, nnz_per_row=8)
+t1 = time.time()
+a_in, b_in = one_sided_rows(lp.a_ineq, lp.b_lower, lp.b_upper)
+A, b, m_eq = stack_operator(lp.a_eq, lp.b_eq, a_in, b_in, lp.c.size)
+s = CpPpdSolver(lp.c, A, m_eq, b, lp.lb, lp.ub, flags=a.flags)
+t2 = time.time()
+info = s.info()
+s.iterate(20); s.sync()
+times = [s.time_iterations(a.iters) / a.iters for _ in range(a.reps)]
+ms = float(np.median(times))
+out = dict(kind=a.kind, size=a.size, n=info["n"], m=info["m_eq"] + info["m_ineq"], nnz=info["nnz"],
+           build_s=round(t1 - t0, 2), setup_s=round(t2 - t1, 2), ms_per_iter=ms, it_per_s=1e3 / ms,
+           algo_GBs=info["bytes_per_iteration_algorithmic"] / ms / 1e6,
+           actual_GBs=info["bytes_per_iteration_actual"] / ms / 1e6, times=times,
+           pad_A=info["a_padded_entries"] / max(info["nnz"], 1), pad_AT=info["at_padded_entries"] / max(info["nnz"], 1),
+           device_GB=info["device_bytes"] / 1e9)
+print(json.dumps(out))
