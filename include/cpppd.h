@@ -169,6 +169,9 @@ int cpppd_read_stats(cpppd_handle h, cpppd_stats *out);
 /* Run k iterations bracketed by CUDA events on the solver's stream; returns the
  * elapsed device time in milliseconds.  Synchronises. */
 int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms);
+/* Run k (<= 64) iterations with a CUDA event between every kernel; returns the summed
+ * device time of the primal kernels and of the dual kernels (ms).  Synchronises. */
+int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_ms);
 
 /* -- state access (synchronising copies to/from HOST memory) ------------------------- */
 int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst);

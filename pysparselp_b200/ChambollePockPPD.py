@@ -176,6 +176,12 @@ class CpPpdSolver:
         self._call(self.lib.cpppd_time_iterations, int(k), C.byref(ms))
         return ms.value
 
+    def time_kernels(self, k):
+        """(primal_ms, dual_ms) summed over k iterations, one CUDA event between every kernel."""
+        a, b = C.c_float(), C.c_float()
+        self._call(self.lib.cpppd_time_kernels, int(k), C.byref(a), C.byref(b))
+        return a.value, b.value
+
     # -- state ------------------------------------------------------------------------------
     def _get(self, which, size):
         out = np.empty(size, dtype=np.float64)
@@ -266,6 +272,25 @@ def stack_operator(a_eq, beq, a_ineq, b_ineq, n):
     return None, None, 0
 
 
+def make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0):
+    """Upload an LP given with the arguments of ``chambolle_pock_ppd`` and return the live solver.
+
+    Returns None when the LP has no constraint row at all (closed-form case, ``:147-151``).
+    """
+    n = np.size(c)
+    if a_eq is not None and a_eq.shape[0] == 0:  # :70-72
+        a_eq, beq = None, None
+    a_ineq, b_ineq = one_sided_rows(a_ineq, b_lower, b_upper)
+    if a_eq is not None and a_eq.shape[0] != np.size(beq):
+        raise ValueError("a_eq has %d rows but beq has %d entries" % (a_eq.shape[0], np.size(beq)))
+    if a_ineq is not None and a_ineq.shape[0] != np.size(b_ineq):
+        raise ValueError("a_ineq has %d rows but its bounds have %d entries" % (a_ineq.shape[0], np.size(b_ineq)))
+    a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, n)
+    if a is None:
+        return None
+    return CpPpdSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, device=device, flags=flags)
+
+
 def chambolle_pock_ppd(
     c,
     a_eq,
@@ -312,32 +337,20 @@ def chambolle_pock_ppd(
     n = c.size
     lb = _as_f64(lb, n, "lb")  # the reference asserts these sizes (:95-96)
     ub = _as_f64(ub, n, "ub")
-    if a_eq is not None and a_eq.shape[0] == 0:  # :70-72
-        a_eq, beq = None, None
-    a_ineq, b_ineq = one_sided_rows(a_ineq, b_lower, b_upper)
-    if a_eq is not None and a_eq.shape[0] != np.size(beq):
-        raise ValueError("a_eq has %d rows but beq has %d entries" % (a_eq.shape[0], np.size(beq)))
-    if a_ineq is not None and a_ineq.shape[0] != np.size(b_ineq):
-        raise ValueError("a_ineq has %d rows but its bounds have %d entries" % (a_ineq.shape[0], np.size(b_ineq)))
     if save_problem:  # :99-112
         import pickle
 
+        a_in_1s, b_in_1s = one_sided_rows(a_ineq, b_lower, b_upper)
         with open("LP_problem2.pkl", "wb") as f:
-            pickle.dump({"c": c, "a_eq": a_eq, "beq": beq, "a_ineq": a_ineq, "b_ineq": b_ineq,
+            pickle.dump({"c": c, "a_eq": a_eq, "beq": beq, "a_ineq": a_in_1s, "b_ineq": b_in_1s,
                          "lb": lb, "ub": ub}, f)
-    if a_eq is None and a_ineq is None:  # :147-151
+    solver = make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
+                         device=device, flags=flags)
+    if solver is None:  # no constraint row: closed form, bare vector (:147-151)
         x = np.zeros_like(lb)
         x[c > 0] = lb[c > 0]
         x[c < 0] = ub[c < 0]
         return x
-    a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, n)
-    if a is None:  # only empty blocks were given
-        x = np.zeros_like(lb)
-        x[c > 0] = lb[c > 0]
-        x[c < 0] = ub[c < 0]
-        return x
-
-    solver = CpPpdSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, device=device, flags=flags)
     try:
         nb_iter_plot = int(nb_iter_plot)
         if nb_iter_plot < 1:

@@ -75,6 +75,7 @@ SYMBOLS = {
     "cpppd_sync": (C.c_int, [C.c_void_p]),
     "cpppd_read_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "cpppd_time_iterations": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float)]),
+    "cpppd_time_kernels": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "cpppd_get_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_set_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),

@@ -950,6 +950,33 @@ int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms) {
   return 0;
 }
 
+int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_ms) {
+  CHECK_HANDLE(h);
+  if (!primal_ms || !dual_ms || k < 0 || k > 64) return fail(h, CPPPD_ERR_INVALID, "bad argument (k must be in [0, 64])");
+  if (h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "cpppd_dual_step must close the open iteration first");
+  std::vector<cudaEvent_t> ev(2 * k + 1);
+  for (auto &e : ev) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev[0], h->stream));
+  for (int64_t i = 0; i < k; ++i) {
+    launch_primal(h, false);
+    CK(cudaEventRecord(ev[2 * i + 1], h->stream));
+    launch_dual(h);
+    CK(cudaEventRecord(ev[2 * i + 2], h->stream));
+  }
+  h->niter += k;
+  CK(cudaEventSynchronize(ev[2 * k]));
+  *primal_ms = *dual_ms = 0.f;
+  for (int64_t i = 0; i < k; ++i) {
+    float a = 0.f, b = 0.f;
+    CK(cudaEventElapsedTime(&a, ev[2 * i], ev[2 * i + 1]));
+    CK(cudaEventElapsedTime(&b, ev[2 * i + 1], ev[2 * i + 2]));
+    *primal_ms += a;
+    *dual_ms += b;
+  }
+  for (auto &e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
 static int vector_ptr(cpppd_solver *h, int32_t which, double **p, int64_t *count) {
   switch (which) {
     case CPPPD_VEC_X: *p = h->x; *count = h->n; return 0;

@@ -75,3 +75,20 @@ def test_oracle_reproduces_reference_potts_curve():
     curve = _curve_through_solve_semantics(args, gt, idx, 5001, 500)
     np.testing.assert_almost_equal(curve, ref[: len(curve)])
     assert np.max(np.abs(np.array(curve) - np.array(ref[: len(curve)]))) == 0.0
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_c_port_bit_exact_vs_reference_golden(name):
+    """oracle/cpppd_oracle.c (multi-threaded CPU baseline) against the reference-minted goldens."""
+    from oracle.c_port import COracle
+
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    o = COracle(*args, **kw)
+    o.iterate(100)
+    y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+    if "alpha" in kw:  # pow() of libm vs numpy may differ in the last place
+        assert np.allclose(o.x, g["x_100"], rtol=1e-12, atol=0) and np.allclose(o.y, y_gold, rtol=1e-12, atol=1e-300)
+    else:
+        assert np.array_equal(o.x, g["x_100"]) and np.array_equal(o.y, y_gold)
+        assert np.array_equal(o.T, g["diag_t"])
