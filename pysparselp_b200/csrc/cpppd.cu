@@ -48,6 +48,7 @@ thread_local std::string g_create_error;
 
 struct Sell {
   int64_t nrows = 0, nslices = 0, padded = 0;
+  int64_t uniform_width = -1;    // >= 0 when every slice has this width (slice_ptr is then implicit)
   int64_t *slice_ptr = nullptr;  // nslices+1 element offsets
   int32_t *idx = nullptr;        // padded entries, -1 = padding
   double *val = nullptr;
@@ -58,7 +59,19 @@ struct SellView {
   const int32_t *__restrict__ idx;
   const double *__restrict__ val;
   int64_t nrows, nslices;
+  int64_t uniform_width;  // -1: read slice_ptr
 };
+
+// first / one-past-last element offset of slice s
+__device__ __forceinline__ void slice_range(const SellView &S, int64_t s, int64_t &p0, int64_t &p1) {
+  if (S.uniform_width >= 0) {
+    p0 = s * S.uniform_width * 32;
+    p1 = p0 + S.uniform_width * 32;
+  } else {
+    p0 = __ldg(S.slice_ptr + s);
+    p1 = __ldg(S.slice_ptr + s + 1);
+  }
+}
 
 struct StatsDev {  // device-resident, copied verbatim into cpppd_stats
   cpppd_stats s;
@@ -319,9 +332,10 @@ __global__ void k_precond_cols(SellView AT, int64_t n, int64_t m_eq, int has_eq,
   int64_t s = j >> 5;
   if (s >= AT.nslices) return;
   int lane = threadIdx.x & 31;
-  int64_t p1 = AT.slice_ptr[s + 1];
+  int64_t p0, p1;
+  slice_range(AT, s, p0, p1);
   double s_eq = 0.0, s_in = 0.0;
-  for (int64_t p = AT.slice_ptr[s] + lane; p < p1; p += kSlice) {
+  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
     int32_t r = AT.idx[p];
     if (r >= 0) {
       double t = __dmul_rn(abs_pow(AT.val[p], power), 1.0);
@@ -343,9 +357,10 @@ __global__ void k_precond_rows(SellView A, int64_t m, double power, double *__re
   int64_t s = i >> 5;
   if (s >= A.nslices) return;
   int lane = threadIdx.x & 31;
-  int64_t p1 = A.slice_ptr[s + 1];
+  int64_t p0, p1;
+  slice_range(A, s, p0, p1);
   double acc = 0.0;
-  for (int64_t p = A.slice_ptr[s] + lane; p < p1; p += kSlice) {
+  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
     if (A.idx[p] >= 0) acc = __dadd_rn(acc, __dmul_rn(abs_pow(A.val[p], power), 1.0));
   }
   if (i < m) {
@@ -358,6 +373,8 @@ __global__ void k_precond_rows(SellView A, int64_t m, double power, double *__re
 // the two hot kernels
 // ------------------------------------------------------------------------------------------
 // Primal half-iteration (:198-228).  Thread j owns column j of A (row j of A^T).
+// Loads that do not depend on the matrix (c, T, x, lb, ub) are issued first so that they are
+// in flight together with the slice entries; matrix entries are read once (ld.global.cs).
 template <bool kWriteD>
 __global__ void __launch_bounds__(kBlock)
 k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c, const double *__restrict__ T,
@@ -368,24 +385,32 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
   const int64_t s = j >> 5;
   if (s >= AT.nslices) return;
   const int lane = threadIdx.x & 31;
-  const int64_t p1 = AT.slice_ptr[s + 1];
+  int64_t p0, p1;
+  slice_range(AT, s, p0, p1);
+  const bool live = j < n;
+  double cj = 0.0, tj = 0.0, xo = 0.0, l = 0.0, u = 0.0;
+  if (live) {
+    cj = __ldcs(c + j);
+    tj = __ldcs(T + j);
+    xo = __ldcs(x + j);
+    l = __ldcs(lb + j);
+    u = __ldcs(ub + j);
+  }
   double s_eq = 0.0, s_in = 0.0;
 #pragma unroll 4
-  for (int64_t p = AT.slice_ptr[s] + lane; p < p1; p += kSlice) {
-    const int32_t r = __ldg(AT.idx + p);
-    const double a = __ldg(AT.val + p);
+  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
+    const int32_t r = __ldcs(AT.idx + p);
+    const double a = __ldcs(AT.val + p);
     if (r >= 0) {
       const double t = __dmul_rn(a, __ldg(y + r));
       if (r < m_eq) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
     }
   }
-  if (j >= n) return;
-  double d = c[j];
+  if (!live) return;
+  double d = cj;
   if (has_eq) d = __dadd_rn(d, s_eq);
   if (has_ineq) d = __dadd_rn(d, s_in);
-  const double xo = x[j];
-  double x2 = __dsub_rn(xo, __dmul_rn(T[j], d));
-  const double l = lb[j], u = ub[j];
+  double x2 = __dsub_rn(xo, __dmul_rn(tj, d));
   x2 = (l > x2) ? l : x2;  // np.maximum(x2, lb)  (NaN in x2 propagates)
   x2 = (u < x2) ? u : x2;  // np.minimum(x2, ub)
   xbar[j] = __dsub_rn(__dmul_rn(one_plus_theta, x2), __dmul_rn(theta, xo));
@@ -401,17 +426,25 @@ k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b
   const int64_t s = i >> 5;
   if (s >= A.nslices) return;
   const int lane = threadIdx.x & 31;
-  const int64_t p1 = A.slice_ptr[s + 1];
+  int64_t p0, p1;
+  slice_range(A, s, p0, p1);
+  const bool live = i < m;
+  double bi = 0.0, si = 0.0, yi = 0.0;
+  if (live) {
+    bi = __ldcs(b + i);
+    si = __ldcs(sigma + i);
+    yi = __ldcs(y + i);
+  }
   double acc = 0.0;
 #pragma unroll 4
-  for (int64_t p = A.slice_ptr[s] + lane; p < p1; p += kSlice) {
-    const int32_t jc = __ldg(A.idx + p);
-    const double a = __ldg(A.val + p);
+  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
+    const int32_t jc = __ldcs(A.idx + p);
+    const double a = __ldcs(A.val + p);
     if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + jc)));
   }
-  if (i >= m) return;
-  const double r = __dsub_rn(acc, b[i]);
-  double yn = __dadd_rn(y[i], __dmul_rn(sigma[i], r));
+  if (!live) return;
+  const double r = __dsub_rn(acc, bi);
+  double yn = __dadd_rn(yi, __dmul_rn(si, r));
   if (i >= m_eq) yn = (yn < 0.0) ? 0.0 : yn;  // np.maximum(y_ineq, 0): NaN stays NaN, -0.0 stays
   y[i] = yn;
 }
@@ -455,9 +488,10 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
   for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; (i >> 5) < A.nslices;
        i += (int64_t)gridDim.x * kBlock) {
     const int64_t s = i >> 5;
-    const int64_t p1 = A.slice_ptr[s + 1];
+    int64_t p0, p1;
+    slice_range(A, s, p0, p1);
     double ax = 0.0, ax4 = 0.0, axb = 0.0, axr = 0.0;
-    for (int64_t p = A.slice_ptr[s] + lane; p < p1; p += kSlice) {
+    for (int64_t p = p0 + lane; p < p1; p += kSlice) {
       const int32_t jc = A.idx[p];
       if (jc >= 0) {
         const double a = A.val[p];
@@ -552,7 +586,7 @@ __global__ void k_init_stats(StatsDev *st) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-SellView view(const Sell &s) { return SellView{s.slice_ptr, s.idx, s.val, s.nrows, s.nslices}; }
+SellView view(const Sell &s) { return SellView{s.slice_ptr, s.idx, s.val, s.nrows, s.nslices, s.uniform_width}; }
 
 // CSR (device, int64 rowptr) -> SELL-32 (device)
 int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, const double *values, int64_t nrows,
@@ -571,6 +605,25 @@ int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "scan workspace allocation failed");
   CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, extent, out->slice_ptr, ns + 1, h->stream));
   CK(cudaMemcpyAsync(&out->padded, out->slice_ptr + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  {  // uniform slice width <=> min extent == max extent
+    int64_t *mm = nullptr;
+    if (int rc = alloc_array(h, &mm, 2, false)) return rc;
+    size_t b1 = 0, b2 = 0;
+    CK(cub::DeviceReduce::Min(nullptr, b1, extent, mm, ns, h->stream));
+    CK(cub::DeviceReduce::Max(nullptr, b2, extent, mm + 1, ns, h->stream));
+    void *t2 = dev_alloc(h, std::max(b1, b2), false);
+    if (!t2) return fail(h, CPPPD_ERR_NOMEM, "reduce workspace allocation failed");
+    int64_t host_mm[2] = {0, 1};
+    if (ns) {
+      CK(cub::DeviceReduce::Min(t2, b1, extent, mm, ns, h->stream));
+      CK(cub::DeviceReduce::Max(t2, b2, extent, mm + 1, ns, h->stream));
+      CK(cudaMemcpyAsync(host_mm, mm, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    out->uniform_width = (ns && host_mm[0] == host_mm[1]) ? host_mm[0] / kSlice : -1;
+    dev_free(h, t2);
+    dev_free(h, mm);
+  }
   CK(cudaStreamSynchronize(h->stream));
   dev_free(h, tmp);
   dev_free(h, extent);
