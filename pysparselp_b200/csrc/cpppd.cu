@@ -376,7 +376,7 @@ __global__ void k_precond_rows(SellView A, int64_t m, double power, double *__re
 // Loads that do not depend on the matrix (c, T, x, lb, ub) are issued first so that they are
 // in flight together with the slice entries; matrix entries are read once (ld.global.cs).
 template <bool kWriteD>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 8)
 k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c, const double *__restrict__ T,
          const double *__restrict__ lb, const double *__restrict__ ub, double *__restrict__ x,
          double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int64_t m_eq, int has_eq, int has_ineq,
@@ -388,28 +388,33 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
   int64_t p0, p1;
   slice_range(AT, s, p0, p1);
   const bool live = j < n;
-  double cj = 0.0, tj = 0.0, xo = 0.0, l = 0.0, u = 0.0;
+  double cj = 0.0, tj = 0.0, xo = 0.0;
   if (live) {
     cj = __ldcs(c + j);
     tj = __ldcs(T + j);
     xo = __ldcs(x + j);
-    l = __ldcs(lb + j);
-    u = __ldcs(ub + j);
   }
   double s_eq = 0.0, s_in = 0.0;
+  {
+    const int32_t *ip = AT.idx + p0 + lane;
+    const double *vp = AT.val + p0 + lane;
+    const int width = (int)((p1 - p0) >> 5);
+    const int32_t meq = (int32_t)m_eq;
 #pragma unroll 4
-  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
-    const int32_t r = __ldcs(AT.idx + p);
-    const double a = __ldcs(AT.val + p);
-    if (r >= 0) {
-      const double t = __dmul_rn(a, __ldg(y + r));
-      if (r < m_eq) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+    for (int k = 0; k < width; ++k) {
+      const int32_t r = __ldcs(ip + k * kSlice);
+      const double a = __ldcs(vp + k * kSlice);
+      if (r >= 0) {
+        const double t = __dmul_rn(a, __ldg(y + r));
+        if (r < meq) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+      }
     }
   }
   if (!live) return;
   double d = cj;
   if (has_eq) d = __dadd_rn(d, s_eq);
   if (has_ineq) d = __dadd_rn(d, s_in);
+  const double l = __ldcs(lb + j), u = __ldcs(ub + j);
   double x2 = __dsub_rn(xo, __dmul_rn(tj, d));
   x2 = (l > x2) ? l : x2;  // np.maximum(x2, lb)  (NaN in x2 propagates)
   x2 = (u < x2) ? u : x2;  // np.minimum(x2, ub)
@@ -419,7 +424,7 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
 }
 
 // Dual half-iteration (:231-240, :333-341).  Thread i owns row i of A.
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 8)
 k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b,
        const double *__restrict__ sigma, double *__restrict__ y, int64_t m, int64_t m_eq) {
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
@@ -436,11 +441,16 @@ k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b
     yi = __ldcs(y + i);
   }
   double acc = 0.0;
+  {
+    const int32_t *ip = A.idx + p0 + lane;
+    const double *vp = A.val + p0 + lane;
+    const int width = (int)((p1 - p0) >> 5);
 #pragma unroll 4
-  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
-    const int32_t jc = __ldcs(A.idx + p);
-    const double a = __ldcs(A.val + p);
-    if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + jc)));
+    for (int k = 0; k < width; ++k) {
+      const int32_t jc = __ldcs(ip + k * kSlice);
+      const double a = __ldcs(vp + k * kSlice);
+      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + jc)));
+    }
   }
   if (!live) return;
   const double r = __dsub_rn(acc, bi);
