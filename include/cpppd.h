@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CPPPD_ABI_VERSION 1
+#define CPPPD_ABI_VERSION 2
 
 typedef struct cpppd_solver *cpppd_handle;
 
@@ -65,7 +65,11 @@ enum {
   /* replace constant vectors (b, sigma, lb, ub) by scalars inside the kernels */
   CPPPD_FLAG_CONST_VECTORS = 1u << 1,
   /* do not capture the inner iterations into CUDA graphs */
-  CPPPD_FLAG_NO_GRAPH = 1u << 2
+  CPPPD_FLAG_NO_GRAPH = 1u << 2,
+  /* on one GPU: still renumber rows / columns by locality (always done when world_size > 1) */
+  CPPPD_FLAG_REORDER = 1u << 3,
+  /* world_size > 1: capture the iterations including the NCCL halo exchanges into CUDA graphs */
+  CPPPD_FLAG_GRAPH_COMM = 1u << 4
 };
 
 typedef struct {
@@ -95,6 +99,13 @@ typedef struct {
   cpppd_alloc_fn alloc; /* may be NULL */
   cpppd_free_fn free;   /* may be NULL */
   void *alloc_user;
+  /* multi-GPU (one process per GPU).  Every rank passes the SAME full LP; the library keeps
+   * only its share on the device.  comm_id: the 128 bytes produced by cpppd_comm_unique_id()
+   * on one rank and broadcast by the host program (torch.distributed in the Python front). */
+  int32_t rank;         /* 0 .. world_size-1 */
+  int32_t world_size;   /* <= 1: single GPU */
+  const void *comm_id;  /* 128 bytes, required when world_size > 1 */
+  int64_t partition_granule; /* locality bucket width in columns; <= 0: default */
 } cpppd_problem;
 
 /* The numbers the reference's stats block produces (ChambollePockPPD.py:242-291). */
@@ -125,7 +136,13 @@ typedef struct {
   int32_t const_vector_mask; /* bit0 b, bit1 sigma, bit2 lb, bit3 ub folded to scalars         */
   int32_t sm_count;
   int32_t world_size;
-  int64_t row_begin, row_end;/* rows of the stacked matrix owned by this rank                   */
+  int32_t rank;
+  int32_t reserved;
+  int64_t n_local, m_local, m_eq_local;  /* columns / rows / equality rows owned by this rank      */
+  int64_t n_ghost, m_ghost;              /* ghost columns (xbar) / ghost rows (y) kept by this rank */
+  int64_t nnz_local_rows, nnz_local_cols;/* entries of the owned rows of A / owned columns of A     */
+  int64_t halo_send_bytes_per_iteration; /* bytes this rank sends per iteration (xbar + y halos)    */
+  int64_t partition_granule;
 } cpppd_info;
 
 typedef enum {
@@ -147,6 +164,8 @@ int cpppd_destroy(cpppd_handle h);
  * on this thread when h is NULL). */
 const char *cpppd_last_error(cpppd_handle h);
 int cpppd_abi_version(void);
+/* 128-byte NCCL unique id for a new multi-GPU solve (call on one rank, broadcast, pass as comm_id). */
+int cpppd_comm_unique_id(void *out128);
 
 /* -- the iteration (ChambollePockPPD.py:195-343) ----------------------------------- */
 /* k full iterations: [x,xbar <- primal(y)] ; [y <- dual(xbar)], asynchronous. */
@@ -177,6 +196,11 @@ int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_
 int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst);
 int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src); /* X, XBAR, Y only */
 int cpppd_get_info(cpppd_handle h, cpppd_info *out);
+/* Partition of this rank: number of owned and ghost columns (columns != 0) or rows (columns == 0)
+ * and, when ids is not NULL, their original indices in local order (owned first, then ghosts in
+ * exchange order).  A pure function of (indptr, indices, m_eq, world_size, granule):
+ * oracle/partition_oracle.py restates it. */
+int cpppd_get_layout(cpppd_handle h, int32_t columns, int64_t *owned, int64_t *ghost, int32_t *ids);
 int64_t cpppd_iteration_count(cpppd_handle h);
 
 #ifdef __cplusplus

@@ -12,7 +12,9 @@ the current CUDA stream.  There is no CPU fallback.
 Extra keyword-only arguments (defaults keep the reference behaviour):
 ``device`` (CUDA ordinal or torch.device), ``verbose`` (print the reference's per-block
 line), ``flags`` (CPPPD_FLAG_* bit mask), ``return_solver`` (also return the live
-``CpPpdSolver`` for inspection).
+``CpPpdSolver`` for inspection), ``distributed`` (None: use the initialised torch.distributed
+world when it has more than one rank — one process per GPU, every rank passes the same LP and
+gets the same result; False: this GPU only; or an explicit ProcessGroup).
 """
 import ctypes as C
 import time
@@ -84,7 +86,7 @@ class CpPpdSolver:
     """Live solver state on one GPU (thin wrapper over a ``cpppd_handle``)."""
 
     def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
-                 sort_window=1):
+                 sort_window=1, process_group=None, partition_granule=0):
         import torch
 
         self.lib = _cabi.load_library()
@@ -96,6 +98,10 @@ class CpPpdSolver:
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
+        self.rank, self.world = 0, 1
+        comm_id = None
+        if process_group is not None:
+            comm_id = self._negotiate_comm_id(process_group, dev)
         a = sp.csr_matrix(a) if not sp.isspmatrix_csr(a) else a
         m, n = a.shape
         self.n, self.m, self.m_eq = n, m, int(m_eq)
@@ -111,7 +117,7 @@ class CpPpdSolver:
         indptr = np.ascontiguousarray(a.indptr)
         if indptr.dtype not in (np.int32, np.int64):
             indptr = indptr.astype(np.int64)
-        self._keep = (c, lb, ub, b, x0, data, indices, indptr)
+        self._keep = (c, lb, ub, b, x0, data, indices, indptr, comm_id)
         self._buffers = _TorchBuffers(dev)
         p = _cabi.Problem()
         p.abi_version = _cabi.ABI_VERSION
@@ -132,11 +138,51 @@ class CpPpdSolver:
         p.alloc = self._buffers.alloc_cb
         p.free = self._buffers.free_cb
         p.alloc_user = None
+        p.rank, p.world_size = self.rank, self.world
+        p.comm_id = None if comm_id is None else comm_id.ctypes.data
+        p.partition_granule = int(partition_granule)
         handle = C.c_void_p()
         with torch.cuda.device(dev):
             _cabi.check(self.lib, None, self.lib.cpppd_create(C.byref(p), C.byref(handle)))
         self.handle = handle
         self._keep = None  # host arrays are only read during create
+
+    def _negotiate_comm_id(self, group, dev):
+        """One NCCL communicator per solve: rank 0 draws the id, torch.distributed broadcasts it."""
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        if group is True:
+            group = dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world == 1:
+            return None
+        if "CPPPD_NCCL_LIB" not in os.environ:  # use the NCCL that torch itself loaded
+            try:
+                import nvidia.nccl
+
+                cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+                if os.path.isfile(cand):
+                    os.environ["CPPPD_NCCL_LIB"] = cand
+            except Exception:
+                pass
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            _cabi.check(self.lib, None, self.lib.cpppd_comm_unique_id(ident.ctypes.data))
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.from_numpy(ident).to(dev) if on_gpu else torch.from_numpy(ident)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
+        return t.cpu().numpy().copy()
+
+    def layout(self, columns=True):
+        """(owned original ids, ghost original ids) of this rank, local order."""
+        owned, ghost = C.c_int64(), C.c_int64()
+        self._call(self.lib.cpppd_get_layout, int(columns), C.byref(owned), C.byref(ghost), None)
+        ids = np.empty(owned.value + ghost.value, dtype=np.int32)
+        self._call(self.lib.cpppd_get_layout, int(columns), C.byref(owned), C.byref(ghost), ids.ctypes.data)
+        return ids[: owned.value], ids[owned.value:]
 
     # -- schedule ---------------------------------------------------------------------------
     def _call(self, fn, *args):
@@ -272,7 +318,8 @@ def stack_operator(a_eq, beq, a_ineq, b_ineq, n):
     return None, None, 0
 
 
-def make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0):
+def make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
+                distributed=None, partition_granule=0):
     """Upload an LP given with the arguments of ``chambolle_pock_ppd`` and return the live solver.
 
     Returns None when the LP has no constraint row at all (closed-form case, ``:147-151``).
@@ -288,7 +335,24 @@ def make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1
     a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, n)
     if a is None:
         return None
-    return CpPpdSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, device=device, flags=flags)
+    return CpPpdSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, device=device, flags=flags,
+                       process_group=_resolve_group(distributed), partition_granule=partition_granule)
+
+
+def _resolve_group(distributed):
+    """None -> the default torch.distributed group when one with more than one rank is initialised
+    (SPMD use: every rank calls the solver with the same LP); False -> single GPU; a ProcessGroup -> it."""
+    if distributed is False:
+        return None
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None
+    if distributed is None or distributed is True:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.group.WORLD
+        return None
+    return distributed
 
 
 def chambolle_pock_ppd(
@@ -314,6 +378,7 @@ def chambolle_pock_ppd(
     verbose=False,
     flags=0,
     return_solver=False,
+    distributed=None,
 ):
     """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
 
@@ -345,7 +410,7 @@ def chambolle_pock_ppd(
             pickle.dump({"c": c, "a_eq": a_eq, "beq": beq, "a_ineq": a_in_1s, "b_ineq": b_in_1s,
                          "lb": lb, "ub": ub}, f)
     solver = make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
-                         device=device, flags=flags)
+                         device=device, flags=flags, distributed=distributed)
     if solver is None:  # no constraint row: closed form, bare vector (:147-151)
         x = np.zeros_like(lb)
         x[c > 0] = lb[c > 0]

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
@@ -18,6 +18,8 @@ FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 FLAG_VALUE_DICT = 1 << 0
 FLAG_CONST_VECTORS = 1 << 1
 FLAG_NO_GRAPH = 1 << 2
+FLAG_REORDER = 1 << 3
+FLAG_GRAPH_COMM = 1 << 4
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 
@@ -32,6 +34,8 @@ class Problem(C.Structure):
         ("alpha", C.c_double), ("theta", C.c_double), ("one_plus_theta", C.c_double),
         ("stream", C.c_void_p), ("flags", C.c_uint32), ("sort_window", C.c_int32),
         ("alloc", ALLOC_FN), ("free", FREE_FN), ("alloc_user", C.c_void_p),
+        ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.c_void_p),
+        ("partition_granule", C.c_int64),
     ]
 
 
@@ -55,7 +59,11 @@ class Info(C.Structure):
         ("a_padded_entries", C.c_int64), ("at_padded_entries", C.c_int64), ("device_bytes", C.c_int64),
         ("bytes_per_iteration_algorithmic", C.c_int64), ("bytes_per_iteration_actual", C.c_int64),
         ("value_bytes", C.c_int32), ("const_vector_mask", C.c_int32), ("sm_count", C.c_int32),
-        ("world_size", C.c_int32), ("row_begin", C.c_int64), ("row_end", C.c_int64),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("reserved", C.c_int32),
+        ("n_local", C.c_int64), ("m_local", C.c_int64), ("m_eq_local", C.c_int64),
+        ("n_ghost", C.c_int64), ("m_ghost", C.c_int64),
+        ("nnz_local_rows", C.c_int64), ("nnz_local_cols", C.c_int64),
+        ("halo_send_bytes_per_iteration", C.c_int64), ("partition_granule", C.c_int64),
     ]
 
     def as_dict(self):
@@ -65,6 +73,7 @@ class Info(C.Structure):
 # every symbol include/cpppd.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "cpppd_abi_version": (C.c_int, []),
+    "cpppd_comm_unique_id": (C.c_int, [C.c_void_p]),
     "cpppd_create": (C.c_int, [C.POINTER(Problem), C.POINTER(C.c_void_p)]),
     "cpppd_destroy": (C.c_int, [C.c_void_p]),
     "cpppd_last_error": (C.c_char_p, [C.c_void_p]),
@@ -79,6 +88,7 @@ SYMBOLS = {
     "cpppd_get_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_set_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "cpppd_get_layout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "cpppd_iteration_count": (C.c_int64, [C.c_void_p]),
 }
 

@@ -14,16 +14,26 @@
 //   * k_precond_*      : column / row abs-power sums -> diag_t, diag_sigma (:122-179).
 //   * k_stats_*        : the stats block (:248-291) as warp-shuffle + block reductions with a
 //                        deterministic two-level tree, the best-integer bookkeeping on device.
+//   * multi-GPU        : owner-computes partition.  Every rank owns a set of rows (its y) and a
+//                        set of columns (its x); it stores its rows of A and its columns of A (as
+//                        rows of A^T) and keeps *ghost* copies of the few xbar / y entries owned by
+//                        other ranks that its rows / columns touch.  One halo exchange of xbar and
+//                        one of y per iteration replace the dense all-reduce of A^T y: no partial
+//                        sums cross GPUs, so the iterates stay bit-identical to the single-GPU
+//                        (and reference) ones.  The partition is a pure integer function of the
+//                        sparsity pattern (oracle/partition_oracle.py restates it).
 //
 // Floating point: IEEE fp64, compiled with -fmad=false and written with explicit
 // __dmul_rn/__dadd_rn so products and sums round exactly like the numpy/scipy code of the
 // reference.  A row (column) sum is accumulated sequentially in the stored entry order from
 // 0.0 — the same order as scipy's csr_matvec (csc_matvec) — so x, xbar, y, T and Sigma are
-// bit-identical to the reference on a single GPU.  Only the scalar dot products of the
-// stats block use a different (tree) order than numpy.dot.
+// bit-identical to the reference.  Only the scalar dot products of the stats block use a
+// different (tree) order than numpy.dot.
 #include "../../include/cpppd.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cub/cub.cuh>
 
@@ -31,6 +41,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -43,6 +54,10 @@ constexpr int kBlock = 256;      // threads per CTA for the streaming kernels (8
 constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
 constexpr int kColQ = 4;         // column-pass partial sums per CTA
 constexpr int kRowQ = 7;         // row-pass partial sums per CTA
+constexpr int kStatQ = kColQ + kRowQ;
+constexpr int32_t kEqBit = 0x40000000;   // A^T entries: set when the source row is an equality
+constexpr int32_t kIdxMask = 0x3fffffff;
+constexpr int kMaxWorld = 64;
 
 thread_local std::string g_create_error;
 
@@ -77,15 +92,75 @@ struct StatsDev {  // device-resident, copied verbatim into cpppd_stats
   cpppd_stats s;
 };
 
+// Halo of one distributed vector: which owned entries go to which peer, where ghosts land.
+struct Halo {
+  int64_t owned = 0, ghost = 0, send_total = 0;
+  std::vector<int64_t> send_count, send_off, recv_count, recv_off;  // per peer rank
+  int32_t *send_idx = nullptr;  // send_total local indices (owned part), grouped by peer
+  double *send_buf = nullptr;   // send_total staging values
+};
+
+// NCCL is resolved at run time (dlopen) so that the library loads without it on one GPU.
+struct NcclApi {
+  void *dl = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+const char *load_nccl() {
+  if (g_nccl.dl) return nullptr;
+  const char *env = getenv("CPPPD_NCCL_LIB");
+  void *dl = nullptr;
+  if (env && *env) dl = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) dl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) return "cannot dlopen libnccl.so.2 (set CPPPD_NCCL_LIB)";
+#define SYM(field, name)                                       \
+  g_nccl.field = (decltype(g_nccl.field))dlsym(dl, name);      \
+  if (!g_nccl.field) return "libnccl lacks symbol " name;
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(AllGather, "ncclAllGather")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.dl = dl;
+  return nullptr;
+}
+
 }  // namespace
 
 struct cpppd_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  int64_t n = 0, m_eq = 0, m_ineq = 0, m = 0, nnz = 0;
+  // global problem
+  int64_t n_glob = 0, m_eq_glob = 0, m_ineq_glob = 0, m_glob = 0, nnz_glob = 0;
+  // this rank's share (== global on one GPU)
+  int64_t n = 0, m = 0, m_eq = 0, nnz_rows = 0, nnz_cols = 0;
+  int rank = 0, world = 1;
+  bool identity_layout = true;  // local index == original index (one GPU, no reordering)
+  int32_t *col_old = nullptr;   // n + ghosts : original column id of a local column
+  int32_t *row_old = nullptr;   // m + ghosts : original row id of a local row
+  Halo hx, hy;                  // xbar-like vectors (columns) / y-like vectors (rows)
+  ncclComm_t comm = nullptr;
   double alpha = 1, theta = 1, one_plus_theta = 2;
   uint32_t flags = 0;
+  int64_t granule = 0;
   cpppd_alloc_fn alloc = nullptr;
   cpppd_free_fn free_fn = nullptr;
   void *alloc_user = nullptr;
@@ -95,6 +170,7 @@ struct cpppd_solver {
   double *c = nullptr, *T = nullptr, *lb = nullptr, *ub = nullptr, *x = nullptr, *xbar = nullptr;
   double *b = nullptr, *sigma = nullptr, *y = nullptr, *dbuf = nullptr, *best = nullptr;
   double *colpart = nullptr, *rowpart = nullptr, *xr_scratch = nullptr;
+  double *stat_local = nullptr, *stat_all = nullptr;  // kStatQ / world*kStatQ
   int stat_blocks_c = 0, stat_blocks_r = 0;
   StatsDev *stats_dev = nullptr;
   cpppd_stats *stats_host = nullptr;
@@ -104,7 +180,6 @@ struct cpppd_solver {
   bool have_d = false;
   int sm_count = 148;
   std::map<int64_t, cudaGraphExec_t> graphs;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int sticky = 0;
 };
@@ -119,7 +194,7 @@ int fail(cpppd_solver *h, int code, const char *fmt, ...) {
   va_end(ap);
   if (h) {
     h->err = buf;
-    if (code == CPPPD_ERR_CUDA) h->sticky = code;
+    if (code == CPPPD_ERR_CUDA || code == CPPPD_ERR_COMM) h->sticky = code;
   }
   g_create_error = buf;
   return code;
@@ -131,6 +206,14 @@ int fail(cpppd_solver *h, int code, const char *fmt, ...) {
     if (e_ != cudaSuccess)                                                                    \
       return fail(h, CPPPD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
                   __FILE__, __LINE__);                                                        \
+  } while (0)
+
+#define NK(call)                                                                                    \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess)                                                                          \
+      return fail(h, CPPPD_ERR_COMM, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_),    \
+                  __FILE__, __LINE__);                                                              \
   } while (0)
 
 #define CHECK_HANDLE(h)                                  \
@@ -172,7 +255,25 @@ int alloc_array(cpppd_solver *h, T **out, int64_t count, bool persistent = true)
   return 0;
 }
 
-inline int grid_for(int64_t items, int block = kBlock) { return (int)((items + block - 1) / block); }
+// temporaries of setup(): freed on scope exit
+struct Scratch {
+  cpppd_solver *h;
+  std::vector<void *> ptrs;
+  explicit Scratch(cpppd_solver *h_) : h(h_) {}
+  ~Scratch() { for (void *p : ptrs) dev_free(h, p); }
+  template <typename T>
+  int get(T **out, int64_t count) {
+    int rc = alloc_array(h, out, count, false);
+    if (!rc) ptrs.push_back(*out);
+    return rc;
+  }
+  void release(void *p) {
+    for (auto &q : ptrs)
+      if (q == p) { dev_free(h, p); q = nullptr; }
+  }
+};
+
+inline int grid_for(int64_t items, int block = kBlock) { return (int)std::max<int64_t>(1, (items + block - 1) / block); }
 
 // ------------------------------------------------------------------------------------------
 // device helpers
@@ -227,27 +328,6 @@ __device__ __forceinline__ void block_reduce_write(double (&v)[Q], unsigned is_m
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// setup kernels: CSR -> SELL-32, transpose, preconditioners
-// ------------------------------------------------------------------------------------------
-__global__ void k_widen_indptr(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t count) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = in[i];
-}
-
-// flags[0] |= 1 when a row has negative length, |= 2 when a column index is out of range
-__global__ void k_validate(const int64_t *__restrict__ rowptr, int64_t m, const int32_t *__restrict__ indices,
-                           int64_t nnz, int64_t n, int *flags) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int bad = 0;
-  if (i < m && rowptr[i + 1] < rowptr[i]) bad |= 1;
-  for (int64_t e = i; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
-    int32_t j = indices[e];
-    if (j < 0 || j >= n) bad |= 2;
-  }
-  if (bad) atomicOr(flags, bad);
-}
-
 // one warp per slice: width = longest row of the slice; out[s] = 32 * width
 __global__ void k_slice_extent(const int64_t *__restrict__ rowptr, int64_t nrows, int64_t nslices,
                                int64_t *__restrict__ extent) {
@@ -289,6 +369,27 @@ __global__ void k_fill_sell(const int64_t *__restrict__ rowptr, const int32_t *_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// setup kernels: validation, locality keys, partition, local matrices, SELL-32, transpose
+// ------------------------------------------------------------------------------------------
+__global__ void k_widen_indptr(const int32_t *__restrict__ in, int64_t *__restrict__ out, int64_t count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = in[i];
+}
+
+// flags[0] |= 1 when a row has negative length, |= 2 when a column index is out of range
+__global__ void k_validate(const int64_t *__restrict__ rowptr, int64_t m, const int32_t *__restrict__ indices,
+                           int64_t nnz, int64_t n, int *flags) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < m && rowptr[i + 1] < rowptr[i]) bad |= 1;
+  for (int64_t e = i; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+    int32_t j = indices[e];
+    if (j < 0 || j >= n) bad |= 2;
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
 __global__ void k_row_of_entry(const int64_t *__restrict__ rowptr, int64_t m, int64_t nnz,
                                uint32_t *__restrict__ row_of, uint32_t *__restrict__ entry_id) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -302,31 +403,188 @@ __global__ void k_row_of_entry(const int64_t *__restrict__ rowptr, int64_t m, in
   entry_id[e] = (uint32_t)e;
 }
 
-__global__ void k_colptr_from_sorted(const uint32_t *__restrict__ sorted_cols, int64_t nnz, int64_t n,
-                                     int64_t *__restrict__ colptr) {
-  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j > n) return;
-  int64_t lo = 0, hi = nnz;  // first position with sorted_cols[pos] >= j
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)sorted_cols[mid] < j) lo = mid + 1; else hi = mid;
-  }
-  colptr[j] = lo;
+__global__ void k_fill_i32(int32_t *p, int64_t count, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) p[i] = v;
 }
 
-__global__ void k_gather_transposed(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ row_of,
-                                    const double *__restrict__ values, int64_t nnz, int32_t *__restrict__ t_idx,
-                                    double *__restrict__ t_val) {
+// row_key[i] = min column index of row i (n for an empty row)
+__global__ void k_row_key(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indices, int64_t m,
+                          int32_t n, int32_t *__restrict__ row_key) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int32_t k = n;
+  for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) k = min(k, indices[e]);
+  row_key[i] = k;
+}
+
+// col_key[j] = min row_key over the rows that hit column j; col_len[j] = entries of column j
+__global__ void k_col_key(const int32_t *__restrict__ indices, const uint32_t *__restrict__ row_of, int64_t nnz,
+                          const int32_t *__restrict__ row_key, int32_t *__restrict__ col_key,
+                          int32_t *__restrict__ col_len) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int32_t j = indices[e];
+  atomicMin(col_key + j, row_key[row_of[e]]);
+  atomicAdd(col_len + j, 1);
+}
+
+// work[bucket] += entries (rows: their length; columns: their length)
+__global__ void k_bucket_work(const int32_t *__restrict__ key, const int64_t *__restrict__ rowptr,
+                              const int32_t *__restrict__ len32, int64_t count, int32_t granule,
+                              unsigned long long *__restrict__ work) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  unsigned long long w = rowptr ? (unsigned long long)(rowptr[i + 1] - rowptr[i]) : (unsigned long long)len32[i];
+  if (w) atomicAdd(work + key[i] / granule, w);
+}
+
+// sort key of a row / column: (owner, [is_ineq,] bucket); also counts per owner
+__global__ void k_sort_keys(const int32_t *__restrict__ key, int64_t count, int32_t granule,
+                            const int32_t *__restrict__ owner_of_bucket, int64_t m_eq, int is_rows,
+                            uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_id,
+                            int32_t *__restrict__ count_per_owner, int32_t *__restrict__ eq_per_owner) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int32_t q = key[i] / granule;
+  int32_t o = owner_of_bucket[q];
+  uint64_t major = is_rows ? (uint64_t)o * 2 + (i >= m_eq ? 1 : 0) : (uint64_t)o;
+  out_key[i] = (major << 32) | (uint32_t)q;
+  out_id[i] = (uint32_t)i;
+  atomicAdd(count_per_owner + o, 1);
+  if (is_rows && i < m_eq) atomicAdd(eq_per_owner + o, 1);
+}
+
+__global__ void k_invert(const uint32_t *__restrict__ order, int64_t count, int32_t *__restrict__ pos) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= nnz) return;
-  uint32_t e = perm[p];
-  t_idx[p] = (int32_t)row_of[e];
-  t_val[p] = values[e];
+  if (p < count) pos[order[p]] = (int32_t)p;
+}
+
+// ghost marking: a column position is a ghost of this rank when one of this rank's rows hits a
+// column owned elsewhere; a row position is a ghost when it hits one of this rank's columns.
+__global__ void k_mark_ghosts(const int32_t *__restrict__ indices, const uint32_t *__restrict__ row_of, int64_t nnz,
+                              const int32_t *__restrict__ row_pos, const int32_t *__restrict__ col_pos, int32_t rs,
+                              int32_t re, int32_t cs, int32_t ce, int32_t *__restrict__ gcol_flag,
+                              int32_t *__restrict__ grow_flag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int32_t rp = row_pos[row_of[e]], cp = col_pos[indices[e]];
+  bool row_mine = rp >= rs && rp < re, col_mine = cp >= cs && cp < ce;
+  if (row_mine && !col_mine) gcol_flag[cp] = 1;
+  if (col_mine && !row_mine) grow_flag[rp] = 1;
+}
+
+// what this rank must send to peer t: its columns hit by t's rows, its rows hitting t's columns
+__global__ void k_mark_sends(const int32_t *__restrict__ indices, const uint32_t *__restrict__ row_of, int64_t nnz,
+                             const int32_t *__restrict__ row_pos, const int32_t *__restrict__ col_pos, int32_t rs,
+                             int32_t re, int32_t cs, int32_t ce, int32_t trs, int32_t tre, int32_t tcs, int32_t tce,
+                             int32_t *__restrict__ sendx_flag, int32_t *__restrict__ sendy_flag) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int32_t rp = row_pos[row_of[e]], cp = col_pos[indices[e]];
+  if (cp >= cs && cp < ce && rp >= trs && rp < tre) sendx_flag[cp - cs] = 1;
+  if (rp >= rs && rp < re && cp >= tcs && cp < tce) sendy_flag[rp - rs] = 1;
+}
+
+// out[base + scan[i]] = value(i) for flagged i
+__global__ void k_compact(const int32_t *__restrict__ flag, const int32_t *__restrict__ scan, int64_t count,
+                          const uint32_t *__restrict__ map, int32_t add, int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count || !flag[i]) return;
+  out[scan[i]] = map ? (int32_t)map[i] : (int32_t)i + add;
+}
+
+__global__ void k_copy_u32_i32(const uint32_t *__restrict__ in, int64_t count, int32_t *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (int32_t)in[i];
+}
+
+// lengths of this rank's rows in local order
+__global__ void k_local_row_len(const uint32_t *__restrict__ row_order, int32_t rs, int64_t mloc,
+                                const int64_t *__restrict__ rowptr, int64_t *__restrict__ len) {
+  int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li > mloc) return;
+  if (li == mloc) { len[li] = 0; return; }
+  uint32_t old = row_order[rs + li];
+  len[li] = rowptr[old + 1] - rowptr[old];
+}
+
+// this rank's rows of A in local numbering (entry order inside a row untouched)
+__global__ void k_local_rows_fill(const uint32_t *__restrict__ row_order, int32_t rs, int64_t mloc,
+                                  const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indices,
+                                  const double *__restrict__ values, const int32_t *__restrict__ col_pos, int32_t cs,
+                                  int32_t ce, const int32_t *__restrict__ gcol_scan,
+                                  const int64_t *__restrict__ lrowptr, int32_t *__restrict__ out_idx,
+                                  double *__restrict__ out_val) {
+  int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= mloc) return;
+  uint32_t old = row_order[rs + li];
+  int64_t src = rowptr[old], len = rowptr[old + 1] - src, dst = lrowptr[li];
+  for (int64_t k = 0; k < len; ++k) {
+    int32_t cp = col_pos[indices[src + k]];
+    out_idx[dst + k] = (cp >= cs && cp < ce) ? cp - cs : (ce - cs) + gcol_scan[cp];
+    out_val[dst + k] = values[src + k];
+  }
+}
+
+__global__ void k_entry_col_pos(const int32_t *__restrict__ indices, const int32_t *__restrict__ col_pos,
+                                int64_t nnz, uint32_t *__restrict__ out) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) out[e] = (uint32_t)col_pos[indices[e]];
+}
+
+// first sorted position whose key is >= j, for j in [j0, j0 + count]
+__global__ void k_lower_bounds(const uint32_t *__restrict__ sorted, int64_t nnz, int64_t j0, int64_t count,
+                               int64_t *__restrict__ out) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > count) return;
+  int64_t j = j0 + t, lo = 0, hi = nnz;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)sorted[mid] < j) lo = mid + 1; else hi = mid;
+  }
+  out[t] = lo;
+}
+
+// this rank's columns of A as rows of A^T: entries in original row order, local row numbering,
+// equality rows tagged with kEqBit
+__global__ void k_local_cols_fill(const uint32_t *__restrict__ perm, const uint32_t *__restrict__ row_of,
+                                  const double *__restrict__ values, int64_t first, int64_t count,
+                                  const int32_t *__restrict__ row_pos, int32_t rs, int32_t re,
+                                  const int32_t *__restrict__ grow_scan, int64_t m_eq_glob,
+                                  int32_t *__restrict__ out_idx, double *__restrict__ out_val) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  uint32_t e = perm[first + t];
+  uint32_t old = row_of[e];
+  int32_t rp = row_pos ? row_pos[old] : (int32_t)old;
+  int32_t local = (rp >= rs && rp < re) ? rp - rs : (re - rs) + grow_scan[rp];
+  out_idx[t] = local | ((int64_t)old < m_eq_glob ? kEqBit : 0);
+  out_val[t] = values[e];
+}
+
+__global__ void k_subtract_base(int64_t *p, int64_t count, int64_t base) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) p[i] -= base;
+}
+
+// dst[i] = src[map[i]]
+__global__ void k_gather_f64(const double *__restrict__ src, const int32_t *__restrict__ map, int64_t count,
+                             double *__restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[i] = src[map[i]];
+}
+
+// dst[map[i]] = src[i]
+__global__ void k_scatter_f64(const double *__restrict__ src, const int32_t *__restrict__ map, int64_t count,
+                              double *__restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[map[i]] = src[i];
 }
 
 // diag_t (:122-153): thread per column of A, sequential over the column in row order,
 // equality and inequality parts accumulated separately then  (0 + s_eq) + s_ineq.
-__global__ void k_precond_cols(SellView AT, int64_t n, int64_t m_eq, int has_eq, int has_ineq, double power,
+__global__ void k_precond_cols(SellView AT, int64_t n, int has_eq, int has_ineq, double power,
                                double *__restrict__ T) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t s = j >> 5;
@@ -339,7 +597,7 @@ __global__ void k_precond_cols(SellView AT, int64_t n, int64_t m_eq, int has_eq,
     int32_t r = AT.idx[p];
     if (r >= 0) {
       double t = __dmul_rn(abs_pow(AT.val[p], power), 1.0);
-      if (r < m_eq) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+      if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
     }
   }
   if (j < n) {
@@ -379,7 +637,7 @@ template <bool kWriteD>
 __global__ void __launch_bounds__(kBlock, 8)
 k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c, const double *__restrict__ T,
          const double *__restrict__ lb, const double *__restrict__ ub, double *__restrict__ x,
-         double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int64_t m_eq, int has_eq, int has_ineq,
+         double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int has_eq, int has_ineq,
          double theta, double one_plus_theta) {
   const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = j >> 5;
@@ -399,14 +657,13 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
     const int32_t *ip = AT.idx + p0 + lane;
     const double *vp = AT.val + p0 + lane;
     const int width = (int)((p1 - p0) >> 5);
-    const int32_t meq = (int32_t)m_eq;
 #pragma unroll 4
     for (int k = 0; k < width; ++k) {
       const int32_t r = __ldcs(ip + k * kSlice);
       const double a = __ldcs(vp + k * kSlice);
       if (r >= 0) {
-        const double t = __dmul_rn(a, __ldg(y + r));
-        if (r < meq) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+        const double t = __dmul_rn(a, __ldg(y + (r & kIdxMask)));
+        if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
       }
     }
   }
@@ -531,10 +788,10 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
   block_reduce_write<kRowQ>(v, 0x70u, part + (int64_t)blockIdx.x * kRowQ);
 }
 
-// One CTA: fold the per-CTA partials in a fixed order, apply :248-291's scalar logic.
+// One CTA: fold this rank's per-CTA partials in a fixed order into kStatQ numbers.
 __global__ void __launch_bounds__(kBlock)
-k_stats_final(const double *__restrict__ colpart, int nbc, const double *__restrict__ rowpart, int nbr,
-              int64_t n, int has_eq, int has_ineq, int64_t niter, StatsDev *out) {
+k_stats_local(const double *__restrict__ colpart, int nbc, const double *__restrict__ rowpart, int nbr,
+              double *__restrict__ out) {
   double cv[kColQ] = {0.0, 0.0, 0.0, 0.0};
   const double ninf = -INFINITY;
   double rv[kRowQ] = {0.0, 0.0, 0.0, 0.0, ninf, ninf, ninf};
@@ -547,12 +804,25 @@ k_stats_final(const double *__restrict__ colpart, int nbc, const double *__restr
 #pragma unroll
     for (int q = 4; q < kRowQ; ++q) rv[q] = nan_max(rv[q], rowpart[(int64_t)bi * kRowQ + q]);
   }
-  __shared__ double fin[kColQ + kRowQ];
+  __shared__ double fin[kStatQ];
   block_reduce_write<kColQ>(cv, 0u, fin);
   __syncthreads();
   block_reduce_write<kRowQ>(rv, 0x70u, fin + kColQ);
   __syncthreads();
-  if (threadIdx.x != 0) return;
+  if (threadIdx.x < kStatQ) out[threadIdx.x] = fin[threadIdx.x];
+}
+
+// One thread: fold the ranks' numbers in rank order, then apply :248-291's scalar logic.
+__global__ void k_stats_final(const double *__restrict__ all, int world, int64_t n_glob, int has_eq, int has_ineq,
+                              int64_t niter, StatsDev *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double fin[kStatQ];
+  for (int q = 0; q < kStatQ; ++q) fin[q] = all[q];
+  for (int r = 1; r < world; ++r)
+    for (int q = 0; q < kStatQ; ++q) {
+      const double v = all[r * kStatQ + q];
+      fin[q] = (q >= kColQ + 4) ? nan_max(fin[q], v) : __dadd_rn(fin[q], v);
+    }
   cpppd_stats &s = out->s;
   double e1 = fin[0], e2 = fin[1];
   if (has_eq) {
@@ -570,7 +840,7 @@ k_stats_final(const double *__restrict__ colpart, int nbc, const double *__restr
   s.max_violated_equality_rounded = has_eq ? fin[kColQ + 5] : 0.0;
   s.max_violated_inequality = fin[kColQ + 6];  // -inf when there is no inequality row
   s.energy_rounded = fin[2];
-  s.frac_zero_xbar = n > 0 ? fin[3] / (double)n : 0.0;
+  s.frac_zero_xbar = n_glob > 0 ? fin[3] / (double)n_glob : 0.0;
   const int feasible = (s.max_violated_equality_rounded == 0.0) && (s.max_violated_inequality <= 0.0);
   s.feasible = feasible;
   s.improved = 0;
@@ -593,99 +863,141 @@ __global__ void k_init_stats(StatsDev *st) {
   st->s.best_integer_energy = INFINITY;  // :192
 }
 
+// halo staging: buf[k] = vec[idx[k]]
+__global__ void k_pack(const double *__restrict__ vec, const int32_t *__restrict__ idx, int64_t count,
+                       double *__restrict__ buf) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) buf[k] = vec[idx[k]];
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 SellView view(const Sell &s) { return SellView{s.slice_ptr, s.idx, s.val, s.nrows, s.nslices, s.uniform_width}; }
+
+template <typename T>
+int exclusive_scan(cpppd_solver *h, const T *in, T *out, int64_t count) {
+  size_t bytes = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, h->stream));
+  void *tmp = dev_alloc(h, bytes, false);
+  if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "scan workspace allocation failed");
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, count, h->stream);
+  cudaStreamSynchronize(h->stream);
+  dev_free(h, tmp);
+  CK(e);
+  return 0;
+}
+
+template <typename K>
+int sort_pairs(cpppd_solver *h, cub::DoubleBuffer<K> &keys, cub::DoubleBuffer<uint32_t> &vals, int64_t count,
+               int end_bit) {
+  if (count == 0) return 0;
+  size_t bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, vals, count, 0, end_bit, h->stream));
+  void *tmp = dev_alloc(h, bytes, false);
+  if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "sort workspace allocation failed");
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, vals, count, 0, end_bit, h->stream);
+  cudaStreamSynchronize(h->stream);
+  dev_free(h, tmp);
+  CK(e);
+  return 0;
+}
+
+int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b)) ++b;
+  return b;
+}
 
 // CSR (device, int64 rowptr) -> SELL-32 (device)
 int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, const double *values, int64_t nrows,
                Sell *out) {
   out->nrows = nrows;
   out->nslices = (nrows + kSlice - 1) / kSlice;
-  int64_t ns = out->nslices;
-  int64_t *extent = nullptr;
-  if (int rc = alloc_array(h, &extent, ns + 1, false)) return rc;
+  const int64_t ns = out->nslices;
+  Scratch tmp(h);
+  int64_t *extent = nullptr, *mm = nullptr;
+  if (int rc = tmp.get(&extent, ns + 1)) return rc;
+  if (int rc = tmp.get(&mm, 2)) return rc;
   if (int rc = alloc_array(h, &out->slice_ptr, ns + 1)) return rc;
   CK(cudaMemsetAsync(extent, 0, sizeof(int64_t) * (ns + 1), h->stream));
   if (ns) k_slice_extent<<<grid_for(ns * 32), kBlock, 0, h->stream>>>(rowptr, nrows, ns, extent);
-  size_t tmp_bytes = 0;
-  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, extent, out->slice_ptr, ns + 1, h->stream));
-  void *tmp = dev_alloc(h, tmp_bytes, false);
-  if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "scan workspace allocation failed");
-  CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, extent, out->slice_ptr, ns + 1, h->stream));
+  if (int rc = exclusive_scan(h, extent, out->slice_ptr, ns + 1)) return rc;
   CK(cudaMemcpyAsync(&out->padded, out->slice_ptr + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-  {  // uniform slice width <=> min extent == max extent
-    int64_t *mm = nullptr;
-    if (int rc = alloc_array(h, &mm, 2, false)) return rc;
+  int64_t host_mm[2] = {0, 1};
+  if (ns) {  // uniform slice width <=> min extent == max extent
     size_t b1 = 0, b2 = 0;
     CK(cub::DeviceReduce::Min(nullptr, b1, extent, mm, ns, h->stream));
     CK(cub::DeviceReduce::Max(nullptr, b2, extent, mm + 1, ns, h->stream));
-    void *t2 = dev_alloc(h, std::max(b1, b2), false);
-    if (!t2) return fail(h, CPPPD_ERR_NOMEM, "reduce workspace allocation failed");
-    int64_t host_mm[2] = {0, 1};
-    if (ns) {
-      CK(cub::DeviceReduce::Min(t2, b1, extent, mm, ns, h->stream));
-      CK(cub::DeviceReduce::Max(t2, b2, extent, mm + 1, ns, h->stream));
-      CK(cudaMemcpyAsync(host_mm, mm, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-    }
-    CK(cudaStreamSynchronize(h->stream));
-    out->uniform_width = (ns && host_mm[0] == host_mm[1]) ? host_mm[0] / kSlice : -1;
-    dev_free(h, t2);
-    dev_free(h, mm);
+    char *t2 = nullptr;
+    if (int rc = tmp.get(&t2, (int64_t)std::max(b1, b2))) return rc;
+    CK(cub::DeviceReduce::Min(t2, b1, extent, mm, ns, h->stream));
+    CK(cub::DeviceReduce::Max(t2, b2, extent, mm + 1, ns, h->stream));
+    CK(cudaMemcpyAsync(host_mm, mm, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
-  dev_free(h, tmp);
-  dev_free(h, extent);
+  out->uniform_width = (ns && host_mm[0] == host_mm[1]) ? host_mm[0] / kSlice : -1;
   if (int rc = alloc_array(h, &out->idx, out->padded)) return rc;
   if (int rc = alloc_array(h, &out->val, out->padded)) return rc;
   if (ns) k_fill_sell<<<grid_for(ns * 32), kBlock, 0, h->stream>>>(rowptr, indices, values, nrows, ns, out->slice_ptr,
                                                                   out->idx, out->val);
   CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
-int upload(cpppd_solver *h, double *dst, const double *src, int64_t count) {
+int upload_f64(cpppd_solver *h, double *dst, const double *src, int64_t count) {
   if (count == 0) return 0;
   CK(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
 
+int read_i32(cpppd_solver *h, const int32_t *dev, int32_t *host, int64_t count) {
+  CK(cudaMemcpyAsync(host, dev, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t default_granule(int64_t n) {
+  int64_t g = 32;
+  while (g < (n >> 14)) g *= 2;
+  return g;
+}
+
+// gather a full-length host vector into this rank's local layout (owned + ghosts)
+int upload_local(cpppd_solver *h, Scratch &tmp, const double *host_full, int64_t full_count, const int32_t *map,
+                 int64_t local_count, double *dst) {
+  if (h->identity_layout) return upload_f64(h, dst, host_full, local_count);
+  double *full = nullptr;
+  if (int rc = tmp.get(&full, full_count)) return rc;
+  if (int rc = upload_f64(h, full, host_full, full_count)) return rc;
+  if (local_count) k_gather_f64<<<grid_for(local_count), kBlock, 0, h->stream>>>(full, map, local_count, dst);
+  CK(cudaStreamSynchronize(h->stream));
+  tmp.release(full);
+  return 0;
+}
+
 int setup(cpppd_solver *h, const cpppd_problem *P) {
-  const int64_t n = h->n, m = h->m, nnz = h->nnz;
+  const int64_t n = h->n_glob, m = h->m_glob, nnz = h->nnz_glob, m_eq = h->m_eq_glob;
+  const int N = h->world, me = h->rank;
   cudaStream_t st = h->stream;
-  // ---- vectors
-  for (double **v : {&h->c, &h->T, &h->lb, &h->ub, &h->x, &h->xbar, &h->dbuf, &h->best})
-    if (int rc = alloc_array(h, v, n)) return rc;
-  for (double **v : {&h->b, &h->sigma, &h->y})
-    if (int rc = alloc_array(h, v, m)) return rc;
-  if (int rc = upload(h, h->c, P->c, n)) return rc;
-  if (int rc = upload(h, h->lb, P->lb, n)) return rc;
-  if (int rc = upload(h, h->ub, P->ub, n)) return rc;
-  if (int rc = upload(h, h->b, P->b, m)) return rc;
-  if (P->x0) {
-    if (int rc = upload(h, h->x, P->x0, n)) return rc;
-  } else {
-    CK(cudaMemsetAsync(h->x, 0, sizeof(double) * std::max<int64_t>(n, 1), st));
-  }
-  CK(cudaMemcpyAsync(h->xbar, h->x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));  // x3 = x (:190)
-  CK(cudaMemsetAsync(h->y, 0, sizeof(double) * std::max<int64_t>(m, 1), st));            // :166,:177
-  // ---- CSR of A on the device (temporary)
+  Scratch tmp(h);
+  // ---- CSR of the whole A on the device (temporary; every rank analyses the same pattern)
   int64_t *rowptr = nullptr;
   int32_t *indices = nullptr;
   double *values = nullptr;
-  if (int rc = alloc_array(h, &rowptr, m + 1, false)) return rc;
-  if (int rc = alloc_array(h, &indices, nnz, false)) return rc;
-  if (int rc = alloc_array(h, &values, nnz, false)) return rc;
+  if (int rc = tmp.get(&rowptr, m + 1)) return rc;
+  if (int rc = tmp.get(&indices, nnz)) return rc;
+  if (int rc = tmp.get(&values, nnz)) return rc;
   if (P->indptr_bits == 64) {
     CK(cudaMemcpyAsync(rowptr, P->indptr, sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
   } else {
     int32_t *tmp32 = nullptr;
-    if (int rc = alloc_array(h, &tmp32, m + 1, false)) return rc;
+    if (int rc = tmp.get(&tmp32, m + 1)) return rc;
     CK(cudaMemcpyAsync(tmp32, P->indptr, sizeof(int32_t) * (m + 1), cudaMemcpyHostToDevice, st));
     k_widen_indptr<<<grid_for(m + 1), kBlock, 0, st>>>(tmp32, rowptr, m + 1);
     CK(cudaStreamSynchronize(st));
-    dev_free(h, tmp32);
+    tmp.release(tmp32);
   }
   if (nnz) {
     CK(cudaMemcpyAsync(indices, P->indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
@@ -693,108 +1005,340 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   }
   {  // validation on the device: monotone row pointers, column indices in range
     int *flag = nullptr;
-    if (int rc = alloc_array(h, &flag, 1, false)) return rc;
+    if (int rc = tmp.get(&flag, 1)) return rc;
     CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
     int64_t items = std::max<int64_t>(m, std::min<int64_t>(nnz, (int64_t)h->sm_count * 64 * kBlock));
     if (items) k_validate<<<grid_for(items), kBlock, 0, st>>>(rowptr, m, indices, nnz, n, flag);
     int host_flag = 0;
     CK(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    dev_free(h, flag);
     if (host_flag & 1) return fail(h, CPPPD_ERR_INVALID, "indptr is not non-decreasing");
     if (host_flag & 2) return fail(h, CPPPD_ERR_INVALID, "column index outside [0, n)");
   }
-  // ---- A in SELL-32
-  if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
-  // ---- transpose: stable radix sort of the entries by column keeps, inside each column, the
-  //      row order of the CSR — exactly the accumulation order of scipy's csc_matvec.
+  uint32_t *row_of = nullptr, *entry_id = nullptr;
+  if (int rc = tmp.get(&row_of, nnz)) return rc;
+  if (int rc = tmp.get(&entry_id, nnz)) return rc;
+  if (nnz) k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, entry_id);
+
+  const bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
+  h->identity_layout = !reorder;
+  int32_t rs = 0, re = (int32_t)m, cs = 0, ce = (int32_t)n;
+  int64_t n_ghost = 0, m_ghost = 0;
+  uint32_t *row_order = nullptr, *col_order = nullptr;
+  int32_t *row_pos = nullptr, *col_pos = nullptr, *gcol_scan = nullptr, *grow_scan = nullptr;
+  std::vector<int32_t> row_start(N + 1, 0), col_start(N + 1, 0), eq_count(N, 0);
+  h->hx = Halo();
+  h->hy = Halo();
+  for (Halo *H : {&h->hx, &h->hy}) {
+    H->send_count.assign(N, 0);
+    H->send_off.assign(N, 0);
+    H->recv_count.assign(N, 0);
+    H->recv_off.assign(N, 0);
+  }
+
+  if (reorder) {
+    // ---- locality keys -> buckets -> owners (oracle/partition_oracle.py restates this block)
+    const int64_t G = h->granule > 0 ? h->granule : default_granule(n);
+    h->granule = G;
+    const int64_t nb = n / G + 2;
+    int32_t *row_key = nullptr, *col_key = nullptr, *col_len = nullptr, *owner_dev = nullptr, *counts = nullptr;
+    unsigned long long *work = nullptr;
+    if (int rc = tmp.get(&row_key, m)) return rc;
+    if (int rc = tmp.get(&col_key, n)) return rc;
+    if (int rc = tmp.get(&col_len, n)) return rc;
+    if (int rc = tmp.get(&work, nb)) return rc;
+    if (int rc = tmp.get(&owner_dev, nb)) return rc;
+    if (int rc = tmp.get(&counts, 3 * (int64_t)N)) return rc;
+    if (m) k_row_key<<<grid_for(m), kBlock, 0, st>>>(rowptr, indices, m, (int32_t)n, row_key);
+    if (n) k_fill_i32<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)n);
+    CK(cudaMemsetAsync(col_len, 0, sizeof(int32_t) * std::max<int64_t>(n, 1), st));
+    if (nnz) k_col_key<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_key, col_key, col_len);
+    CK(cudaMemsetAsync(work, 0, sizeof(unsigned long long) * nb, st));
+    if (m) k_bucket_work<<<grid_for(m), kBlock, 0, st>>>(row_key, rowptr, nullptr, m, (int32_t)G, work);
+    if (n) k_bucket_work<<<grid_for(n), kBlock, 0, st>>>(col_key, nullptr, col_len, n, (int32_t)G, work);
+    std::vector<unsigned long long> work_h(nb);
+    CK(cudaMemcpyAsync(work_h.data(), work, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<int32_t> owner_h(nb, 0);
+    unsigned long long total = 0, before = 0;
+    for (auto w : work_h) total += w;
+    for (int64_t q = 0; q < nb; ++q) {
+      owner_h[q] = total ? (int32_t)std::min<unsigned long long>(N - 1, (unsigned __int128)before * N / total) : 0;
+      before += work_h[q];
+    }
+    CK(cudaMemcpyAsync(owner_dev, owner_h.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    // ---- local orders: rows by (owner, is_ineq, bucket, id), columns by (owner, bucket, id)
+    uint64_t *rk_a = nullptr, *rk_b = nullptr, *ck_a = nullptr, *ck_b = nullptr;
+    uint32_t *ro_a = nullptr, *ro_b = nullptr, *co_a = nullptr, *co_b = nullptr;
+    if (int rc = tmp.get(&rk_a, m)) return rc;
+    if (int rc = tmp.get(&rk_b, m)) return rc;
+    if (int rc = tmp.get(&ro_a, m)) return rc;
+    if (int rc = tmp.get(&ro_b, m)) return rc;
+    if (int rc = tmp.get(&ck_a, n)) return rc;
+    if (int rc = tmp.get(&ck_b, n)) return rc;
+    if (int rc = tmp.get(&co_a, n)) return rc;
+    if (int rc = tmp.get(&co_b, n)) return rc;
+    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * N, st));
+    if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rk_a, ro_a, counts, counts + N);
+    if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, ck_a, co_a, counts + 2 * N, nullptr);
+    const int end_bit = 32 + bits_for((uint64_t)2 * N + 1);
+    cub::DoubleBuffer<uint64_t> rk(rk_a, rk_b), ck(ck_a, ck_b);
+    cub::DoubleBuffer<uint32_t> rov(ro_a, ro_b), cov(co_a, co_b);
+    if (int rc = sort_pairs(h, rk, rov, m, end_bit)) return rc;
+    if (int rc = sort_pairs(h, ck, cov, n, end_bit)) return rc;
+    row_order = rov.Current();
+    col_order = cov.Current();
+    std::vector<int32_t> counts_h(3 * N);
+    if (int rc = read_i32(h, counts, counts_h.data(), 3 * N)) return rc;
+    for (int r = 0; r < N; ++r) {
+      row_start[r + 1] = row_start[r] + counts_h[r];
+      eq_count[r] = counts_h[N + r];
+      col_start[r + 1] = col_start[r] + counts_h[2 * N + r];
+    }
+    if (int rc = tmp.get(&row_pos, m)) return rc;
+    if (int rc = tmp.get(&col_pos, n)) return rc;
+    if (m) k_invert<<<grid_for(m), kBlock, 0, st>>>(row_order, m, row_pos);
+    if (n) k_invert<<<grid_for(n), kBlock, 0, st>>>(col_order, n, col_pos);
+    rs = row_start[me]; re = row_start[me + 1]; cs = col_start[me]; ce = col_start[me + 1];
+    tmp.release(rk_a); tmp.release(rk_b); tmp.release(ck_a); tmp.release(ck_b);
+    tmp.release(rov.Alternate()); tmp.release(cov.Alternate());
+    tmp.release(row_key); tmp.release(col_key); tmp.release(col_len); tmp.release(work);
+    // ---- ghosts of this rank
+    int32_t *gcol_flag = nullptr, *grow_flag = nullptr;
+    if (int rc = tmp.get(&gcol_flag, n + 1)) return rc;
+    if (int rc = tmp.get(&grow_flag, m + 1)) return rc;
+    if (int rc = tmp.get(&gcol_scan, n + 1)) return rc;
+    if (int rc = tmp.get(&grow_scan, m + 1)) return rc;
+    CK(cudaMemsetAsync(gcol_flag, 0, sizeof(int32_t) * (n + 1), st));
+    CK(cudaMemsetAsync(grow_flag, 0, sizeof(int32_t) * (m + 1), st));
+    if (nnz && N > 1) k_mark_ghosts<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, gcol_flag, grow_flag);
+    if (int rc = exclusive_scan(h, gcol_flag, gcol_scan, n + 1)) return rc;
+    if (int rc = exclusive_scan(h, grow_flag, grow_scan, m + 1)) return rc;
+    std::vector<int32_t> cb(N + 1), rb(N + 1);
+    for (int r = 0; r <= N; ++r) {
+      if (int rc = read_i32(h, gcol_scan + col_start[r], &cb[r], 1)) return rc;
+      if (int rc = read_i32(h, grow_scan + row_start[r], &rb[r], 1)) return rc;
+    }
+    n_ghost = cb[N];
+    m_ghost = rb[N];
+    for (int r = 0; r < N; ++r) {
+      h->hx.recv_count[r] = cb[r + 1] - cb[r];
+      h->hx.recv_off[r] = cb[r];
+      h->hy.recv_count[r] = rb[r + 1] - rb[r];
+      h->hy.recv_off[r] = rb[r];
+    }
+    // ---- local -> original id maps (owned, then ghosts in exchange order)
+    const int64_t nloc = ce - cs, mloc = re - rs;
+    if (int rc = alloc_array(h, &h->col_old, nloc + n_ghost)) return rc;
+    if (int rc = alloc_array(h, &h->row_old, mloc + m_ghost)) return rc;
+    if (nloc) k_copy_u32_i32<<<grid_for(nloc), kBlock, 0, st>>>(col_order + cs, nloc, h->col_old);
+    if (mloc) k_copy_u32_i32<<<grid_for(mloc), kBlock, 0, st>>>(row_order + rs, mloc, h->row_old);
+    if (n_ghost) k_compact<<<grid_for(n), kBlock, 0, st>>>(gcol_flag, gcol_scan, n, col_order, 0, h->col_old + nloc);
+    if (m_ghost) k_compact<<<grid_for(m), kBlock, 0, st>>>(grow_flag, grow_scan, m, row_order, 0, h->row_old + mloc);
+    CK(cudaStreamSynchronize(st));
+    tmp.release(gcol_flag);
+    tmp.release(grow_flag);
+    // ---- what to send to every peer
+    if (N > 1) {
+      int32_t *sx_flag = nullptr, *sy_flag = nullptr, *sx_scan = nullptr, *sy_scan = nullptr;
+      if (int rc = tmp.get(&sx_flag, nloc + 1)) return rc;
+      if (int rc = tmp.get(&sy_flag, mloc + 1)) return rc;
+      if (int rc = tmp.get(&sx_scan, nloc + 1)) return rc;
+      if (int rc = tmp.get(&sy_scan, mloc + 1)) return rc;
+      std::vector<std::vector<int32_t>> sx_lists(N), sy_lists(N);
+      int32_t *list_dev = nullptr;
+      if (int rc = tmp.get(&list_dev, std::max(nloc, mloc) + 1)) return rc;
+      for (int t = 0; t < N; ++t) {
+        if (t == me) continue;
+        CK(cudaMemsetAsync(sx_flag, 0, sizeof(int32_t) * (nloc + 1), st));
+        CK(cudaMemsetAsync(sy_flag, 0, sizeof(int32_t) * (mloc + 1), st));
+        if (nnz) k_mark_sends<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce,
+                                                              row_start[t], row_start[t + 1], col_start[t], col_start[t + 1],
+                                                              sx_flag, sy_flag);
+        if (int rc = exclusive_scan(h, sx_flag, sx_scan, nloc + 1)) return rc;
+        if (int rc = exclusive_scan(h, sy_flag, sy_scan, mloc + 1)) return rc;
+        int32_t cx = 0, cy = 0;
+        if (int rc = read_i32(h, sx_scan + nloc, &cx, 1)) return rc;
+        if (int rc = read_i32(h, sy_scan + mloc, &cy, 1)) return rc;
+        if (cx) {
+          k_compact<<<grid_for(nloc), kBlock, 0, st>>>(sx_flag, sx_scan, nloc, nullptr, 0, list_dev);
+          sx_lists[t].resize(cx);
+          if (int rc = read_i32(h, list_dev, sx_lists[t].data(), cx)) return rc;
+        }
+        if (cy) {
+          k_compact<<<grid_for(mloc), kBlock, 0, st>>>(sy_flag, sy_scan, mloc, nullptr, 0, list_dev);
+          sy_lists[t].resize(cy);
+          if (int rc = read_i32(h, list_dev, sy_lists[t].data(), cy)) return rc;
+        }
+      }
+      for (int pass = 0; pass < 2; ++pass) {
+        Halo &H = pass ? h->hy : h->hx;
+        auto &lists = pass ? sy_lists : sx_lists;
+        std::vector<int32_t> flat;
+        for (int t = 0; t < N; ++t) {
+          H.send_off[t] = (int64_t)flat.size();
+          H.send_count[t] = (int64_t)lists[t].size();
+          flat.insert(flat.end(), lists[t].begin(), lists[t].end());
+        }
+        H.send_total = (int64_t)flat.size();
+        if (int rc = alloc_array(h, &H.send_idx, H.send_total)) return rc;
+        if (int rc = alloc_array(h, &H.send_buf, H.send_total)) return rc;
+        if (H.send_total) CK(cudaMemcpy(H.send_idx, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice));
+      }
+      tmp.release(sx_flag); tmp.release(sy_flag); tmp.release(sx_scan); tmp.release(sy_scan); tmp.release(list_dev);
+    }
+  }
+  const int64_t nloc = ce - cs, mloc = re - rs;
+  h->n = nloc;
+  h->m = mloc;
+  h->m_eq = reorder ? eq_count[me] : m_eq;
+  h->hx.owned = nloc;
+  h->hx.ghost = n_ghost;
+  h->hy.owned = mloc;
+  h->hy.ghost = m_ghost;
+
+  // ---- this rank's rows of A -> SELL-32
+  if (!reorder) {
+    h->nnz_rows = nnz;
+    if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
+  } else {
+    int64_t *len = nullptr, *lrowptr = nullptr;
+    if (int rc = tmp.get(&len, mloc + 1)) return rc;
+    if (int rc = tmp.get(&lrowptr, mloc + 1)) return rc;
+    k_local_row_len<<<grid_for(mloc + 1), kBlock, 0, st>>>(row_order, rs, mloc, rowptr, len);
+    if (int rc = exclusive_scan(h, len, lrowptr, mloc + 1)) return rc;
+    int64_t lnnz = 0;
+    CK(cudaMemcpyAsync(&lnnz, lrowptr + mloc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->nnz_rows = lnnz;
+    int32_t *lidx = nullptr;
+    double *lval = nullptr;
+    if (int rc = tmp.get(&lidx, lnnz)) return rc;
+    if (int rc = tmp.get(&lval, lnnz)) return rc;
+    if (mloc) k_local_rows_fill<<<grid_for(mloc), kBlock, 0, st>>>(row_order, rs, mloc, rowptr, indices, values, col_pos,
+                                                                  cs, ce, gcol_scan, lrowptr, lidx, lval);
+    if (int rc = build_sell(h, lrowptr, lidx, lval, mloc, &h->A)) return rc;
+    tmp.release(len); tmp.release(lrowptr); tmp.release(lidx); tmp.release(lval);
+  }
+  // ---- this rank's columns of A as rows of A^T.  A stable radix sort of the entries (taken in CSR
+  //      order) by column keeps, inside each column, the original row order — exactly the
+  //      accumulation order of scipy's csc_matvec.
   {
-    uint32_t *row_of = nullptr, *keys_a = nullptr, *keys_b = nullptr, *ids_a = nullptr, *ids_b = nullptr;
-    int64_t *colptr = nullptr;
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *ids_b = nullptr;
+    if (int rc = tmp.get(&keys_a, nnz)) return rc;
+    if (int rc = tmp.get(&keys_b, nnz)) return rc;
+    if (int rc = tmp.get(&ids_b, nnz)) return rc;
+    if (nnz) {
+      if (reorder) k_entry_col_pos<<<grid_for(nnz), kBlock, 0, st>>>(indices, col_pos, nnz, keys_a);
+      else CK(cudaMemcpyAsync(keys_a, indices, sizeof(uint32_t) * nnz, cudaMemcpyDeviceToDevice, st));
+    }
+    cub::DoubleBuffer<uint32_t> keys(keys_a, keys_b), ids(entry_id, ids_b);
+    if (int rc = sort_pairs(h, keys, ids, nnz, bits_for((uint64_t)std::max<int64_t>(n, 1)))) return rc;
+    int64_t *lcolptr = nullptr;
+    if (int rc = tmp.get(&lcolptr, nloc + 1)) return rc;
+    k_lower_bounds<<<grid_for(nloc + 1), kBlock, 0, st>>>(keys.Current(), nnz, cs, nloc, lcolptr);
+    int64_t first = 0, last = 0;
+    CK(cudaMemcpyAsync(&first, lcolptr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last, lcolptr + nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t lnnz = last - first;
+    h->nnz_cols = lnnz;
+    if (first) k_subtract_base<<<grid_for(nloc + 1), kBlock, 0, st>>>(lcolptr, nloc + 1, first);
+    tmp.release(keys.Current() == keys_a ? keys_b : keys_a);
     int32_t *t_idx = nullptr;
     double *t_val = nullptr;
-    if (int rc = alloc_array(h, &row_of, nnz, false)) return rc;
-    if (int rc = alloc_array(h, &keys_a, nnz, false)) return rc;
-    if (int rc = alloc_array(h, &keys_b, nnz, false)) return rc;
-    if (int rc = alloc_array(h, &ids_a, nnz, false)) return rc;
-    if (int rc = alloc_array(h, &ids_b, nnz, false)) return rc;
-    if (int rc = alloc_array(h, &colptr, n + 1, false)) return rc;
-    if (nnz) {
-      k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, ids_a);
-      CK(cudaMemcpyAsync(keys_a, indices, sizeof(uint32_t) * nnz, cudaMemcpyDeviceToDevice, st));
+    if (int rc = tmp.get(&t_idx, lnnz)) return rc;
+    if (int rc = tmp.get(&t_val, lnnz)) return rc;
+    if (lnnz) {
+      if (reorder) {
+        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(ids.Current(), row_of, values, first, lnnz, row_pos, rs, re,
+                                                             grow_scan, m_eq, t_idx, t_val);
+      } else {
+        // identity layout: row_pos / grow_scan do not exist; local row == original row
+        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(ids.Current(), row_of, values, first, lnnz, nullptr, 0,
+                                                             (int32_t)m, nullptr, m_eq, t_idx, t_val);
+      }
     }
-    int end_bit = 1;
-    while (end_bit < 32 && ((int64_t)1 << end_bit) < n) ++end_bit;
-    cub::DoubleBuffer<uint32_t> keys(keys_a, keys_b), ids(ids_a, ids_b);
-    if (nnz) {
-      size_t tmp_bytes = 0;
-      CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, ids, nnz, 0, end_bit, st));
-      void *tmp = dev_alloc(h, tmp_bytes, false);
-      if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "sort workspace allocation failed");
-      CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, ids, nnz, 0, end_bit, st));
-      CK(cudaStreamSynchronize(st));
-      dev_free(h, tmp);
-    }
-    k_colptr_from_sorted<<<grid_for(n + 1), kBlock, 0, st>>>(keys.Current(), nnz, n, colptr);
-    // reuse the now dead CSR index/key buffers?  keep it simple: dedicated outputs
-    if (int rc = alloc_array(h, &t_idx, nnz, false)) return rc;
-    if (int rc = alloc_array(h, &t_val, nnz, false)) return rc;
-    if (nnz) k_gather_transposed<<<grid_for(nnz), kBlock, 0, st>>>(ids.Current(), row_of, values, nnz, t_idx, t_val);
     CK(cudaStreamSynchronize(st));
-    dev_free(h, row_of);
-    dev_free(h, keys_a);
-    dev_free(h, keys_b);
-    dev_free(h, ids_a);
-    dev_free(h, ids_b);
-    dev_free(h, indices);
-    dev_free(h, values);
-    dev_free(h, rowptr);
-    if (int rc = build_sell(h, colptr, t_idx, t_val, n, &h->AT)) return rc;
-    CK(cudaStreamSynchronize(st));
-    dev_free(h, colptr);
-    dev_free(h, t_idx);
-    dev_free(h, t_val);
+    tmp.release(keys_a); tmp.release(keys_b); tmp.release(ids_b); tmp.release(entry_id); tmp.release(row_of);
+    tmp.release(indices); tmp.release(values); tmp.release(rowptr);
+    if (int rc = build_sell(h, lcolptr, t_idx, t_val, nloc, &h->AT)) return rc;
+    tmp.release(lcolptr); tmp.release(t_idx); tmp.release(t_val);
   }
-  // ---- preconditioners (:122-179)
-  const int has_eq = h->m_eq > 0, has_ineq = h->m_ineq > 0;
+  // ---- vectors in local layout
+  for (double **v : {&h->c, &h->T, &h->lb, &h->ub, &h->best})
+    if (int rc = alloc_array(h, v, nloc)) return rc;
+  for (double **v : {&h->x, &h->xbar, &h->dbuf})
+    if (int rc = alloc_array(h, v, nloc + n_ghost)) return rc;
+  for (double **v : {&h->b, &h->sigma})
+    if (int rc = alloc_array(h, v, mloc)) return rc;
+  if (int rc = alloc_array(h, &h->y, mloc + m_ghost)) return rc;
+  if (int rc = upload_local(h, tmp, P->c, n, h->col_old, nloc, h->c)) return rc;
+  if (int rc = upload_local(h, tmp, P->lb, n, h->col_old, nloc, h->lb)) return rc;
+  if (int rc = upload_local(h, tmp, P->ub, n, h->col_old, nloc, h->ub)) return rc;
+  if (int rc = upload_local(h, tmp, P->b, m, h->row_old, mloc, h->b)) return rc;
+  if (P->x0) {
+    if (int rc = upload_local(h, tmp, P->x0, n, h->col_old, nloc + n_ghost, h->x)) return rc;
+  } else {
+    CK(cudaMemsetAsync(h->x, 0, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1), st));
+  }
+  CK(cudaMemcpyAsync(h->xbar, h->x, sizeof(double) * (nloc + n_ghost), cudaMemcpyDeviceToDevice, st));  // x3 = x (:190)
+  CK(cudaMemsetAsync(h->dbuf, 0, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1), st));
+  CK(cudaMemsetAsync(h->y, 0, sizeof(double) * std::max<int64_t>(mloc + m_ghost, 1), st));              // :166,:177
+  // ---- preconditioners (:122-179): complete columns / rows are local, so no exchange is needed
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
   if (h->AT.nslices)
-    k_precond_cols<<<grid_for(h->AT.nslices * 32), kBlock, 0, st>>>(view(h->AT), n, h->m_eq, has_eq, has_ineq,
-                                                                     2.0 - h->alpha, h->T);
+    k_precond_cols<<<grid_for(h->AT.nslices * 32), kBlock, 0, st>>>(view(h->AT), nloc, has_eq, has_ineq, 2.0 - h->alpha, h->T);
   if (h->A.nslices)
-    k_precond_rows<<<grid_for(h->A.nslices * 32), kBlock, 0, st>>>(view(h->A), m, h->alpha, h->sigma);
+    k_precond_rows<<<grid_for(h->A.nslices * 32), kBlock, 0, st>>>(view(h->A), mloc, h->alpha, h->sigma);
   // ---- stats plumbing
-  h->stat_blocks_c = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(n), (int64_t)h->sm_count * 8));
+  h->stat_blocks_c = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(nloc), (int64_t)h->sm_count * 8));
   h->stat_blocks_r = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(h->A.nslices * 32), (int64_t)h->sm_count * 8));
   if (int rc = alloc_array(h, &h->colpart, (int64_t)h->stat_blocks_c * kColQ)) return rc;
   if (int rc = alloc_array(h, &h->rowpart, (int64_t)h->stat_blocks_r * kRowQ)) return rc;
+  if (int rc = alloc_array(h, &h->stat_local, kStatQ)) return rc;
+  if (int rc = alloc_array(h, &h->stat_all, (int64_t)kStatQ * N)) return rc;
   if (int rc = alloc_array(h, &h->stats_dev, 1)) return rc;
   k_init_stats<<<1, 1, 0, st>>>(h->stats_dev);
   CK(cudaMallocHost(&h->stats_host, sizeof(cpppd_stats)));
   memset(h->stats_host, 0, sizeof(cpppd_stats));
-  CK(cudaEventCreate(&h->ev0));
-  CK(cudaEventCreate(&h->ev1));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
   return 0;
 }
 
-int launch_primal(cpppd_solver *h, bool write_d) {
-  if (h->AT.nslices == 0) return 0;
-  const int grid = grid_for(h->AT.nslices * 32);
-  const int has_eq = h->m_eq > 0, has_ineq = h->m_ineq > 0;
-  if (write_d)
-    k_primal<true><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
-                                                   h->n, h->m_eq, has_eq, has_ineq, h->theta, h->one_plus_theta);
-  else
-    k_primal<false><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
-                                                    h->n, h->m_eq, has_eq, has_ineq, h->theta, h->one_plus_theta);
+// Refresh the ghost part of a distributed vector: every rank sends the owned entries its peers
+// need and receives its ghosts straight into vec[owned ...].
+int exchange(cpppd_solver *h, double *vec, Halo &H) {
+  if (h->world == 1) return 0;
+  if (H.send_total) k_pack<<<grid_for(H.send_total), kBlock, 0, h->stream>>>(vec, H.send_idx, H.send_total, H.send_buf);
+  NK(g_nccl.GroupStart());
+  for (int t = 0; t < h->world; ++t) {
+    if (H.send_count[t]) NK(g_nccl.Send(H.send_buf + H.send_off[t], (size_t)H.send_count[t], ncclFloat64, t, h->comm, h->stream));
+    if (H.recv_count[t]) NK(g_nccl.Recv(vec + H.owned + H.recv_off[t], (size_t)H.recv_count[t], ncclFloat64, t, h->comm, h->stream));
+  }
+  NK(g_nccl.GroupEnd());
   return 0;
 }
 
+int launch_primal(cpppd_solver *h, bool write_d) {
+  if (h->AT.nslices) {
+    const int grid = grid_for(h->AT.nslices * 32);
+    const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+    if (write_d)
+      k_primal<true><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
+                                                     h->n, has_eq, has_ineq, h->theta, h->one_plus_theta);
+    else
+      k_primal<false><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
+                                                      h->n, has_eq, has_ineq, h->theta, h->one_plus_theta);
+  }
+  return exchange(h, h->xbar, h->hx);
+}
+
 int launch_dual(cpppd_solver *h) {
-  if (h->A.nslices == 0) return 0;
-  k_dual<<<grid_for(h->A.nslices * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->b, h->sigma, h->y, h->m, h->m_eq);
-  return 0;
+  if (h->A.nslices)
+    k_dual<<<grid_for(h->A.nslices * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->b, h->sigma, h->y, h->m, h->m_eq);
+  return exchange(h, h->y, h->hy);
 }
 
 int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
@@ -805,11 +1349,14 @@ int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
   }
   cudaGraph_t g = nullptr;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  for (int64_t i = 0; i < k; ++i) {
-    launch_primal(h, false);
-    launch_dual(h);
+  int rc = 0;
+  for (int64_t i = 0; i < k && !rc; ++i) {
+    rc = launch_primal(h, false);
+    if (!rc) rc = launch_dual(h);
   }
-  CK(cudaStreamEndCapture(h->stream, &g));
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  if (rc) return rc;
+  CK(e);
   cudaGraphExec_t ge = nullptr;
   CK(cudaGraphInstantiate(&ge, g, 0));
   cudaGraphDestroy(g);
@@ -819,7 +1366,7 @@ int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
 }
 
 int run_iterations(cpppd_solver *h, int64_t k) {
-  const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH);
+  const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH) && (h->world == 1 || (h->flags & CPPPD_FLAG_GRAPH_COMM));
   while (k > 0) {
     int64_t step = std::min<int64_t>(k, kGraphChunk);
     if (use_graph && step >= 2) {
@@ -828,8 +1375,8 @@ int run_iterations(cpppd_solver *h, int64_t k) {
       CK(cudaGraphLaunch(ge, h->stream));
     } else {
       for (int64_t i = 0; i < step; ++i) {
-        launch_primal(h, false);
-        launch_dual(h);
+        if (int rc = launch_primal(h, false)) return rc;
+        if (int rc = launch_dual(h)) return rc;
       }
       CK(cudaGetLastError());
     }
@@ -844,11 +1391,58 @@ int run_iterations(cpppd_solver *h, int64_t k) {
 // ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
+namespace {
+
+// assemble a distributed vector (local layout, owned part) into original order on the host
+int fetch_vector(cpppd_solver *h, const double *local, bool is_col, double *host_dst) {
+  const int64_t owned = is_col ? h->n : h->m, full = is_col ? h->n_glob : h->m_glob;
+  if (h->identity_layout) {
+    if (full) CK(cudaMemcpyAsync(host_dst, local, sizeof(double) * full, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  Scratch tmp(h);
+  double *buf = nullptr;
+  if (int rc = tmp.get(&buf, full)) return rc;
+  CK(cudaMemsetAsync(buf, 0, sizeof(double) * std::max<int64_t>(full, 1), h->stream));
+  if (owned) k_scatter_f64<<<grid_for(owned), kBlock, 0, h->stream>>>(local, is_col ? h->col_old : h->row_old, owned, buf);
+  // every entry is owned by exactly one rank, the others contribute +0.0: the sum is exact
+  if (h->world > 1 && full) NK(g_nccl.AllReduce(buf, buf, (size_t)full, ncclFloat64, ncclSum, h->comm, h->stream));
+  if (full) CK(cudaMemcpyAsync(host_dst, buf, sizeof(double) * full, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int vector_ptr(cpppd_solver *h, int32_t which, double **p, bool *is_col) {
+  switch (which) {
+    case CPPPD_VEC_X: *p = h->x; *is_col = true; return 0;
+    case CPPPD_VEC_XBAR: *p = h->xbar; *is_col = true; return 0;
+    case CPPPD_VEC_Y: *p = h->y; *is_col = false; return 0;
+    case CPPPD_VEC_T: *p = h->T; *is_col = true; return 0;
+    case CPPPD_VEC_SIGMA: *p = h->sigma; *is_col = false; return 0;
+    case CPPPD_VEC_BEST_INTEGER: *p = h->best; *is_col = true; return 0;
+    case CPPPD_VEC_D: *p = h->dbuf; *is_col = true; return 0;
+    default: return fail(h, CPPPD_ERR_INVALID, "unknown vector id %d", which);
+  }
+}
+
+}  // namespace
+
 extern "C" {
 
 int cpppd_abi_version(void) { return CPPPD_ABI_VERSION; }
 
 const char *cpppd_last_error(cpppd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cpppd_comm_unique_id(void *out128) {
+  cpppd_solver *h = nullptr;
+  if (!out128) return fail(h, CPPPD_ERR_INVALID, "null output");
+  if (const char *e = load_nccl()) return fail(h, CPPPD_ERR_COMM, "%s", e);
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, sizeof id);
+  return 0;
+}
 
 int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   cpppd_solver *h = nullptr;
@@ -857,11 +1451,14 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   if (P->abi_version != CPPPD_ABI_VERSION)
     return fail(h, CPPPD_ERR_INVALID, "ABI version mismatch: caller %d, library %d", P->abi_version, CPPPD_ABI_VERSION);
   if (P->n < 0 || P->m_eq < 0 || P->m_ineq < 0 || P->nnz < 0) return fail(h, CPPPD_ERR_INVALID, "negative size");
-  if (P->n >= (int64_t)1 << 31 || P->m_eq + P->m_ineq >= (int64_t)1 << 31)
-    return fail(h, CPPPD_ERR_INVALID, "n and m must be below 2^31 (32-bit indices)");
+  if (P->n >= (int64_t)1 << 30 || P->m_eq + P->m_ineq >= (int64_t)1 << 30)
+    return fail(h, CPPPD_ERR_INVALID, "n and m must be below 2^30 (30-bit local indices)");
   if (P->nnz >= (int64_t)1 << 32) return fail(h, CPPPD_ERR_INVALID, "nnz must be below 2^32");
   if (P->index_bits != 32) return fail(h, CPPPD_ERR_INVALID, "column indices must be int32 (narrow them on the host)");
   if (P->indptr_bits != 32 && P->indptr_bits != 64) return fail(h, CPPPD_ERR_INVALID, "indptr_bits must be 32 or 64");
+  const int world = P->world_size <= 0 ? 1 : P->world_size;
+  if (world > kMaxWorld || P->rank < 0 || P->rank >= world) return fail(h, CPPPD_ERR_INVALID, "bad rank / world_size");
+  if (world > 1 && !P->comm_id) return fail(h, CPPPD_ERR_INVALID, "world_size > 1 needs comm_id (cpppd_comm_unique_id)");
   const int64_t m = P->m_eq + P->m_ineq;
   if (!P->indptr || (P->nnz && (!P->indices || !P->values)) || (P->n && (!P->c || !P->lb || !P->ub)) || (m && !P->b))
     return fail(h, CPPPD_ERR_INVALID, "null array pointer");
@@ -878,15 +1475,18 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   if (P->device < 0 || P->device >= ndev) return fail(h, CPPPD_ERR_INVALID, "device %d out of range (%d devices)", P->device, ndev);
   h = new cpppd_solver();
   h->device = P->device;
-  h->n = P->n;
-  h->m_eq = P->m_eq;
-  h->m_ineq = P->m_ineq;
-  h->m = m;
-  h->nnz = P->nnz;
+  h->n_glob = P->n;
+  h->m_eq_glob = P->m_eq;
+  h->m_ineq_glob = P->m_ineq;
+  h->m_glob = m;
+  h->nnz_glob = P->nnz;
   h->alpha = P->alpha;
   h->theta = P->theta;
   h->one_plus_theta = P->one_plus_theta;
   h->flags = P->flags;
+  h->granule = P->partition_granule;
+  h->rank = P->rank;
+  h->world = world;
   h->alloc = P->alloc;
   h->free_fn = P->free;
   h->alloc_user = P->alloc_user;
@@ -906,6 +1506,19 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
       }
       h->own_stream = true;
     }
+    if (world > 1) {
+      if (const char *e = load_nccl()) {
+        rc = fail(h, CPPPD_ERR_COMM, "%s", e);
+        break;
+      }
+      ncclUniqueId id;
+      memcpy(&id, P->comm_id, sizeof id);
+      ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, h->rank);
+      if (r != ncclSuccess) {
+        rc = fail(h, CPPPD_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+        break;
+      }
+    }
     rc = setup(h, P);
   } while (0);
   if (rc) {
@@ -922,10 +1535,9 @@ int cpppd_destroy(cpppd_handle h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->comm) g_nccl.CommDestroy(h->comm);
   for (void *p : h->owned) dev_free(h, p);
   if (h->stats_host) cudaFreeHost(h->stats_host);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
@@ -942,7 +1554,7 @@ int cpppd_iterate(cpppd_handle h, int64_t k) {
 int cpppd_primal_step(cpppd_handle h, int32_t keep_d) {
   CHECK_HANDLE(h);
   if (h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "primal step already issued for this iteration");
-  launch_primal(h, keep_d != 0);
+  if (int rc = launch_primal(h, keep_d != 0)) return rc;
   h->mid_iteration = true;
   h->have_d = keep_d != 0;
   CK(cudaGetLastError());
@@ -953,20 +1565,30 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
   CHECK_HANDLE(h);
   if (!h->mid_iteration || !h->have_d)
     return fail(h, CPPPD_ERR_STATE, "cpppd_stats_step needs a preceding cpppd_primal_step(keep_d=1)");
-  const int has_eq = h->m_eq > 0, has_ineq = h->m_ineq > 0;
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
   // column pass turns dbuf into x4 in place; with force_integer it also materialises xr = rint(x)
   double *xr = h->x;
   if (force_integer) {
     if (!h->xr_scratch)
-      if (int rc = alloc_array(h, &h->xr_scratch, h->n)) return rc;
+      if (int rc = alloc_array(h, &h->xr_scratch, h->n + h->hx.ghost)) return rc;
     xr = h->xr_scratch;
   }
   k_stats_cols<<<h->stat_blocks_c, kBlock, 0, h->stream>>>(h->c, h->x, h->xbar, h->lb, h->ub, h->dbuf, xr, h->n,
                                                           force_integer, h->colpart);
+  // the row pass reads x, x4 and xr at ghost columns too
+  if (int rc = exchange(h, h->x, h->hx)) return rc;
+  if (int rc = exchange(h, h->dbuf, h->hx)) return rc;
+  if (force_integer)
+    if (int rc = exchange(h, xr, h->hx)) return rc;
   k_stats_rows<<<h->stat_blocks_r, kBlock, 0, h->stream>>>(view(h->A), h->x, h->dbuf, h->xbar, xr, h->b, h->y, h->m,
                                                           h->m_eq, force_integer, h->rowpart);
-  k_stats_final<<<1, kBlock, 0, h->stream>>>(h->colpart, h->stat_blocks_c, h->rowpart, h->stat_blocks_r, h->n, has_eq,
-                                             has_ineq, h->niter, h->stats_dev);
+  k_stats_local<<<1, kBlock, 0, h->stream>>>(h->colpart, h->stat_blocks_c, h->rowpart, h->stat_blocks_r, h->stat_local);
+  const double *all = h->stat_local;
+  if (h->world > 1) {
+    NK(g_nccl.AllGather(h->stat_local, h->stat_all, kStatQ, ncclFloat64, h->comm, h->stream));
+    all = h->stat_all;
+  }
+  k_stats_final<<<1, 32, 0, h->stream>>>(all, h->world, h->n_glob, has_eq, has_ineq, h->niter, h->stats_dev);
   k_snapshot_best<<<std::max(1, std::min(grid_for(h->n), h->sm_count * 8)), kBlock, 0, h->stream>>>(h->stats_dev, xr,
                                                                                                   h->best, h->n);
   CK(cudaMemcpyAsync(h->stats_host, h->stats_dev, sizeof(cpppd_stats), cudaMemcpyDeviceToHost, h->stream));
@@ -979,7 +1601,7 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
 int cpppd_dual_step(cpppd_handle h) {
   CHECK_HANDLE(h);
   if (!h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "no primal step open");
-  launch_dual(h);
+  if (int rc = launch_dual(h)) return rc;
   h->mid_iteration = false;
   h->niter += 1;
   CK(cudaGetLastError());
@@ -1005,25 +1627,33 @@ int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms) {
   CHECK_HANDLE(h);
   if (!elapsed_ms || k < 0) return fail(h, CPPPD_ERR_INVALID, "bad argument");
   if (h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "cpppd_dual_step must close the open iteration first");
-  CK(cudaEventRecord(h->ev0, h->stream));
-  if (int rc = run_iterations(h, k)) return rc;
-  CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaEventSynchronize(h->ev1));
-  CK(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
-  return 0;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, h->stream));
+  int rc = run_iterations(h, k);
+  if (!rc) {
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(elapsed_ms, e0, e1));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return rc;
 }
 
 int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_ms) {
   CHECK_HANDLE(h);
   if (!primal_ms || !dual_ms || k < 0 || k > 64) return fail(h, CPPPD_ERR_INVALID, "bad argument (k must be in [0, 64])");
   if (h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "cpppd_dual_step must close the open iteration first");
+  // the halo exchanges (world > 1) fall inside the brackets of the kernel that produces the data
   std::vector<cudaEvent_t> ev(2 * k + 1);
   for (auto &e : ev) CK(cudaEventCreate(&e));
   CK(cudaEventRecord(ev[0], h->stream));
   for (int64_t i = 0; i < k; ++i) {
-    launch_primal(h, false);
+    if (int rc = launch_primal(h, false)) return rc;
     CK(cudaEventRecord(ev[2 * i + 1], h->stream));
-    launch_dual(h);
+    if (int rc = launch_dual(h)) return rc;
     CK(cudaEventRecord(ev[2 * i + 2], h->stream));
   }
   h->niter += k;
@@ -1040,28 +1670,13 @@ int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_
   return 0;
 }
 
-static int vector_ptr(cpppd_solver *h, int32_t which, double **p, int64_t *count) {
-  switch (which) {
-    case CPPPD_VEC_X: *p = h->x; *count = h->n; return 0;
-    case CPPPD_VEC_XBAR: *p = h->xbar; *count = h->n; return 0;
-    case CPPPD_VEC_Y: *p = h->y; *count = h->m; return 0;
-    case CPPPD_VEC_T: *p = h->T; *count = h->n; return 0;
-    case CPPPD_VEC_SIGMA: *p = h->sigma; *count = h->m; return 0;
-    case CPPPD_VEC_BEST_INTEGER: *p = h->best; *count = h->n; return 0;
-    case CPPPD_VEC_D: *p = h->dbuf; *count = h->n; return 0;
-    default: return fail(h, CPPPD_ERR_INVALID, "unknown vector id %d", which);
-  }
-}
-
 int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst) {
   CHECK_HANDLE(h);
   double *p = nullptr;
-  int64_t count = 0;
-  if (int rc = vector_ptr(h, which, &p, &count)) return rc;
+  bool is_col = true;
+  if (int rc = vector_ptr(h, which, &p, &is_col)) return rc;
   if (!host_dst) return fail(h, CPPPD_ERR_INVALID, "null destination");
-  if (count) CK(cudaMemcpyAsync(host_dst, p, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return fetch_vector(h, p, is_col, host_dst);
 }
 
 int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src) {
@@ -1069,10 +1684,29 @@ int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src) {
   if (which != CPPPD_VEC_X && which != CPPPD_VEC_XBAR && which != CPPPD_VEC_Y)
     return fail(h, CPPPD_ERR_INVALID, "only x, xbar and y can be set");
   double *p = nullptr;
-  int64_t count = 0;
-  if (int rc = vector_ptr(h, which, &p, &count)) return rc;
+  bool is_col = true;
+  if (int rc = vector_ptr(h, which, &p, &is_col)) return rc;
   if (!host_src) return fail(h, CPPPD_ERR_INVALID, "null source");
-  if (count) CK(cudaMemcpyAsync(p, host_src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+  Scratch tmp(h);
+  const int64_t local = is_col ? h->n + h->hx.ghost : h->m + h->hy.ghost;
+  if (int rc = upload_local(h, tmp, host_src, is_col ? h->n_glob : h->m_glob, is_col ? h->col_old : h->row_old, local, p))
+    return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cpppd_get_layout(cpppd_handle h, int32_t columns, int64_t *owned, int64_t *ghost, int32_t *ids) {
+  CHECK_HANDLE(h);
+  const Halo &H = columns ? h->hx : h->hy;
+  if (owned) *owned = H.owned;
+  if (ghost) *ghost = H.ghost;
+  if (!ids) return 0;
+  const int64_t count = H.owned + H.ghost;
+  if (h->identity_layout) {
+    for (int64_t i = 0; i < count; ++i) ids[i] = (int32_t)i;
+    return 0;
+  }
+  if (count) CK(cudaMemcpyAsync(ids, columns ? h->col_old : h->row_old, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1081,23 +1715,34 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   CHECK_HANDLE(h);
   if (!out) return fail(h, CPPPD_ERR_INVALID, "null output");
   memset(out, 0, sizeof *out);
-  out->n = h->n;
-  out->m_eq = h->m_eq;
-  out->m_ineq = h->m_ineq;
-  out->nnz = h->nnz;
+  out->n = h->n_glob;
+  out->m_eq = h->m_eq_glob;
+  out->m_ineq = h->m_ineq_glob;
+  out->nnz = h->nnz_glob;
   out->a_padded_entries = h->A.padded;
   out->at_padded_entries = h->AT.padded;
   out->device_bytes = h->device_bytes;
-  const int64_t P = h->nnz >= ((int64_t)1 << 31) ? 8 : 4;
-  out->bytes_per_iteration_algorithmic = 2 * h->nnz * 12 + P * (h->m + 1) + P * (h->n + 1) + 8 * (8 * h->n + 5 * h->m);
-  out->bytes_per_iteration_actual = (h->A.padded + h->AT.padded) * 12 + 8 * (h->A.nslices + h->AT.nslices + 2) +
-                                    8 * (8 * h->n + 5 * h->m);
+  const int64_t P = h->nnz_glob >= ((int64_t)1 << 31) ? 8 : 4;
+  out->bytes_per_iteration_algorithmic =
+      2 * h->nnz_glob * 12 + P * (h->m_glob + 1) + P * (h->n_glob + 1) + 8 * (8 * h->n_glob + 5 * h->m_glob);
+  out->bytes_per_iteration_actual = (h->A.padded + h->AT.padded) * 12 +
+                                    (h->A.uniform_width >= 0 ? 0 : 8 * (h->A.nslices + 1)) +
+                                    (h->AT.uniform_width >= 0 ? 0 : 8 * (h->AT.nslices + 1)) + 8 * (8 * h->n + 5 * h->m) +
+                                    8 * (h->hx.ghost + h->hy.ghost);
   out->value_bytes = 8;
   out->const_vector_mask = 0;
   out->sm_count = h->sm_count;
-  out->world_size = 1;
-  out->row_begin = 0;
-  out->row_end = h->m;
+  out->world_size = h->world;
+  out->rank = h->rank;
+  out->n_local = h->n;
+  out->m_local = h->m;
+  out->m_eq_local = h->m_eq;
+  out->n_ghost = h->hx.ghost;
+  out->m_ghost = h->hy.ghost;
+  out->nnz_local_rows = h->nnz_rows;
+  out->nnz_local_cols = h->nnz_cols;
+  out->halo_send_bytes_per_iteration = 8 * (h->hx.send_total + h->hy.send_total);
+  out->partition_granule = h->granule;
   return 0;
 }
 

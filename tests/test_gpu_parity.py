@@ -247,3 +247,46 @@ def test_large_properties_potts256():
     assert np.array_equal(x, xo)
     assert np.all(x >= lp.lb) and np.all(x <= lp.ub) and np.all(y >= 0)
     assert info["nnz"] == lp.a_ineq.nnz and info["a_padded_entries"] >= info["nnz"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_locality_reordering_keeps_iterates_bit_identical(name):
+    """CPPPD_FLAG_REORDER renumbers rows and columns (the multi-GPU layout on one GPU); entry order
+    inside rows / columns is untouched, so every iterate must stay bit-identical."""
+    from pysparselp_b200 import _cabi
+
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    x, best, trace, xs, solver = traced(args, 100, 10, flags=_cabi.FLAG_REORDER, **kw)
+    try:
+        y = solver.get_y()
+        T, sigma = solver.get_preconditioners()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        if "alpha" not in kw:
+            assert np.array_equal(x, g["x_100"]) and np.array_equal(y, y_gold) and np.array_equal(T, g["diag_t"])
+        else:
+            assert rel_inf(x, g["x_100"]) <= REL_ITERATE and rel_inf(y, y_gold) <= REL_ITERATE
+        assert_curves_close(trace, g["trace_10"])
+        owned, ghost = solver.layout(columns=True)
+        assert ghost.size == 0 and np.array_equal(np.sort(owned), np.arange(args[0].size))
+    finally:
+        solver.close()
+
+
+def test_partition_matches_python_restatement():
+    """The row / column order computed on the device equals oracle/partition_oracle.py (world = 1)."""
+    from oracle import partition_oracle as po
+    from pysparselp_b200 import _cabi, generators
+    from pysparselp_b200.ChambollePockPPD import make_solver
+
+    for lp, m_eq in ((generators.potts_lp(40), 0), (generators.random_sparse_lp(700, 900, n_eq=150, seed=4)[0], 150)):
+        solver = make_solver(*generators.lp_args(lp), flags=_cabi.FLAG_REORDER, partition_granule=32)
+        cols, _ = solver.layout(columns=True)
+        rows, _ = solver.layout(columns=False)
+        solver.close()
+        blocks = [a for a in (lp.a_eq, lp.a_ineq) if a is not None]
+        import scipy.sparse as sp
+
+        a = sp.vstack(blocks).tocsr() if len(blocks) > 1 else blocks[0]
+        part = po.partition(a.indptr, a.indices, a.shape[1], m_eq, 1, granule=32)
+        assert np.array_equal(cols, part["col_order"]) and np.array_equal(rows, part["row_order"])
