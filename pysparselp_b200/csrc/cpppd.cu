@@ -39,7 +39,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <climits>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,6 +59,9 @@ constexpr int kRowQ = 7;         // row-pass partial sums per CTA
 constexpr int kStatQ = kColQ + kRowQ;
 constexpr int32_t kEqBit = 0x40000000;   // A^T entries: set when the source row is an equality
 constexpr int32_t kIdxMask = 0x3fffffff;
+// padding entry of a slice: negative, and its masked index is 0 so that a gather the compiler
+// hoists above the `idx >= 0` test still reads a valid address
+constexpr int32_t kPad = INT32_MIN;
 constexpr int kMaxWorld = 64;
 
 thread_local std::string g_create_error;
@@ -65,7 +70,7 @@ struct Sell {
   int64_t nrows = 0, nslices = 0, padded = 0;
   int64_t uniform_width = -1;    // >= 0 when every slice has this width (slice_ptr is then implicit)
   int64_t *slice_ptr = nullptr;  // nslices+1 element offsets
-  int32_t *idx = nullptr;        // padded entries, -1 = padding
+  int32_t *idx = nullptr;        // padded entries, kPad = padding
   double *val = nullptr;
 };
 
@@ -267,9 +272,18 @@ struct Scratch {
     if (!rc) ptrs.push_back(*out);
     return rc;
   }
-  void release(void *p) {
+  // frees now and NULLs the caller's variable: the allocator may hand the same address out again,
+  // so a stale copy of the pointer must never reach release() a second time
+  template <typename T>
+  void release(T *&p) {
+    if (!p) return;
     for (auto &q : ptrs)
-      if (q == p) { dev_free(h, p); q = nullptr; }
+      if (q == (void *)p) {
+        dev_free(h, q);
+        q = nullptr;
+        break;
+      }
+    p = nullptr;
   }
 };
 
@@ -363,7 +377,7 @@ __global__ void k_fill_sell(const int64_t *__restrict__ rowptr, const int32_t *_
       idx[p] = indices[e0 + k];
       val[p] = values[e0 + k];
     } else {
-      idx[p] = -1;
+      idx[p] = kPad;
       val[p] = 0.0;
     }
   }
@@ -706,7 +720,7 @@ k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b
     for (int k = 0; k < width; ++k) {
       const int32_t jc = __ldcs(ip + k * kSlice);
       const double a = __ldcs(vp + k * kSlice);
-      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + jc)));
+      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + (jc & kIdxMask))));
     }
   }
   if (!live) return;
@@ -759,8 +773,9 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
     slice_range(A, s, p0, p1);
     double ax = 0.0, ax4 = 0.0, axb = 0.0, axr = 0.0;
     for (int64_t p = p0 + lane; p < p1; p += kSlice) {
-      const int32_t jc = A.idx[p];
-      if (jc >= 0) {
+      const int32_t jr = A.idx[p];
+      if (jr >= 0) {
+        const int32_t jc = jr & kIdxMask;
         const double a = A.val[p];
         ax = __dadd_rn(ax, __dmul_rn(a, x[jc]));
         ax4 = __dadd_rn(ax4, __dmul_rn(a, x4[jc]));
@@ -1101,7 +1116,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (n) k_invert<<<grid_for(n), kBlock, 0, st>>>(col_order, n, col_pos);
     rs = row_start[me]; re = row_start[me + 1]; cs = col_start[me]; ce = col_start[me + 1];
     tmp.release(rk_a); tmp.release(rk_b); tmp.release(ck_a); tmp.release(ck_b);
-    tmp.release(rov.Alternate()); tmp.release(cov.Alternate());
+    if (row_order == ro_a) tmp.release(ro_b); else tmp.release(ro_a);
+    if (col_order == co_a) tmp.release(co_b); else tmp.release(co_a);
     tmp.release(row_key); tmp.release(col_key); tmp.release(col_len); tmp.release(work);
     // ---- ghosts of this rank
     int32_t *gcol_flag = nullptr, *grow_flag = nullptr;
@@ -1244,18 +1260,19 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     const int64_t lnnz = last - first;
     h->nnz_cols = lnnz;
     if (first) k_subtract_base<<<grid_for(nloc + 1), kBlock, 0, st>>>(lcolptr, nloc + 1, first);
-    tmp.release(keys.Current() == keys_a ? keys_b : keys_a);
+    const uint32_t *sorted_ids = ids.Current();
+    if (keys.Current() == keys_a) tmp.release(keys_b); else tmp.release(keys_a);
     int32_t *t_idx = nullptr;
     double *t_val = nullptr;
     if (int rc = tmp.get(&t_idx, lnnz)) return rc;
     if (int rc = tmp.get(&t_val, lnnz)) return rc;
     if (lnnz) {
       if (reorder) {
-        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(ids.Current(), row_of, values, first, lnnz, row_pos, rs, re,
+        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(sorted_ids, row_of, values, first, lnnz, row_pos, rs, re,
                                                              grow_scan, m_eq, t_idx, t_val);
       } else {
         // identity layout: row_pos / grow_scan do not exist; local row == original row
-        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(ids.Current(), row_of, values, first, lnnz, nullptr, 0,
+        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(sorted_ids, row_of, values, first, lnnz, nullptr, 0,
                                                              (int32_t)m, nullptr, m_eq, t_idx, t_val);
       }
     }
