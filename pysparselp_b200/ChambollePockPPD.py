@@ -379,6 +379,7 @@ def chambolle_pock_ppd(
     flags=0,
     return_solver=False,
     distributed=None,
+    partition_granule=0,
 ):
     """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
 
@@ -410,7 +411,7 @@ def chambolle_pock_ppd(
             pickle.dump({"c": c, "a_eq": a_eq, "beq": beq, "a_ineq": a_in_1s, "b_ineq": b_in_1s,
                          "lb": lb, "ub": ub}, f)
     solver = make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
-                         device=device, flags=flags, distributed=distributed)
+                         device=device, flags=flags, distributed=distributed, partition_granule=partition_granule)
     if solver is None:  # no constraint row: closed form, bare vector (:147-151)
         x = np.zeros_like(lb)
         x[c > 0] = lb[c > 0]

@@ -290,3 +290,20 @@ def test_partition_matches_python_restatement():
         a = sp.vstack(blocks).tocsr() if len(blocks) > 1 else blocks[0]
         part = po.partition(a.indptr, a.indices, a.shape[1], m_eq, 1, granule=32)
         assert np.array_equal(cols, part["col_order"]) and np.array_equal(rows, part["row_order"])
+
+
+@pytest.mark.parametrize("world", [2])
+def test_multi_gpu_parity(world):
+    """Row/column-partitioned solve on `world` GPUs (one process per GPU, NCCL halo exchange)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(here, "dist_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "DIST_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
