@@ -303,7 +303,8 @@ def run_b200(a):
                     "k_dual": {"ms": kd, "algorithmic_GBs": bd / (kd * 1e-3) / 1e9}},
         "iteration": {"algorithmic_bytes": info["bytes_per_iteration_algorithmic"],
                       "effective_GBs": info["bytes_per_iteration_algorithmic"] * its_per_s / 1e9,
-                      "frac_of_peak": info["bytes_per_iteration_algorithmic"] * its_per_s / 1e9 / peak},
+                      "frac_of_peak": info["bytes_per_iteration_algorithmic"] * its_per_s / 1e9 / (peak * world),
+                      "note": "whole job: algorithmic bytes of the full LP x iterations/s, against n_gpus x peak"},
     }
     solver.close()
     del solver
@@ -346,9 +347,13 @@ def run_b200(a):
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
                             "preconditioners on device, iterate, read x back"},
-            "gpu_launches": 2 * a.steps * a.iters_per_step,
+            # k_primal + k_dual per iteration; with N > 1 also the two k_pack halo-staging kernels
+            "gpu_launches": (2 if world == 1 else 4) * a.steps * a.iters_per_step,
             "clocks": clocks.summary(),
-            "problem": {"n": n, "m": m, "nnz": nnz, "build_host_s": round(t_build, 2), "setup_device_s": round(t_setup, 2),
+            "partition": None if world == 1 else {k: info[k] for k in (
+            "n_local", "m_local", "n_ghost", "m_ghost", "nnz_local_rows", "nnz_local_cols",
+            "halo_send_bytes_per_iteration", "partition_granule")},
+        "problem": {"n": n, "m": m, "nnz": nnz, "build_host_s": round(t_build, 2), "setup_device_s": round(t_setup, 2),
                         "device_bytes": info["device_bytes"], "padding_A": info["a_padded_entries"] / nnz,
                         "padding_AT": info["at_padded_entries"] / nnz},
         }
