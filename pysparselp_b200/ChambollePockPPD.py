@@ -230,7 +230,14 @@ class CpPpdSolver:
 
     # -- state ------------------------------------------------------------------------------
     def _get(self, which, size):
-        out = np.empty(size, dtype=np.float64)
+        # large results land in pinned host memory (torch's caching host allocator): the D2H copy
+        # then runs at PCIe speed instead of going through a pageable staging buffer
+        if size >= (1 << 16):
+            import torch
+
+            out = torch.empty(size, dtype=torch.float64, pin_memory=True).numpy()
+        else:
+            out = np.empty(size, dtype=np.float64)
         self._call(self.lib.cpppd_get_vector, which, out.ctypes.data)
         return out
 
