@@ -232,7 +232,9 @@ def workload_config(a):
             "generator": "pysparselp_b200.generators.potts_lp(seed=1, coef_potts=0.5, coef_mul=500)",
             "iters_per_step": a.iters_per_step, "theta": 1, "alpha": 1,
             "l2": "inputs larger than L2 (about 11 GB streamed per iteration vs 126 MB L2); no flush needed",
-            "parallelism": "1 GPU" if a.gpus == 1 else "%d GPUs, row/column strips, halo exchange" % a.gpus}
+            "flags": a.flags,
+            "parallelism": "1 GPU" if a.gpus == 1 else "%d GPUs, owner-computes row/column strips, %s halo exchange" % (
+                a.gpus, "NCCL send/recv" if a.flags & 32 else "peer-memory (NVLink) push-kernel")}
 
 
 # ------------------------------------------------------------------------------------------
@@ -269,7 +271,7 @@ def run_b200(a):
 
     # ---- device-resident timing -------------------------------------------------------------
     t_setup = time.perf_counter()
-    solver = make_solver(*args)
+    solver = make_solver(*args, flags=a.flags)
     t_setup = time.perf_counter() - t_setup
     info = solver.info()
     for _ in range(a.warmup):
@@ -315,7 +317,7 @@ def run_b200(a):
     e2e_value = None
     if a.e2e_steps > 0:
         def one_call():
-            x, best = chambolle_pock_ppd(*args, nb_max_iter=a.e2e_iters, nb_iter_plot=a.e2e_iters)
+            x, best = chambolle_pock_ppd(*args, nb_max_iter=a.e2e_iters, nb_iter_plot=a.e2e_iters, flags=a.flags)
             return x
 
         one_call()  # warm-up (allocator pools, graph instantiation)
@@ -384,6 +386,7 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=500)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0, help="CPPPD_FLAG_* bit mask (8 reorder, 32 NCCL halos instead of peer memory)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":

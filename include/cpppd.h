@@ -69,7 +69,9 @@ enum {
   /* on one GPU: still renumber rows / columns by locality (always done when world_size > 1) */
   CPPPD_FLAG_REORDER = 1u << 3,
   /* world_size > 1: capture the iterations including the NCCL halo exchanges into CUDA graphs */
-  CPPPD_FLAG_GRAPH_COMM = 1u << 4
+  CPPPD_FLAG_GRAPH_COMM = 1u << 4,
+  /* world_size > 1: exchange the halos with NCCL send/recv instead of the peer-memory push kernels */
+  CPPPD_FLAG_NO_P2P = 1u << 5
 };
 
 typedef struct {

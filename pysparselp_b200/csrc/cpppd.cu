@@ -105,6 +105,30 @@ struct Halo {
   double *send_buf = nullptr;   // send_total staging values
 };
 
+// Peer-memory halo exchange (world > 1): the ghost tails of xbar / y live in cudaMalloc'ed memory
+// that every neighbour maps through CUDA IPC; a push kernel stores the halo values straight into the
+// neighbours' ghost slots over NVLink and then raises a per-neighbour flag, a wait kernel spins on
+// the local flags.  No staging buffer, no NCCL call, and the whole iteration is graph-capturable.
+struct PeerPtrs {
+  double *vec[kMaxWorld];
+  unsigned long long *flags[kMaxWorld];
+};
+struct SyncState {
+  unsigned long long push_stamp[2];  // halos pushed so far        ([0] xbar, [1] y)
+  unsigned long long wait_stamp[2];  // halos consumed so far
+  unsigned int ticket[2];            // CTA arrival counter of k_push
+};
+struct P2P {
+  bool active = false;
+  PeerPtrs ptrs[2];                  // [0]: peers' xbar, [1]: peers' y (+ their flag arrays)
+  unsigned long long *flags = nullptr;  // 2 * world stamps written by the peers
+  SyncState *state = nullptr;
+  int32_t *push_peer[2] = {nullptr, nullptr};
+  int64_t *push_dst[2] = {nullptr, nullptr};
+  unsigned long long send_mask[2] = {0, 0}, recv_mask[2] = {0, 0};
+  std::vector<void *> opened, own;
+};
+
 // NCCL is resolved at run time (dlopen) so that the library loads without it on one GPU.
 struct NcclApi {
   void *dl = nullptr;
@@ -163,6 +187,7 @@ struct cpppd_solver {
   int32_t *row_old = nullptr;   // m + ghosts : original row id of a local row
   Halo hx, hy;                  // xbar-like vectors (columns) / y-like vectors (rows)
   ncclComm_t comm = nullptr;
+  P2P p2p;
   double alpha = 1, theta = 1, one_plus_theta = 2;
   uint32_t flags = 0;
   int64_t granule = 0;
@@ -878,6 +903,50 @@ __global__ void k_init_stats(StatsDev *st) {
   st->s.best_integer_energy = INFINITY;  // :192
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Halo push over peer memory: entry k of the send list goes to peer push_peer[k], element
+// push_dst[k] of that peer's vector (its ghost slot).  The last CTA to finish raises, on every
+// neighbour it sent to, the flag [kind * world + me] to the new stamp (release at system scope after
+// every CTA fenced its stores).
+__global__ void __launch_bounds__(kBlock)
+k_push(const double *__restrict__ vec, const int32_t *__restrict__ src, const int64_t *__restrict__ dst,
+       const int32_t *__restrict__ peer, int64_t count, PeerPtrs P, int kind, int world, int me,
+       unsigned long long send_mask, SyncState *st) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k < count) P.vec[peer[k]][dst[k]] = vec[src[k]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const unsigned int ticket = atomicAdd(&st->ticket[kind], 1u);
+  if (ticket != gridDim.x - 1) return;
+  __threadfence_system();
+  st->ticket[kind] = 0;
+  const unsigned long long stamp = st->push_stamp[kind] + 1;
+  st->push_stamp[kind] = stamp;
+  for (int t = 0; t < world; ++t)
+    if ((send_mask >> t) & 1ull) st_release_sys(P.flags[t] + kind * world + me, stamp);
+}
+
+// Wait until every neighbour this rank receives from has pushed its halo for this exchange.
+__global__ void k_wait(const unsigned long long *__restrict__ flags, int kind, int world,
+                       unsigned long long recv_mask, SyncState *st) {
+  const int t = threadIdx.x;
+  const unsigned long long want = st->wait_stamp[kind] + 1;
+  if (t < world && ((recv_mask >> t) & 1ull)) {
+    while (ld_acquire_sys(flags + kind * world + t) < want) __nanosleep(200);
+  }
+  __syncthreads();
+  if (t == 0) st->wait_stamp[kind] = want;
+}
+
 // halo staging: buf[k] = vec[idx[k]]
 __global__ void k_pack(const double *__restrict__ vec, const int32_t *__restrict__ idx, int64_t count,
                        double *__restrict__ buf) {
@@ -989,6 +1058,105 @@ int upload_local(cpppd_solver *h, Scratch &tmp, const double *host_full, int64_t
   if (local_count) k_gather_f64<<<grid_for(local_count), kBlock, 0, h->stream>>>(full, map, local_count, dst);
   CK(cudaStreamSynchronize(h->stream));
   tmp.release(full);
+  return 0;
+}
+
+// What every rank publishes so that its neighbours can write into its ghost slots.
+struct PeerRecord {
+  cudaIpcMemHandle_t xbar, y, flags;
+  int64_t owned_x, owned_y;
+  int64_t recv_off_x[kMaxWorld], recv_off_y[kMaxWorld];
+};
+
+int setup_p2p(cpppd_solver *h) {
+  const int N = h->world, me = h->rank;
+  P2P &pp = h->p2p;
+  cudaStream_t st = h->stream;
+  CK(cudaMalloc(&pp.flags, sizeof(unsigned long long) * 2 * N));
+  pp.own.push_back(pp.flags);
+  CK(cudaMalloc(&pp.state, sizeof(SyncState)));
+  pp.own.push_back(pp.state);
+  CK(cudaMemsetAsync(pp.flags, 0, sizeof(unsigned long long) * 2 * N, st));
+  CK(cudaMemsetAsync(pp.state, 0, sizeof(SyncState), st));
+  PeerRecord mine;
+  memset(&mine, 0, sizeof mine);
+  CK(cudaIpcGetMemHandle(&mine.xbar, h->xbar));
+  CK(cudaIpcGetMemHandle(&mine.y, h->y));
+  CK(cudaIpcGetMemHandle(&mine.flags, pp.flags));
+  mine.owned_x = h->hx.owned;
+  mine.owned_y = h->hy.owned;
+  for (int t = 0; t < N; ++t) {
+    mine.recv_off_x[t] = h->hx.recv_off[t];
+    mine.recv_off_y[t] = h->hy.recv_off[t];
+  }
+  // all-gather the records (NCCL, setup only)
+  Scratch tmp(h);
+  char *send = nullptr, *recv = nullptr;
+  if (int rc = tmp.get(&send, (int64_t)sizeof(PeerRecord))) return rc;
+  if (int rc = tmp.get(&recv, (int64_t)sizeof(PeerRecord) * N)) return rc;
+  CK(cudaMemcpyAsync(send, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllGather(send, recv, sizeof(PeerRecord), ncclInt8, h->comm, st));
+  std::vector<PeerRecord> all(N);
+  CK(cudaMemcpyAsync(all.data(), recv, sizeof(PeerRecord) * N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // map the neighbours' vectors
+  memset(pp.ptrs, 0, sizeof pp.ptrs);
+  for (int t = 0; t < N; ++t) {
+    if (t == me) continue;
+    const bool nb = h->hx.send_count[t] || h->hx.recv_count[t] || h->hy.send_count[t] || h->hy.recv_count[t];
+    if (!nb) continue;
+    void *px = nullptr, *py = nullptr, *pf = nullptr;
+    cudaError_t e1 = cudaIpcOpenMemHandle(&px, all[t].xbar, cudaIpcMemLazyEnablePeerAccess);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&py, all[t].y, cudaIpcMemLazyEnablePeerAccess) : e1;
+    cudaError_t e3 = e2 == cudaSuccess ? cudaIpcOpenMemHandle(&pf, all[t].flags, cudaIpcMemLazyEnablePeerAccess) : e2;
+    if (e3 != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, CPPPD_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (use CPPPD_FLAG_NO_P2P for the NCCL path)",
+                  t, cudaGetErrorString(e3));
+    }
+    pp.opened.insert(pp.opened.end(), {px, py, pf});
+    pp.ptrs[0].vec[t] = (double *)px;
+    pp.ptrs[1].vec[t] = (double *)py;
+    pp.ptrs[0].flags[t] = pp.ptrs[1].flags[t] = (unsigned long long *)pf;
+  }
+  // per-entry destinations of the two send lists
+  for (int kind = 0; kind < 2; ++kind) {
+    Halo &H = kind ? h->hy : h->hx;
+    std::vector<int32_t> peer(H.send_total);
+    std::vector<int64_t> dst(H.send_total);
+    for (int t = 0; t < N; ++t) {
+      if (H.send_count[t]) pp.send_mask[kind] |= 1ull << t;
+      if (H.recv_count[t]) pp.recv_mask[kind] |= 1ull << t;
+      const int64_t base = (kind ? all[t].owned_y : all[t].owned_x) + (kind ? all[t].recv_off_y[me] : all[t].recv_off_x[me]);
+      for (int64_t k = 0; k < H.send_count[t]; ++k) {
+        peer[H.send_off[t] + k] = t;
+        dst[H.send_off[t] + k] = base + k;
+      }
+    }
+    if (int rc = alloc_array(h, &pp.push_peer[kind], H.send_total)) return rc;
+    if (int rc = alloc_array(h, &pp.push_dst[kind], H.send_total)) return rc;
+    if (H.send_total) {
+      CK(cudaMemcpy(pp.push_peer[kind], peer.data(), sizeof(int32_t) * H.send_total, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pp.push_dst[kind], dst.data(), sizeof(int64_t) * H.send_total, cudaMemcpyHostToDevice));
+    }
+  }
+  // nobody may push before every rank has initialised its vectors and flags
+  NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
+  CK(cudaStreamSynchronize(st));
+  pp.active = true;
+  return 0;
+}
+
+// xbar (kind 0) / y (kind 1) halo over peer memory: push mine, then wait for the neighbours'.
+int exchange_p2p(cpppd_solver *h, int kind) {
+  P2P &pp = h->p2p;
+  Halo &H = kind ? h->hy : h->hx;
+  const double *vec = kind ? h->y : h->xbar;
+  if (H.send_total)
+    k_push<<<grid_for(H.send_total), kBlock, 0, h->stream>>>(vec, H.send_idx, pp.push_dst[kind], pp.push_peer[kind],
+                                                            H.send_total, pp.ptrs[kind], kind, h->world, h->rank,
+                                                            pp.send_mask[kind], pp.state);
+  if (pp.recv_mask[kind]) k_wait<<<1, kMaxWorld, 0, h->stream>>>(pp.flags, kind, h->world, pp.recv_mask[kind], pp.state);
   return 0;
 }
 
@@ -1285,11 +1453,21 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   // ---- vectors in local layout
   for (double **v : {&h->c, &h->T, &h->lb, &h->ub, &h->best})
     if (int rc = alloc_array(h, v, nloc)) return rc;
-  for (double **v : {&h->x, &h->xbar, &h->dbuf})
+  const bool want_p2p = N > 1 && !(h->flags & CPPPD_FLAG_NO_P2P);
+  for (double **v : {&h->x, &h->dbuf})
     if (int rc = alloc_array(h, v, nloc + n_ghost)) return rc;
   for (double **v : {&h->b, &h->sigma})
     if (int rc = alloc_array(h, v, mloc)) return rc;
-  if (int rc = alloc_array(h, &h->y, mloc + m_ghost)) return rc;
+  if (want_p2p) {  // the two vectors with peer-written ghost tails: plain cudaMalloc, exportable by IPC
+    CK(cudaMalloc(&h->xbar, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1)));
+    h->p2p.own.push_back(h->xbar);
+    CK(cudaMalloc(&h->y, sizeof(double) * std::max<int64_t>(mloc + m_ghost, 1)));
+    h->p2p.own.push_back(h->y);
+    h->device_bytes += 8 * (nloc + n_ghost + mloc + m_ghost);
+  } else {
+    if (int rc = alloc_array(h, &h->xbar, nloc + n_ghost)) return rc;
+    if (int rc = alloc_array(h, &h->y, mloc + m_ghost)) return rc;
+  }
   if (int rc = upload_local(h, tmp, P->c, n, h->col_old, nloc, h->c)) return rc;
   if (int rc = upload_local(h, tmp, P->lb, n, h->col_old, nloc, h->lb)) return rc;
   if (int rc = upload_local(h, tmp, P->ub, n, h->col_old, nloc, h->ub)) return rc;
@@ -1321,6 +1499,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   memset(h->stats_host, 0, sizeof(cpppd_stats));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
+  if (want_p2p)
+    if (int rc = setup_p2p(h)) return rc;
   return 0;
 }
 
@@ -1349,13 +1529,13 @@ int launch_primal(cpppd_solver *h, bool write_d) {
       k_primal<false><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
                                                       h->n, has_eq, has_ineq, h->theta, h->one_plus_theta);
   }
-  return exchange(h, h->xbar, h->hx);
+  return h->p2p.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
 }
 
 int launch_dual(cpppd_solver *h) {
   if (h->A.nslices)
     k_dual<<<grid_for(h->A.nslices * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->b, h->sigma, h->y, h->m, h->m_eq);
-  return exchange(h, h->y, h->hy);
+  return h->p2p.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
 }
 
 int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
@@ -1383,7 +1563,7 @@ int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
 }
 
 int run_iterations(cpppd_solver *h, int64_t k) {
-  const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH) && (h->world == 1 || (h->flags & CPPPD_FLAG_GRAPH_COMM));
+  const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH) && (h->world == 1 || h->p2p.active || (h->flags & CPPPD_FLAG_GRAPH_COMM));
   while (k > 0) {
     int64_t step = std::min<int64_t>(k, kGraphChunk);
     if (use_graph && step >= 2) {
@@ -1552,6 +1732,13 @@ int cpppd_destroy(cpppd_handle h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->p2p.active && h->comm && !h->sticky) {
+    // neighbours may still be storing into this rank's ghost slots: rendezvous before unmapping
+    if (g_nccl.AllReduce(h->p2p.flags, h->p2p.flags, 1, ncclInt8, ncclSum, h->comm, h->stream) == ncclSuccess)
+      cudaStreamSynchronize(h->stream);
+  }
+  for (void *p : h->p2p.opened) cudaIpcCloseMemHandle(p);
+  for (void *p : h->p2p.own) cudaFree(p);
   if (h->comm) g_nccl.CommDestroy(h->comm);
   for (void *p : h->owned) dev_free(h, p);
   if (h->stats_host) cudaFreeHost(h->stats_host);
