@@ -66,12 +66,15 @@ enum {
   CPPPD_FLAG_CONST_VECTORS = 1u << 1,
   /* do not capture the inner iterations into CUDA graphs */
   CPPPD_FLAG_NO_GRAPH = 1u << 2,
-  /* on one GPU: still renumber rows / columns by locality (always done when world_size > 1) */
+  /* on one GPU: renumber rows / columns by locality and length (always done when world_size > 1;
+   * done automatically on one GPU when SELL-32 would otherwise pad the matrix by more than 15 %) */
   CPPPD_FLAG_REORDER = 1u << 3,
   /* world_size > 1: capture the iterations including the NCCL halo exchanges into CUDA graphs */
   CPPPD_FLAG_GRAPH_COMM = 1u << 4,
   /* world_size > 1: exchange the halos with NCCL send/recv instead of the peer-memory push kernels */
-  CPPPD_FLAG_NO_P2P = 1u << 5
+  CPPPD_FLAG_NO_P2P = 1u << 5,
+  /* one GPU: never renumber, whatever the padding */
+  CPPPD_FLAG_NO_REORDER = 1u << 6
 };
 
 typedef struct {

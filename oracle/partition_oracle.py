@@ -3,7 +3,8 @@
 The reference has no distributed code; the partition is this build's own contract
 ("a pure function of (indptr, indices, N), exposed through the ABI, tested bit-exact
 against a Python restatement").  The CUDA library computes exactly the same integers on the
-device (csrc/cpppd.cu: setup_partition); ``tests/test_partition.py`` compares them.
+device (csrc/cpppd.cu: setup()); ``tests/test_gpu_parity.py::test_partition_matches_python_restatement``
+and ``tests/dist_worker.py`` compare them, ``tests/test_dist_cpu.py`` checks its invariants on CPU.
 
 Definitions (A = [A_eq; A_ineq], m x n, CSR; N ranks; granule G):
   row_key[i] = min column index of row i                (n for an empty row)
@@ -12,8 +13,10 @@ Definitions (A = [A_eq; A_ineq], m x n, CSR; N ranks; granule G):
   work[q]    = nnz of the rows in bucket q + nnz of the columns in bucket q
   owner(q)   = min(N-1, (work before bucket q) * N // total work)
 A row / column belongs to the owner of its bucket.  Rank r keeps its rows in the order
-(equalities first, then inequalities; inside each, by bucket, then by original index) and its
-columns in the order (bucket, original index).
+(equalities first, then inequalities; inside each, by bucket, then by min(length, 4095), then by
+original index) and its columns in the order (bucket, min(length, 4095), original index) — grouping
+equal lengths inside a bucket is the sigma-sorting of SELL-C-sigma: slices of 32 neighbours get
+nearly equal widths.
 Ghost columns of rank r: columns owned by another rank that appear in r's rows; ghost rows:
 rows owned by another rank that hit r's columns.  Both are listed by (owner, local position).
 """
@@ -68,8 +71,8 @@ def partition(indptr, indices, n, m_eq, world, granule=None, reorder=True):
         owner_of_bucket = np.zeros(nb, dtype=np.int64)
     row_owner, col_owner = owner_of_bucket[rq], owner_of_bucket[cq]
     is_ineq = (np.arange(m) >= m_eq).astype(np.int64)
-    row_order = np.lexsort((np.arange(m), rq, is_ineq, row_owner))
-    col_order = np.lexsort((np.arange(n), cq, col_owner))
+    row_order = np.lexsort((np.arange(m), np.minimum(lens, 4095), rq, is_ineq, row_owner))
+    col_order = np.lexsort((np.arange(n), np.minimum(col_lens, 4095), cq, col_owner))
     row_start = np.concatenate(([0], np.cumsum(np.bincount(row_owner, minlength=world))))
     col_start = np.concatenate(([0], np.cumsum(np.bincount(col_owner, minlength=world))))
     m_eq_local = np.bincount(row_owner[:m_eq], minlength=world)

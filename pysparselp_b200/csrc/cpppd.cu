@@ -481,17 +481,40 @@ __global__ void k_bucket_work(const int32_t *__restrict__ key, const int64_t *__
 // sort key of a row / column: (owner, [is_ineq,] bucket); also counts per owner
 __global__ void k_sort_keys(const int32_t *__restrict__ key, int64_t count, int32_t granule,
                             const int32_t *__restrict__ owner_of_bucket, int64_t m_eq, int is_rows,
+                            const int64_t *__restrict__ rowptr, const int32_t *__restrict__ len32,
                             uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_id,
                             int32_t *__restrict__ count_per_owner, int32_t *__restrict__ eq_per_owner) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   int32_t q = key[i] / granule;
   int32_t o = owner_of_bucket[q];
+  // inside a bucket, rows / columns of equal length sit together (SELL sigma-sorting: slices of
+  // 32 neighbours then have nearly equal widths and little padding)
+  int64_t len = rowptr ? rowptr[i + 1] - rowptr[i] : (int64_t)len32[i];
+  uint64_t len12 = (uint64_t)(len > 4095 ? 4095 : len);
   uint64_t major = is_rows ? (uint64_t)o * 2 + (i >= m_eq ? 1 : 0) : (uint64_t)o;
-  out_key[i] = (major << 32) | (uint32_t)q;
+  out_key[i] = (major << 44) | ((uint64_t)(uint32_t)q << 12) | len12;
   out_id[i] = (uint32_t)i;
   atomicAdd(count_per_owner + o, 1);
   if (is_rows && i < m_eq) atomicAdd(eq_per_owner + o, 1);
+}
+
+__global__ void k_col_len(const int32_t *__restrict__ indices, int64_t nnz, int32_t *__restrict__ col_len) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nnz) atomicAdd(col_len + indices[e], 1);
+}
+
+// total[0] += 32 * (longest row of each slice of 32 consecutive rows)
+__global__ void k_padded_total(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ len32, int64_t nrows,
+                               unsigned long long *__restrict__ total) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int lane = threadIdx.x & 31;
+  if (r - lane >= nrows) return;
+  long long len = 0;
+  if (r < nrows) len = rowptr ? rowptr[r + 1] - rowptr[r] : (long long)len32[r];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0 && len) atomicAdd(total, (unsigned long long)len * kSlice);
 }
 
 __global__ void k_invert(const uint32_t *__restrict__ order, int64_t count, int32_t *__restrict__ pos) {
@@ -1203,7 +1226,25 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   if (int rc = tmp.get(&entry_id, nnz)) return rc;
   if (nnz) k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, entry_id);
 
-  const bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
+  bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
+  if (!reorder && nnz && !(h->flags & CPPPD_FLAG_NO_REORDER)) {
+    // keep the caller's numbering unless SELL-32 would pad it by more than 15 %: then renumber
+    // (rows / columns of equal length are grouped inside locality buckets)
+    int32_t *col_len = nullptr;
+    unsigned long long *total = nullptr, total_h = 0;
+    if (int rc = tmp.get(&col_len, n)) return rc;
+    if (int rc = tmp.get(&total, 1)) return rc;
+    CK(cudaMemsetAsync(col_len, 0, sizeof(int32_t) * std::max<int64_t>(n, 1), st));
+    CK(cudaMemsetAsync(total, 0, sizeof(unsigned long long), st));
+    k_col_len<<<grid_for(nnz), kBlock, 0, st>>>(indices, nnz, col_len);
+    if (m) k_padded_total<<<grid_for(((m + 31) / 32) * 32), kBlock, 0, st>>>(rowptr, nullptr, m, total);
+    if (n) k_padded_total<<<grid_for(((n + 31) / 32) * 32), kBlock, 0, st>>>(nullptr, col_len, n, total);
+    CK(cudaMemcpyAsync(&total_h, total, sizeof total_h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    tmp.release(col_len);
+    tmp.release(total);
+    reorder = (double)total_h > 1.15 * 2.0 * (double)nnz;
+  }
   h->identity_layout = !reorder;
   int32_t rs = 0, re = (int32_t)m, cs = 0, ce = (int32_t)n;
   int64_t n_ghost = 0, m_ghost = 0;
@@ -1262,9 +1303,9 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = tmp.get(&co_a, n)) return rc;
     if (int rc = tmp.get(&co_b, n)) return rc;
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * N, st));
-    if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rk_a, ro_a, counts, counts + N);
-    if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, ck_a, co_a, counts + 2 * N, nullptr);
-    const int end_bit = 32 + bits_for((uint64_t)2 * N + 1);
+    if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rowptr, nullptr, rk_a, ro_a, counts, counts + N);
+    if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, nullptr, col_len, ck_a, co_a, counts + 2 * N, nullptr);
+    const int end_bit = 44 + bits_for((uint64_t)2 * N + 1);
     cub::DoubleBuffer<uint64_t> rk(rk_a, rk_b), ck(ck_a, ck_b);
     cub::DoubleBuffer<uint32_t> rov(ro_a, ro_b), cov(co_a, co_b);
     if (int rc = sort_pairs(h, rk, rov, m, end_bit)) return rc;
