@@ -71,7 +71,11 @@ struct Sell {
   int64_t uniform_width = -1;    // >= 0 when every slice has this width (slice_ptr is then implicit)
   int64_t *slice_ptr = nullptr;  // nslices+1 element offsets
   int32_t *idx = nullptr;        // padded entries, kPad = padding
-  double *val = nullptr;
+  double *val = nullptr;         // nullptr in dictionary mode
+  // dictionary mode (CPPPD_FLAG_VALUE_DICT): the matrix takes <= 256 distinct values; an entry is one
+  // 32-bit word  [pad:1][eq:1][code][index]  and its value is dict[code] (the exact original double)
+  const double *dict = nullptr;
+  int idx_bits = 30, ndict = 0;
 };
 
 struct SellView {
@@ -80,6 +84,16 @@ struct SellView {
   const double *__restrict__ val;
   int64_t nrows, nslices;
   int64_t uniform_width;  // -1: read slice_ptr
+  const double *__restrict__ dict;
+  int32_t idx_mask;       // low bits of an entry word that hold the gather index
+  int32_t idx_bits, code_mask, ndict;
+};
+
+// a vector operand that may have been folded into a scalar (CPPPD_FLAG_CONST_VECTORS)
+struct Vec {
+  const double *p;
+  double c;
+  __device__ __forceinline__ double at(int64_t i) const { return p ? __ldcs(p + i) : c; }
 };
 
 // first / one-past-last element offset of slice s
@@ -91,6 +105,11 @@ __device__ __forceinline__ void slice_range(const SellView &S, int64_t s, int64_
     p0 = __ldg(S.slice_ptr + s);
     p1 = __ldg(S.slice_ptr + s + 1);
   }
+}
+
+// value of the entry stored at position p whose index word is w (non-hot kernels)
+__device__ __forceinline__ double entry_value(const SellView &S, int64_t p, int32_t w) {
+  return S.dict ? S.dict[(w >> S.idx_bits) & S.code_mask] : S.val[p];
 }
 
 struct StatsDev {  // device-resident, copied verbatim into cpppd_stats
@@ -199,6 +218,10 @@ struct cpppd_solver {
   Sell A, AT;
   double *c = nullptr, *T = nullptr, *lb = nullptr, *ub = nullptr, *x = nullptr, *xbar = nullptr;
   double *b = nullptr, *sigma = nullptr, *y = nullptr, *dbuf = nullptr, *best = nullptr;
+  Vec vc{nullptr, 0}, vT{nullptr, 0}, vlb{nullptr, 0}, vub{nullptr, 0}, vb{nullptr, 0}, vsigma{nullptr, 0};
+  int const_mask = 0;               // bit0 b, bit1 sigma, bit2 lb, bit3 ub, bit4 c, bit5 T folded to scalars
+  unsigned long long *dict = nullptr;  // sorted bit patterns of the distinct matrix values (dictionary mode)
+  int ndict = 0;
   double *colpart = nullptr, *rowpart = nullptr, *xr_scratch = nullptr;
   double *stat_local = nullptr, *stat_all = nullptr;  // kStatQ / world*kStatQ
   int stat_blocks_c = 0, stat_blocks_r = 0;
@@ -380,11 +403,26 @@ __global__ void k_slice_extent(const int64_t *__restrict__ rowptr, int64_t nrows
   if (lane == 0) extent[s] = len * kSlice;
 }
 
-// one warp per slice: copy CSR entries into the column-major slice, pad with idx = -1
+// position of `v` (compared by bit pattern) in the sorted dictionary, or -1
+__device__ __forceinline__ int dict_find(const unsigned long long *__restrict__ dict, int ndict, double v) {
+  const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+  int lo = 0, hi = ndict - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const unsigned long long d = dict[mid];
+    if (d == key) return mid;
+    if (d < key) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+// one warp per slice: copy CSR entries into the column-major slice, pad with idx = kPad.
+// With a dictionary the value is folded into the index word as a code and `val` is not written.
 __global__ void k_fill_sell(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indices,
                             const double *__restrict__ values, int64_t nrows, int64_t nslices,
                             const int64_t *__restrict__ slice_ptr, int32_t *__restrict__ idx,
-                            double *__restrict__ val) {
+                            double *__restrict__ val, const unsigned long long *__restrict__ dict, int ndict,
+                            int idx_bits) {
   int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (s >= nslices) return;
@@ -399,13 +437,33 @@ __global__ void k_fill_sell(const int64_t *__restrict__ rowptr, const int32_t *_
   for (int64_t k = 0; k < width; ++k) {
     int64_t p = p0 + k * kSlice + lane;
     if (k < len) {
-      idx[p] = indices[e0 + k];
-      val[p] = values[e0 + k];
+      int32_t w = indices[e0 + k];
+      if (dict) {
+        const int code = dict_find(dict, ndict, values[e0 + k]);
+        w = (w & kEqBit) | (w & ((1 << idx_bits) - 1)) | (code << idx_bits);
+      } else {
+        val[p] = values[e0 + k];
+      }
+      idx[p] = w;
     } else {
       idx[p] = kPad;
-      val[p] = 0.0;
+      if (!dict) val[p] = 0.0;
     }
   }
+}
+
+// flag[0] = 1 when some value is not in the dictionary
+__global__ void k_dict_check(const double *__restrict__ values, int64_t nnz, const unsigned long long *__restrict__ dict,
+                             int ndict, int *__restrict__ flag) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+    if (dict_find(dict, ndict, values[e]) < 0) *flag = 1;
+}
+
+// flag[0] = 1 when some element differs (bitwise) from the first one
+__global__ void k_not_constant(const double *__restrict__ v, int64_t count, int *__restrict__ flag) {
+  const long long first = __double_as_longlong(v[0]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    if (__double_as_longlong(v[i]) != first) *flag = 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -658,7 +716,7 @@ __global__ void k_precond_cols(SellView AT, int64_t n, int has_eq, int has_ineq,
   for (int64_t p = p0 + lane; p < p1; p += kSlice) {
     int32_t r = AT.idx[p];
     if (r >= 0) {
-      double t = __dmul_rn(abs_pow(AT.val[p], power), 1.0);
+      double t = __dmul_rn(abs_pow(entry_value(AT, p, r), power), 1.0);
       if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
     }
   }
@@ -681,7 +739,8 @@ __global__ void k_precond_rows(SellView A, int64_t m, double power, double *__re
   slice_range(A, s, p0, p1);
   double acc = 0.0;
   for (int64_t p = p0 + lane; p < p1; p += kSlice) {
-    if (A.idx[p] >= 0) acc = __dadd_rn(acc, __dmul_rn(abs_pow(A.val[p], power), 1.0));
+    const int32_t w = A.idx[p];
+    if (w >= 0) acc = __dadd_rn(acc, __dmul_rn(abs_pow(entry_value(A, p, w), power), 1.0));
   }
   if (i < m) {
     if (acc == 0.0) acc = 1.0;
@@ -693,14 +752,20 @@ __global__ void k_precond_rows(SellView A, int64_t m, double power, double *__re
 // the two hot kernels
 // ------------------------------------------------------------------------------------------
 // Primal half-iteration (:198-228).  Thread j owns column j of A (row j of A^T).
-// Loads that do not depend on the matrix (c, T, x, lb, ub) are issued first so that they are
-// in flight together with the slice entries; matrix entries are read once (ld.global.cs).
-template <bool kWriteD>
+// Loads that do not depend on the matrix (c, T, x) are issued first so that they are in flight
+// together with the slice entries; matrix entries are read once (ld.global.cs).
+// kDict: entries are single 32-bit words [pad][eq][code][index]; values come from a <= 256 entry
+// dictionary staged in shared memory.
+template <bool kWriteD, bool kDict>
 __global__ void __launch_bounds__(kBlock, 8)
-k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c, const double *__restrict__ T,
-         const double *__restrict__ lb, const double *__restrict__ ub, double *__restrict__ x,
+k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
          double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int has_eq, int has_ineq,
          double theta, double one_plus_theta) {
+  __shared__ double sdict[kDict ? 256 : 1];
+  if (kDict) {
+    if ((int)threadIdx.x < AT.ndict) sdict[threadIdx.x] = AT.dict[threadIdx.x];
+    __syncthreads();
+  }
   const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = j >> 5;
   if (s >= AT.nslices) return;
@@ -710,8 +775,8 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
   const bool live = j < n;
   double cj = 0.0, tj = 0.0, xo = 0.0;
   if (live) {
-    cj = __ldcs(c + j);
-    tj = __ldcs(T + j);
+    cj = c.at(j);
+    tj = T.at(j);
     xo = __ldcs(x + j);
   }
   double s_eq = 0.0, s_in = 0.0;
@@ -719,12 +784,14 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
     const int32_t *ip = AT.idx + p0 + lane;
     const double *vp = AT.val + p0 + lane;
     const int width = (int)((p1 - p0) >> 5);
+    const int32_t mask = AT.idx_mask;
 #pragma unroll 4
     for (int k = 0; k < width; ++k) {
       const int32_t r = __ldcs(ip + k * kSlice);
-      const double a = __ldcs(vp + k * kSlice);
+      double a;
+      if (kDict) a = sdict[(r >> AT.idx_bits) & AT.code_mask]; else a = __ldcs(vp + k * kSlice);
       if (r >= 0) {
-        const double t = __dmul_rn(a, __ldg(y + (r & kIdxMask)));
+        const double t = __dmul_rn(a, __ldg(y + (r & mask)));
         if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
       }
     }
@@ -733,7 +800,7 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
   double d = cj;
   if (has_eq) d = __dadd_rn(d, s_eq);
   if (has_ineq) d = __dadd_rn(d, s_in);
-  const double l = __ldcs(lb + j), u = __ldcs(ub + j);
+  const double l = lb.at(j), u = ub.at(j);
   double x2 = __dsub_rn(xo, __dmul_rn(tj, d));
   x2 = (l > x2) ? l : x2;  // np.maximum(x2, lb)  (NaN in x2 propagates)
   x2 = (u < x2) ? u : x2;  // np.minimum(x2, ub)
@@ -743,9 +810,15 @@ k_primal(SellView AT, const double *__restrict__ y, const double *__restrict__ c
 }
 
 // Dual half-iteration (:231-240, :333-341).  Thread i owns row i of A.
+template <bool kDict>
 __global__ void __launch_bounds__(kBlock, 8)
-k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b,
-       const double *__restrict__ sigma, double *__restrict__ y, int64_t m, int64_t m_eq) {
+k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__restrict__ y, int64_t m,
+       int64_t m_eq) {
+  __shared__ double sdict[kDict ? 256 : 1];
+  if (kDict) {
+    if ((int)threadIdx.x < A.ndict) sdict[threadIdx.x] = A.dict[threadIdx.x];
+    __syncthreads();
+  }
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = i >> 5;
   if (s >= A.nslices) return;
@@ -755,8 +828,8 @@ k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b
   const bool live = i < m;
   double bi = 0.0, si = 0.0, yi = 0.0;
   if (live) {
-    bi = __ldcs(b + i);
-    si = __ldcs(sigma + i);
+    bi = b.at(i);
+    si = sigma.at(i);
     yi = __ldcs(y + i);
   }
   double acc = 0.0;
@@ -764,11 +837,13 @@ k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b
     const int32_t *ip = A.idx + p0 + lane;
     const double *vp = A.val + p0 + lane;
     const int width = (int)((p1 - p0) >> 5);
+    const int32_t mask = A.idx_mask;
 #pragma unroll 4
     for (int k = 0; k < width; ++k) {
       const int32_t jc = __ldcs(ip + k * kSlice);
-      const double a = __ldcs(vp + k * kSlice);
-      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + (jc & kIdxMask))));
+      double a;
+      if (kDict) a = sdict[(jc >> A.idx_bits) & A.code_mask]; else a = __ldcs(vp + k * kSlice);
+      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + (jc & mask))));
     }
   }
   if (!live) return;
@@ -784,13 +859,13 @@ k_dual(SellView A, const double *__restrict__ xbar, const double *__restrict__ b
 // Column pass: c.x, c.x4, c.xr, #(xbar == 0); turns the d buffer into x4 in place and
 // (force_integer) stores xr into xr_out.
 __global__ void __launch_bounds__(kBlock)
-k_stats_cols(const double *__restrict__ c, const double *__restrict__ x, const double *__restrict__ xbar,
-             const double *__restrict__ lb, const double *__restrict__ ub, double *__restrict__ d_x4,
-             double *__restrict__ xr_out, int64_t n, int force_integer, double *__restrict__ part) {
+k_stats_cols(Vec c, const double *__restrict__ x, const double *__restrict__ xbar, Vec lb, Vec ub,
+             double *__restrict__ d_x4, double *__restrict__ xr_out, int64_t n, int force_integer,
+             double *__restrict__ part) {
   double v[kColQ] = {0.0, 0.0, 0.0, 0.0};
   for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < n; j += (int64_t)gridDim.x * kBlock) {
-    const double cj = c[j], xj = x[j];
-    const double x4 = d_x4[j] < 0.0 ? ub[j] : lb[j];  // x4 = lb; x4[d < 0] = ub[d < 0]  (:260-261)
+    const double cj = c.at(j), xj = x[j];
+    const double x4 = d_x4[j] < 0.0 ? ub.at(j) : lb.at(j);  // x4 = lb; x4[d < 0] = ub[d < 0]  (:260-261)
     d_x4[j] = x4;
     double xr = xj;
     if (force_integer) {
@@ -808,7 +883,7 @@ k_stats_cols(const double *__restrict__ c, const double *__restrict__ x, const d
 // Row pass: A x, A x4, A xbar, A xr per row -> energy terms and violation maxima.
 __global__ void __launch_bounds__(kBlock)
 k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict__ x4,
-             const double *__restrict__ xbar, const double *__restrict__ xr, const double *__restrict__ b,
+             const double *__restrict__ xbar, const double *__restrict__ xr, Vec b,
              const double *__restrict__ y, int64_t m, int64_t m_eq, int force_integer,
              double *__restrict__ part) {
   const double ninf = -INFINITY;
@@ -823,8 +898,8 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
     for (int64_t p = p0 + lane; p < p1; p += kSlice) {
       const int32_t jr = A.idx[p];
       if (jr >= 0) {
-        const int32_t jc = jr & kIdxMask;
-        const double a = A.val[p];
+        const int32_t jc = jr & A.idx_mask;
+        const double a = entry_value(A, p, jr);
         ax = __dadd_rn(ax, __dmul_rn(a, x[jc]));
         ax4 = __dadd_rn(ax4, __dmul_rn(a, x4[jc]));
         if (i < m_eq) axb = __dadd_rn(axb, __dmul_rn(a, xbar[jc]));
@@ -833,7 +908,7 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
     }
     if (i < m) {
       if (!force_integer) axr = ax;
-      const double bi = b[i], yi = y[i];
+      const double bi = b.at(i), yi = y[i];
       const double t1 = __dmul_rn(yi, __dsub_rn(ax, bi));
       const double t2 = __dmul_rn(yi, __dsub_rn(ax4, bi));
       if (i < m_eq) {
@@ -980,7 +1055,11 @@ __global__ void k_pack(const double *__restrict__ vec, const int32_t *__restrict
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-SellView view(const Sell &s) { return SellView{s.slice_ptr, s.idx, s.val, s.nrows, s.nslices, s.uniform_width}; }
+SellView view(const Sell &s) {
+  const int code_bits = s.dict ? 30 - s.idx_bits : 0;
+  return SellView{s.slice_ptr, s.idx, s.val, s.nrows, s.nslices, s.uniform_width, s.dict,
+                  s.dict ? (int32_t)((1u << s.idx_bits) - 1) : kIdxMask, s.idx_bits, (int32_t)((1u << code_bits) - 1), s.ndict};
+}
 
 template <typename T>
 int exclusive_scan(cpppd_solver *h, const T *in, T *out, int64_t count) {
@@ -1045,9 +1124,11 @@ int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   CK(cudaStreamSynchronize(h->stream));
   out->uniform_width = (ns && host_mm[0] == host_mm[1]) ? host_mm[0] / kSlice : -1;
   if (int rc = alloc_array(h, &out->idx, out->padded)) return rc;
-  if (int rc = alloc_array(h, &out->val, out->padded)) return rc;
+  if (!out->dict)
+    if (int rc = alloc_array(h, &out->val, out->padded)) return rc;
   if (ns) k_fill_sell<<<grid_for(ns * 32), kBlock, 0, h->stream>>>(rowptr, indices, values, nrows, ns, out->slice_ptr,
-                                                                  out->idx, out->val);
+                                                                  out->idx, out->val, out->dict ? h->dict : nullptr,
+                                                                  h->ndict, out->idx_bits);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -1081,6 +1162,51 @@ int upload_local(cpppd_solver *h, Scratch &tmp, const double *host_full, int64_t
   if (local_count) k_gather_f64<<<grid_for(local_count), kBlock, 0, h->stream>>>(full, map, local_count, dst);
   CK(cudaStreamSynchronize(h->stream));
   tmp.release(full);
+  return 0;
+}
+
+__global__ void k_sample_bits(const double *__restrict__ values, int64_t nnz, int64_t stride, int64_t count,
+                              unsigned long long *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (unsigned long long)__double_as_longlong(values[min(i * stride, nnz - 1)]);
+}
+
+// CPPPD_FLAG_VALUE_DICT: if the matrix takes at most 256 distinct values (bit patterns), keep them,
+// sorted, in h->dict.  Candidates come from a strided sample; a full pass then proves that every
+// entry is covered (otherwise the dictionary is dropped and the generic format is used).
+int detect_dictionary(cpppd_solver *h, Scratch &tmp, const double *values, int64_t nnz) {
+  cudaStream_t st = h->stream;
+  const int64_t count = std::min<int64_t>(nnz, 1 << 20), stride = std::max<int64_t>(1, nnz / count);
+  unsigned long long *a = nullptr, *b = nullptr, *uniq = nullptr;
+  int *num = nullptr, *flag = nullptr;
+  if (int rc = tmp.get(&a, count)) return rc;
+  if (int rc = tmp.get(&b, count)) return rc;
+  if (int rc = tmp.get(&uniq, count)) return rc;
+  if (int rc = tmp.get(&num, 1)) return rc;
+  if (int rc = tmp.get(&flag, 1)) return rc;
+  k_sample_bits<<<grid_for(count), kBlock, 0, st>>>(values, nnz, stride, count, a);
+  size_t b1 = 0, b2 = 0;
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, b1, a, b, count, 0, 64, st));
+  CK(cub::DeviceSelect::Unique(nullptr, b2, b, uniq, num, count, st));
+  char *ws = nullptr;
+  if (int rc = tmp.get(&ws, (int64_t)std::max(b1, b2))) return rc;
+  CK(cub::DeviceRadixSort::SortKeys(ws, b1, a, b, count, 0, 64, st));
+  CK(cub::DeviceSelect::Unique(ws, b2, b, uniq, num, count, st));
+  int num_h = 0;
+  CK(cudaMemcpyAsync(&num_h, num, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (num_h >= 1 && num_h <= 256) {
+    if (int rc = alloc_array(h, &h->dict, 256)) return rc;
+    CK(cudaMemsetAsync(h->dict, 0, sizeof(unsigned long long) * 256, st));
+    CK(cudaMemcpyAsync(h->dict, uniq, sizeof(unsigned long long) * num_h, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    k_dict_check<<<std::min(grid_for(nnz), h->sm_count * 16), kBlock, 0, st>>>(values, nnz, h->dict, num_h, flag);
+    int miss = 0;
+    CK(cudaMemcpyAsync(&miss, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (miss) h->dict = nullptr; else h->ndict = num_h;
+  }
+  tmp.release(a); tmp.release(b); tmp.release(uniq); tmp.release(num); tmp.release(flag); tmp.release(ws);
   return 0;
 }
 
@@ -1221,6 +1347,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (host_flag & 1) return fail(h, CPPPD_ERR_INVALID, "indptr is not non-decreasing");
     if (host_flag & 2) return fail(h, CPPPD_ERR_INVALID, "column index outside [0, n)");
   }
+  if ((h->flags & CPPPD_FLAG_VALUE_DICT) && nnz)
+    if (int rc = detect_dictionary(h, tmp, values, nnz)) return rc;
   uint32_t *row_of = nullptr, *entry_id = nullptr;
   if (int rc = tmp.get(&row_of, nnz)) return rc;
   if (int rc = tmp.get(&entry_id, nnz)) return rc;
@@ -1422,6 +1550,20 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   h->hy.owned = mloc;
   h->hy.ghost = m_ghost;
 
+  if (h->dict) {  // an entry word must hold index + code below the eq / pad bits
+    const int idx_bits = bits_for((uint64_t)std::max<int64_t>(std::max(nloc + n_ghost, mloc + m_ghost), 2) - 1);
+    const int code_bits = bits_for((uint64_t)std::max(h->ndict, 2) - 1);
+    if (idx_bits + code_bits <= 30) {
+      for (Sell *S : {&h->A, &h->AT}) {
+        S->dict = reinterpret_cast<const double *>(h->dict);
+        S->idx_bits = idx_bits;
+        S->ndict = h->ndict;
+      }
+    } else {
+      h->dict = nullptr;  // (stays allocated, simply unused)
+      h->ndict = 0;
+    }
+  }
   // ---- this rank's rows of A -> SELL-32
   if (!reorder) {
     h->nnz_rows = nnz;
@@ -1527,6 +1669,33 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     k_precond_cols<<<grid_for(h->AT.nslices * 32), kBlock, 0, st>>>(view(h->AT), nloc, has_eq, has_ineq, 2.0 - h->alpha, h->T);
   if (h->A.nslices)
     k_precond_rows<<<grid_for(h->A.nslices * 32), kBlock, 0, st>>>(view(h->A), mloc, h->alpha, h->sigma);
+  h->vc = Vec{h->c, 0};
+  h->vT = Vec{h->T, 0};
+  h->vlb = Vec{h->lb, 0};
+  h->vub = Vec{h->ub, 0};
+  h->vb = Vec{h->b, 0};
+  h->vsigma = Vec{h->sigma, 0};
+  if (h->flags & CPPPD_FLAG_CONST_VECTORS) {
+    struct { Vec *v; double *p; int64_t count; int bit; } cand[] = {
+        {&h->vb, h->b, mloc, 0}, {&h->vsigma, h->sigma, mloc, 1}, {&h->vlb, h->lb, nloc, 2},
+        {&h->vub, h->ub, nloc, 3}, {&h->vc, h->c, nloc, 4},      {&h->vT, h->T, nloc, 5}};
+    int *flag = nullptr;
+    if (int rc = tmp.get(&flag, 1)) return rc;
+    for (auto &cd : cand) {
+      if (cd.count == 0) continue;
+      int host_flag = 0;
+      CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      k_not_constant<<<std::min(grid_for(cd.count), h->sm_count * 8), kBlock, 0, st>>>(cd.p, cd.count, flag);
+      CK(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      double first = 0;
+      CK(cudaMemcpyAsync(&first, cd.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (!host_flag) {
+        *cd.v = Vec{nullptr, first};
+        h->const_mask |= 1 << cd.bit;
+      }
+    }
+  }
   // ---- stats plumbing
   h->stat_blocks_c = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(nloc), (int64_t)h->sm_count * 8));
   h->stat_blocks_r = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(h->A.nslices * 32), (int64_t)h->sm_count * 8));
@@ -1559,23 +1728,31 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
   return 0;
 }
 
+template <bool kWriteD, bool kDict>
+void launch_primal_t(cpppd_solver *h) {
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  k_primal<kWriteD, kDict><<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(
+      view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
+      h->one_plus_theta);
+}
+
 int launch_primal(cpppd_solver *h, bool write_d) {
   if (h->AT.nslices) {
-    const int grid = grid_for(h->AT.nslices * 32);
-    const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-    if (write_d)
-      k_primal<true><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
-                                                     h->n, has_eq, has_ineq, h->theta, h->one_plus_theta);
-    else
-      k_primal<false><<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->c, h->T, h->lb, h->ub, h->x, h->xbar, h->dbuf,
-                                                      h->n, has_eq, has_ineq, h->theta, h->one_plus_theta);
+    const bool dict = h->AT.dict != nullptr;
+    if (write_d) dict ? launch_primal_t<true, true>(h) : launch_primal_t<true, false>(h);
+    else dict ? launch_primal_t<false, true>(h) : launch_primal_t<false, false>(h);
   }
   return h->p2p.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
 }
 
 int launch_dual(cpppd_solver *h) {
-  if (h->A.nslices)
-    k_dual<<<grid_for(h->A.nslices * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->b, h->sigma, h->y, h->m, h->m_eq);
+  if (h->A.nslices) {
+    const int grid = grid_for(h->A.nslices * 32);
+    if (h->A.dict)
+      k_dual<true><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+    else
+      k_dual<false><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+  }
   return h->p2p.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
 }
 
@@ -1818,14 +1995,14 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
       if (int rc = alloc_array(h, &h->xr_scratch, h->n + h->hx.ghost)) return rc;
     xr = h->xr_scratch;
   }
-  k_stats_cols<<<h->stat_blocks_c, kBlock, 0, h->stream>>>(h->c, h->x, h->xbar, h->lb, h->ub, h->dbuf, xr, h->n,
+  k_stats_cols<<<h->stat_blocks_c, kBlock, 0, h->stream>>>(h->vc, h->x, h->xbar, h->vlb, h->vub, h->dbuf, xr, h->n,
                                                           force_integer, h->colpart);
   // the row pass reads x, x4 and xr at ghost columns too
   if (int rc = exchange(h, h->x, h->hx)) return rc;
   if (int rc = exchange(h, h->dbuf, h->hx)) return rc;
   if (force_integer)
     if (int rc = exchange(h, xr, h->hx)) return rc;
-  k_stats_rows<<<h->stat_blocks_r, kBlock, 0, h->stream>>>(view(h->A), h->x, h->dbuf, h->xbar, xr, h->b, h->y, h->m,
+  k_stats_rows<<<h->stat_blocks_r, kBlock, 0, h->stream>>>(view(h->A), h->x, h->dbuf, h->xbar, xr, h->vb, h->y, h->m,
                                                           h->m_eq, force_integer, h->rowpart);
   k_stats_local<<<1, kBlock, 0, h->stream>>>(h->colpart, h->stat_blocks_c, h->rowpart, h->stat_blocks_r, h->stat_local);
   const double *all = h->stat_local;
@@ -1970,12 +2147,17 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   const int64_t P = h->nnz_glob >= ((int64_t)1 << 31) ? 8 : 4;
   out->bytes_per_iteration_algorithmic =
       2 * h->nnz_glob * 12 + P * (h->m_glob + 1) + P * (h->n_glob + 1) + 8 * (8 * h->n_glob + 5 * h->m_glob);
-  out->bytes_per_iteration_actual = (h->A.padded + h->AT.padded) * 12 +
+  const int64_t entry_bytes = h->A.dict ? 4 : 12;
+  int64_t vec_bytes = 8 * (3 * h->n + 2 * h->m);  // x read+write, xbar write, y read+write
+  vec_bytes += 8 * (h->n + h->hx.ghost + h->m + h->hy.ghost);  // xbar / y gathered once
+  const int64_t per_elem[6] = {h->m, h->m, h->n, h->n, h->n, h->n};
+  for (int bit = 0; bit < 6; ++bit)
+    if (!((h->const_mask >> bit) & 1)) vec_bytes += 8 * per_elem[bit];
+  out->bytes_per_iteration_actual = (h->A.padded + h->AT.padded) * entry_bytes +
                                     (h->A.uniform_width >= 0 ? 0 : 8 * (h->A.nslices + 1)) +
-                                    (h->AT.uniform_width >= 0 ? 0 : 8 * (h->AT.nslices + 1)) + 8 * (8 * h->n + 5 * h->m) +
-                                    8 * (h->hx.ghost + h->hy.ghost);
-  out->value_bytes = 8;
-  out->const_vector_mask = 0;
+                                    (h->AT.uniform_width >= 0 ? 0 : 8 * (h->AT.nslices + 1)) + vec_bytes;
+  out->value_bytes = h->A.dict ? 0 : 8;
+  out->const_vector_mask = h->const_mask;
   out->sm_count = h->sm_count;
   out->world_size = h->world;
   out->rank = h->rank;

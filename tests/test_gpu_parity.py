@@ -307,3 +307,36 @@ def test_multi_gpu_parity(world):
            "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(here, "dist_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "DIST_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_lossless_compression_keeps_iterates_bit_identical(name):
+    """CPPPD_FLAG_VALUE_DICT | CPPPD_FLAG_CONST_VECTORS change the storage, not a single bit of the
+    arithmetic: dictionary entries are the original doubles, folded vectors were constant."""
+    from pysparselp_b200 import _cabi
+
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    flags = _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS
+    x, best, trace, xs, solver = traced(args, 100, 10, flags=flags, **kw)
+    try:
+        info = solver.info()
+        y = solver.get_y()
+        T, sigma = solver.get_preconditioners()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        if "alpha" not in kw:
+            assert np.array_equal(x, g["x_100"]) and np.array_equal(y, y_gold) and np.array_equal(T, g["diag_t"])
+        else:
+            assert rel_inf(x, g["x_100"]) <= REL_ITERATE and rel_inf(y, y_gold) <= REL_ITERATE
+        assert_curves_close(trace, g["trace_10"])
+        if name == "potts50":  # values are +-1, b / sigma / lb / ub are constant vectors
+            assert info["value_bytes"] == 0 and (info["const_vector_mask"] & 0xF) == 0xF
+        if name == "random_small":  # hundreds of distinct values: the generic format must be kept
+            assert info["value_bytes"] == 8
+    finally:
+        solver.close()
+    x, best, trace, xs, solver = traced(args, 300, 20, force_integer=True, flags=flags | _cabi.FLAG_REORDER, **kw)
+    solver.close()
+    assert_curves_close(trace, g["trace_20_fi"])
+    if g["best_300_fi"].size:
+        assert best is not None and np.array_equal(best, g["best_300_fi"])
