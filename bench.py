@@ -237,6 +237,24 @@ def workload_config(a):
                 a.gpus, "NCCL send/recv" if a.flags & 32 else "peer-memory (NVLink) push-kernel")}
 
 
+def time_variant(make_solver, args, flags, iters_per_step, peak):
+    """iterations/s of the same solve with opt-in storage flags (iterates stay bit-identical)."""
+    vs = make_solver(*args, flags=flags)
+    try:
+        vs.iterate(2 * iters_per_step)
+        vs.sync()
+        ms = vs.time_iterations(4 * iters_per_step) / (4 * iters_per_step)
+        info = vs.info()
+    finally:
+        vs.close()
+    return {"flags": flags, "iterations_per_s": 1e3 / ms,
+            "actual_bytes_per_iteration": info["bytes_per_iteration_actual"],
+            "actual_GBs": info["bytes_per_iteration_actual"] / ms / 1e6,
+            "actual_frac_of_peak": info["bytes_per_iteration_actual"] / ms / 1e6 / peak,
+            "algorithmic_GBs": info["bytes_per_iteration_algorithmic"] / ms / 1e6,
+            "value_bytes": info["value_bytes"], "const_vector_mask": info["const_vector_mask"]}
+
+
 # ------------------------------------------------------------------------------------------
 def run_b200(a):
     import torch
@@ -311,6 +329,16 @@ def run_b200(a):
     solver.close()
     del solver
 
+    # ---- opt-in variants of the same solve (bit-identical iterates, different storage), N = 1 only
+    variants = None
+    if world == 1 and a.variants:
+        variants = {}
+        for name, vflags in (("reorder", 8), ("compressed", 3), ("compressed+reorder", 11)):
+            try:
+                variants[name] = time_variant(make_solver, args, vflags, a.iters_per_step, peak)
+            except Exception as e:  # a variant must never take the headline measurement down
+                variants[name] = {"flags": vflags, "error": repr(e)}
+
     # ---- end to end through the public API with host buffers -----------------------------------
     h2d = lp_nbytes(lp)
     d2h = 8 * n + 96
@@ -344,7 +372,7 @@ def run_b200(a):
             "metric": METRIC, "value": its_per_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "variants": variants,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
@@ -386,6 +414,7 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=500)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variants", type=int, default=1, help="also time the opt-in storage variants (N = 1)")
     ap.add_argument("--flags", type=int, default=0, help="CPPPD_FLAG_* bit mask (8 reorder, 32 NCCL halos instead of peer memory)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
