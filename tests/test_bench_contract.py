@@ -1,0 +1,83 @@
+"""CPU: pieces of the bench / ABI contract that need no GPU."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+
+def test_algorithmic_bytes_match_survey_numbers():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    # Potts 4096^2 -> 11.20 GB per iteration; random LP 20M x 40M x 320M -> 10.80 GB
+    p, d = bench.algorithmic_bytes(50323456, 67092480, 201277440)
+    assert round((p + d) / 1e9, 2) == 11.20
+    p, d = bench.algorithmic_bytes(20_000_000, 40_000_000, 320_000_000)
+    assert round((p + d) / 1e9, 2) == 10.80
+    assert bench._potts_nnz(4096) == 201277440
+
+
+def test_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` runs the oracle port on the host cores (no GPU involved)."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--size", "128",
+                          "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "iterations/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--size", "128", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
+                         timeout=120, cwd=ROOT, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
+
+
+C_PROBE = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "cpppd.h"
+int main(void) {
+  printf("{\"problem\": %zu, \"stats\": %zu, \"info\": %zu, "
+         "\"p_indptr\": %zu, \"p_alpha\": %zu, \"p_alloc\": %zu, \"p_rank\": %zu, \"p_granule\": %zu, "
+         "\"s_energy1\": %zu, \"s_feasible\": %zu, \"i_device_bytes\": %zu, \"i_n_local\": %zu, \"i_granule\": %zu, "
+         "\"abi\": %d}\n",
+         sizeof(cpppd_problem), sizeof(cpppd_stats), sizeof(cpppd_info),
+         offsetof(cpppd_problem, indptr), offsetof(cpppd_problem, alpha), offsetof(cpppd_problem, alloc),
+         offsetof(cpppd_problem, rank), offsetof(cpppd_problem, partition_granule),
+         offsetof(cpppd_stats, energy1), offsetof(cpppd_stats, feasible),
+         offsetof(cpppd_info, device_bytes), offsetof(cpppd_info, n_local), offsetof(cpppd_info, partition_granule),
+         CPPPD_ABI_VERSION);
+  return 0;
+}
+"""
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile a probe against include/cpppd.h with gcc and compare sizes / offsets with the binding."""
+    from pysparselp_b200 import _cabi
+
+    src = tmp_path / "probe.c"
+    src.write_text(C_PROBE)
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    c = json.loads(subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout)
+    assert c["abi"] == _cabi.ABI_VERSION
+    assert c["problem"] == C.sizeof(_cabi.Problem) and c["stats"] == C.sizeof(_cabi.Stats) and c["info"] == C.sizeof(_cabi.Info)
+    P, S, I = _cabi.Problem, _cabi.Stats, _cabi.Info
+    assert (c["p_indptr"], c["p_alpha"], c["p_alloc"], c["p_rank"], c["p_granule"]) == (
+        P.indptr.offset, P.alpha.offset, P.alloc.offset, P.rank.offset, P.partition_granule.offset)
+    assert (c["s_energy1"], c["s_feasible"]) == (S.energy1.offset, S.feasible.offset)
+    assert (c["i_device_bytes"], c["i_n_local"], c["i_granule"]) == (
+        I.device_bytes.offset, I.n_local.offset, I.partition_granule.offset)
