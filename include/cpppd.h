@@ -99,8 +99,7 @@ typedef struct {
   double one_plus_theta;/* (1 + theta) as evaluated by the host language (:226)            */
   void *stream;         /* cudaStream_t to issue on, or NULL for an internal stream        */
   uint32_t flags;       /* CPPPD_FLAG_* */
-  int32_t sort_window;  /* SELL sigma: rows are sorted by length inside windows of this many
-                           rows (<=1: keep the original order) */
+  int32_t sort_window;  /* reserved (0): length sorting is part of the renumbering, see CPPPD_FLAG_REORDER */
   cpppd_alloc_fn alloc; /* may be NULL */
   cpppd_free_fn free;   /* may be NULL */
   void *alloc_user;

@@ -1,0 +1,756 @@
+// Host side: SELL build, dictionary detection, partition + halos, peer-memory setup, launches.
+// Part of libcpppd (single translation unit, included by cpppd.cu).
+#pragma once
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+SellView view(const Sell &s) {
+  const int code_bits = s.dict ? 30 - s.idx_bits : 0;
+  return SellView{s.slice_ptr, s.idx, s.val, s.nrows, s.nslices, s.uniform_width, s.dict,
+                  s.dict ? (int32_t)((1u << s.idx_bits) - 1) : kIdxMask, s.idx_bits, (int32_t)((1u << code_bits) - 1), s.ndict};
+}
+
+template <typename T>
+int exclusive_scan(cpppd_solver *h, const T *in, T *out, int64_t count) {
+  size_t bytes = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, count, h->stream));
+  void *tmp = dev_alloc(h, bytes, false);
+  if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "scan workspace allocation failed");
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, count, h->stream);
+  cudaStreamSynchronize(h->stream);
+  dev_free(h, tmp);
+  CK(e);
+  return 0;
+}
+
+template <typename K>
+int sort_pairs(cpppd_solver *h, cub::DoubleBuffer<K> &keys, cub::DoubleBuffer<uint32_t> &vals, int64_t count,
+               int end_bit) {
+  if (count == 0) return 0;
+  size_t bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, vals, count, 0, end_bit, h->stream));
+  void *tmp = dev_alloc(h, bytes, false);
+  if (!tmp) return fail(h, CPPPD_ERR_NOMEM, "sort workspace allocation failed");
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, bytes, keys, vals, count, 0, end_bit, h->stream);
+  cudaStreamSynchronize(h->stream);
+  dev_free(h, tmp);
+  CK(e);
+  return 0;
+}
+
+int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b)) ++b;
+  return b;
+}
+
+// CSR (device, int64 rowptr) -> SELL-32 (device)
+int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, const double *values, int64_t nrows,
+               Sell *out) {
+  out->nrows = nrows;
+  out->nslices = (nrows + kSlice - 1) / kSlice;
+  const int64_t ns = out->nslices;
+  Scratch tmp(h);
+  int64_t *extent = nullptr, *mm = nullptr;
+  if (int rc = tmp.get(&extent, ns + 1)) return rc;
+  if (int rc = tmp.get(&mm, 2)) return rc;
+  if (int rc = alloc_array(h, &out->slice_ptr, ns + 1)) return rc;
+  CK(cudaMemsetAsync(extent, 0, sizeof(int64_t) * (ns + 1), h->stream));
+  if (ns) k_slice_extent<<<grid_for(ns * 32), kBlock, 0, h->stream>>>(rowptr, nrows, ns, extent);
+  if (int rc = exclusive_scan(h, extent, out->slice_ptr, ns + 1)) return rc;
+  CK(cudaMemcpyAsync(&out->padded, out->slice_ptr + ns, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  int64_t host_mm[2] = {0, 1};
+  if (ns) {  // uniform slice width <=> min extent == max extent
+    size_t b1 = 0, b2 = 0;
+    CK(cub::DeviceReduce::Min(nullptr, b1, extent, mm, ns, h->stream));
+    CK(cub::DeviceReduce::Max(nullptr, b2, extent, mm + 1, ns, h->stream));
+    char *t2 = nullptr;
+    if (int rc = tmp.get(&t2, (int64_t)std::max(b1, b2))) return rc;
+    CK(cub::DeviceReduce::Min(t2, b1, extent, mm, ns, h->stream));
+    CK(cub::DeviceReduce::Max(t2, b2, extent, mm + 1, ns, h->stream));
+    CK(cudaMemcpyAsync(host_mm, mm, 2 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  out->uniform_width = (ns && host_mm[0] == host_mm[1]) ? host_mm[0] / kSlice : -1;
+  if (int rc = alloc_array(h, &out->idx, out->padded)) return rc;
+  if (!out->dict)
+    if (int rc = alloc_array(h, &out->val, out->padded)) return rc;
+  if (ns) k_fill_sell<<<grid_for(ns * 32), kBlock, 0, h->stream>>>(rowptr, indices, values, nrows, ns, out->slice_ptr,
+                                                                  out->idx, out->val, out->dict ? h->dict : nullptr,
+                                                                  h->ndict, out->idx_bits);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int upload_f64(cpppd_solver *h, double *dst, const double *src, int64_t count) {
+  if (count == 0) return 0;
+  CK(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int read_i32(cpppd_solver *h, const int32_t *dev, int32_t *host, int64_t count) {
+  CK(cudaMemcpyAsync(host, dev, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t default_granule(int64_t n) {
+  int64_t g = 32;
+  while (g < (n >> 14)) g *= 2;
+  return g;
+}
+
+// gather a full-length host vector into this rank's local layout (owned + ghosts)
+int upload_local(cpppd_solver *h, Scratch &tmp, const double *host_full, int64_t full_count, const int32_t *map,
+                 int64_t local_count, double *dst) {
+  if (h->identity_layout) return upload_f64(h, dst, host_full, local_count);
+  double *full = nullptr;
+  if (int rc = tmp.get(&full, full_count)) return rc;
+  if (int rc = upload_f64(h, full, host_full, full_count)) return rc;
+  if (local_count) k_gather_f64<<<grid_for(local_count), kBlock, 0, h->stream>>>(full, map, local_count, dst);
+  CK(cudaStreamSynchronize(h->stream));
+  tmp.release(full);
+  return 0;
+}
+
+__global__ void k_sample_bits(const double *__restrict__ values, int64_t nnz, int64_t stride, int64_t count,
+                              unsigned long long *__restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (unsigned long long)__double_as_longlong(values[min(i * stride, nnz - 1)]);
+}
+
+// CPPPD_FLAG_VALUE_DICT: if the matrix takes at most 256 distinct values (bit patterns), keep them,
+// sorted, in h->dict.  Candidates come from a strided sample; a full pass then proves that every
+// entry is covered (otherwise the dictionary is dropped and the generic format is used).
+int detect_dictionary(cpppd_solver *h, Scratch &tmp, const double *values, int64_t nnz) {
+  cudaStream_t st = h->stream;
+  const int64_t count = std::min<int64_t>(nnz, 1 << 20), stride = std::max<int64_t>(1, nnz / count);
+  unsigned long long *a = nullptr, *b = nullptr, *uniq = nullptr;
+  int *num = nullptr, *flag = nullptr;
+  if (int rc = tmp.get(&a, count)) return rc;
+  if (int rc = tmp.get(&b, count)) return rc;
+  if (int rc = tmp.get(&uniq, count)) return rc;
+  if (int rc = tmp.get(&num, 1)) return rc;
+  if (int rc = tmp.get(&flag, 1)) return rc;
+  k_sample_bits<<<grid_for(count), kBlock, 0, st>>>(values, nnz, stride, count, a);
+  size_t b1 = 0, b2 = 0;
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, b1, a, b, count, 0, 64, st));
+  CK(cub::DeviceSelect::Unique(nullptr, b2, b, uniq, num, count, st));
+  char *ws = nullptr;
+  if (int rc = tmp.get(&ws, (int64_t)std::max(b1, b2))) return rc;
+  CK(cub::DeviceRadixSort::SortKeys(ws, b1, a, b, count, 0, 64, st));
+  CK(cub::DeviceSelect::Unique(ws, b2, b, uniq, num, count, st));
+  int num_h = 0;
+  CK(cudaMemcpyAsync(&num_h, num, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (num_h >= 1 && num_h <= 256) {
+    if (int rc = alloc_array(h, &h->dict, 256)) return rc;
+    CK(cudaMemsetAsync(h->dict, 0, sizeof(unsigned long long) * 256, st));
+    CK(cudaMemcpyAsync(h->dict, uniq, sizeof(unsigned long long) * num_h, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    k_dict_check<<<std::min(grid_for(nnz), h->sm_count * 16), kBlock, 0, st>>>(values, nnz, h->dict, num_h, flag);
+    int miss = 0;
+    CK(cudaMemcpyAsync(&miss, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (miss) h->dict = nullptr; else h->ndict = num_h;
+  }
+  tmp.release(a); tmp.release(b); tmp.release(uniq); tmp.release(num); tmp.release(flag); tmp.release(ws);
+  return 0;
+}
+
+// What every rank publishes so that its neighbours can write into its ghost slots.
+struct PeerRecord {
+  cudaIpcMemHandle_t xbar, y, flags;
+  int64_t owned_x, owned_y;
+  int64_t recv_off_x[kMaxWorld], recv_off_y[kMaxWorld];
+};
+
+int setup_p2p(cpppd_solver *h) {
+  const int N = h->world, me = h->rank;
+  P2P &pp = h->p2p;
+  cudaStream_t st = h->stream;
+  CK(cudaMalloc(&pp.flags, sizeof(unsigned long long) * 2 * N));
+  pp.own.push_back(pp.flags);
+  CK(cudaMalloc(&pp.state, sizeof(SyncState)));
+  pp.own.push_back(pp.state);
+  CK(cudaMemsetAsync(pp.flags, 0, sizeof(unsigned long long) * 2 * N, st));
+  CK(cudaMemsetAsync(pp.state, 0, sizeof(SyncState), st));
+  PeerRecord mine;
+  memset(&mine, 0, sizeof mine);
+  CK(cudaIpcGetMemHandle(&mine.xbar, h->xbar));
+  CK(cudaIpcGetMemHandle(&mine.y, h->y));
+  CK(cudaIpcGetMemHandle(&mine.flags, pp.flags));
+  mine.owned_x = h->hx.owned;
+  mine.owned_y = h->hy.owned;
+  for (int t = 0; t < N; ++t) {
+    mine.recv_off_x[t] = h->hx.recv_off[t];
+    mine.recv_off_y[t] = h->hy.recv_off[t];
+  }
+  // all-gather the records (NCCL, setup only)
+  Scratch tmp(h);
+  char *send = nullptr, *recv = nullptr;
+  if (int rc = tmp.get(&send, (int64_t)sizeof(PeerRecord))) return rc;
+  if (int rc = tmp.get(&recv, (int64_t)sizeof(PeerRecord) * N)) return rc;
+  CK(cudaMemcpyAsync(send, &mine, sizeof mine, cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllGather(send, recv, sizeof(PeerRecord), ncclInt8, h->comm, st));
+  std::vector<PeerRecord> all(N);
+  CK(cudaMemcpyAsync(all.data(), recv, sizeof(PeerRecord) * N, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // map the neighbours' vectors
+  memset(pp.ptrs, 0, sizeof pp.ptrs);
+  for (int t = 0; t < N; ++t) {
+    if (t == me) continue;
+    const bool nb = h->hx.send_count[t] || h->hx.recv_count[t] || h->hy.send_count[t] || h->hy.recv_count[t];
+    if (!nb) continue;
+    void *px = nullptr, *py = nullptr, *pf = nullptr;
+    cudaError_t e1 = cudaIpcOpenMemHandle(&px, all[t].xbar, cudaIpcMemLazyEnablePeerAccess);
+    cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&py, all[t].y, cudaIpcMemLazyEnablePeerAccess) : e1;
+    cudaError_t e3 = e2 == cudaSuccess ? cudaIpcOpenMemHandle(&pf, all[t].flags, cudaIpcMemLazyEnablePeerAccess) : e2;
+    if (e3 != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, CPPPD_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (use CPPPD_FLAG_NO_P2P for the NCCL path)",
+                  t, cudaGetErrorString(e3));
+    }
+    pp.opened.insert(pp.opened.end(), {px, py, pf});
+    pp.ptrs[0].vec[t] = (double *)px;
+    pp.ptrs[1].vec[t] = (double *)py;
+    pp.ptrs[0].flags[t] = pp.ptrs[1].flags[t] = (unsigned long long *)pf;
+  }
+  // per-entry destinations of the two send lists
+  for (int kind = 0; kind < 2; ++kind) {
+    Halo &H = kind ? h->hy : h->hx;
+    std::vector<int32_t> peer(H.send_total);
+    std::vector<int64_t> dst(H.send_total);
+    for (int t = 0; t < N; ++t) {
+      if (H.send_count[t]) pp.send_mask[kind] |= 1ull << t;
+      if (H.recv_count[t]) pp.recv_mask[kind] |= 1ull << t;
+      const int64_t base = (kind ? all[t].owned_y : all[t].owned_x) + (kind ? all[t].recv_off_y[me] : all[t].recv_off_x[me]);
+      for (int64_t k = 0; k < H.send_count[t]; ++k) {
+        peer[H.send_off[t] + k] = t;
+        dst[H.send_off[t] + k] = base + k;
+      }
+    }
+    if (int rc = alloc_array(h, &pp.push_peer[kind], H.send_total)) return rc;
+    if (int rc = alloc_array(h, &pp.push_dst[kind], H.send_total)) return rc;
+    if (H.send_total) {
+      CK(cudaMemcpy(pp.push_peer[kind], peer.data(), sizeof(int32_t) * H.send_total, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pp.push_dst[kind], dst.data(), sizeof(int64_t) * H.send_total, cudaMemcpyHostToDevice));
+    }
+  }
+  // nobody may push before every rank has initialised its vectors and flags
+  NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
+  CK(cudaStreamSynchronize(st));
+  pp.active = true;
+  return 0;
+}
+
+// xbar (kind 0) / y (kind 1) halo over peer memory: push mine, then wait for the neighbours'.
+int exchange_p2p(cpppd_solver *h, int kind) {
+  P2P &pp = h->p2p;
+  Halo &H = kind ? h->hy : h->hx;
+  const double *vec = kind ? h->y : h->xbar;
+  if (H.send_total)
+    k_push<<<grid_for(H.send_total), kBlock, 0, h->stream>>>(vec, H.send_idx, pp.push_dst[kind], pp.push_peer[kind],
+                                                            H.send_total, pp.ptrs[kind], kind, h->world, h->rank,
+                                                            pp.send_mask[kind], pp.state);
+  if (pp.recv_mask[kind]) k_wait<<<1, kMaxWorld, 0, h->stream>>>(pp.flags, kind, h->world, pp.recv_mask[kind], pp.state);
+  return 0;
+}
+
+int setup(cpppd_solver *h, const cpppd_problem *P) {
+  const int64_t n = h->n_glob, m = h->m_glob, nnz = h->nnz_glob, m_eq = h->m_eq_glob;
+  const int N = h->world, me = h->rank;
+  cudaStream_t st = h->stream;
+  Scratch tmp(h);
+  // ---- CSR of the whole A on the device (temporary; every rank analyses the same pattern)
+  int64_t *rowptr = nullptr;
+  int32_t *indices = nullptr;
+  double *values = nullptr;
+  if (int rc = tmp.get(&rowptr, m + 1)) return rc;
+  if (int rc = tmp.get(&indices, nnz)) return rc;
+  if (int rc = tmp.get(&values, nnz)) return rc;
+  if (P->indptr_bits == 64) {
+    CK(cudaMemcpyAsync(rowptr, P->indptr, sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
+  } else {
+    int32_t *tmp32 = nullptr;
+    if (int rc = tmp.get(&tmp32, m + 1)) return rc;
+    CK(cudaMemcpyAsync(tmp32, P->indptr, sizeof(int32_t) * (m + 1), cudaMemcpyHostToDevice, st));
+    k_widen_indptr<<<grid_for(m + 1), kBlock, 0, st>>>(tmp32, rowptr, m + 1);
+    CK(cudaStreamSynchronize(st));
+    tmp.release(tmp32);
+  }
+  if (nnz) {
+    CK(cudaMemcpyAsync(indices, P->indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(values, P->values, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+  }
+  {  // validation on the device: monotone row pointers, column indices in range
+    int *flag = nullptr;
+    if (int rc = tmp.get(&flag, 1)) return rc;
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    int64_t items = std::max<int64_t>(m, std::min<int64_t>(nnz, (int64_t)h->sm_count * 64 * kBlock));
+    if (items) k_validate<<<grid_for(items), kBlock, 0, st>>>(rowptr, m, indices, nnz, n, flag);
+    int host_flag = 0;
+    CK(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (host_flag & 1) return fail(h, CPPPD_ERR_INVALID, "indptr is not non-decreasing");
+    if (host_flag & 2) return fail(h, CPPPD_ERR_INVALID, "column index outside [0, n)");
+  }
+  if ((h->flags & CPPPD_FLAG_VALUE_DICT) && nnz)
+    if (int rc = detect_dictionary(h, tmp, values, nnz)) return rc;
+  uint32_t *row_of = nullptr, *entry_id = nullptr;
+  if (int rc = tmp.get(&row_of, nnz)) return rc;
+  if (int rc = tmp.get(&entry_id, nnz)) return rc;
+  if (nnz) k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, entry_id);
+
+  bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
+  if (!reorder && nnz && !(h->flags & CPPPD_FLAG_NO_REORDER)) {
+    // keep the caller's numbering unless SELL-32 would pad it by more than 15 %: then renumber
+    // (rows / columns of equal length are grouped inside locality buckets)
+    int32_t *col_len = nullptr;
+    unsigned long long *total = nullptr, total_h = 0;
+    if (int rc = tmp.get(&col_len, n)) return rc;
+    if (int rc = tmp.get(&total, 1)) return rc;
+    CK(cudaMemsetAsync(col_len, 0, sizeof(int32_t) * std::max<int64_t>(n, 1), st));
+    CK(cudaMemsetAsync(total, 0, sizeof(unsigned long long), st));
+    k_col_len<<<grid_for(nnz), kBlock, 0, st>>>(indices, nnz, col_len);
+    if (m) k_padded_total<<<grid_for(((m + 31) / 32) * 32), kBlock, 0, st>>>(rowptr, nullptr, m, total);
+    if (n) k_padded_total<<<grid_for(((n + 31) / 32) * 32), kBlock, 0, st>>>(nullptr, col_len, n, total);
+    CK(cudaMemcpyAsync(&total_h, total, sizeof total_h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    tmp.release(col_len);
+    tmp.release(total);
+    reorder = (double)total_h > 1.15 * 2.0 * (double)nnz;
+  }
+  h->identity_layout = !reorder;
+  int32_t rs = 0, re = (int32_t)m, cs = 0, ce = (int32_t)n;
+  int64_t n_ghost = 0, m_ghost = 0;
+  uint32_t *row_order = nullptr, *col_order = nullptr;
+  int32_t *row_pos = nullptr, *col_pos = nullptr, *gcol_scan = nullptr, *grow_scan = nullptr;
+  std::vector<int32_t> row_start(N + 1, 0), col_start(N + 1, 0), eq_count(N, 0);
+  h->hx = Halo();
+  h->hy = Halo();
+  for (Halo *H : {&h->hx, &h->hy}) {
+    H->send_count.assign(N, 0);
+    H->send_off.assign(N, 0);
+    H->recv_count.assign(N, 0);
+    H->recv_off.assign(N, 0);
+  }
+
+  if (reorder) {
+    // ---- locality keys -> buckets -> owners (oracle/partition_oracle.py restates this block)
+    const int64_t G = h->granule > 0 ? h->granule : default_granule(n);
+    h->granule = G;
+    const int64_t nb = n / G + 2;
+    int32_t *row_key = nullptr, *col_key = nullptr, *col_len = nullptr, *owner_dev = nullptr, *counts = nullptr;
+    unsigned long long *work = nullptr;
+    if (int rc = tmp.get(&row_key, m)) return rc;
+    if (int rc = tmp.get(&col_key, n)) return rc;
+    if (int rc = tmp.get(&col_len, n)) return rc;
+    if (int rc = tmp.get(&work, nb)) return rc;
+    if (int rc = tmp.get(&owner_dev, nb)) return rc;
+    if (int rc = tmp.get(&counts, 3 * (int64_t)N)) return rc;
+    if (m) k_row_key<<<grid_for(m), kBlock, 0, st>>>(rowptr, indices, m, (int32_t)n, row_key);
+    if (n) k_fill_i32<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)n);
+    CK(cudaMemsetAsync(col_len, 0, sizeof(int32_t) * std::max<int64_t>(n, 1), st));
+    if (nnz) k_col_key<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_key, col_key, col_len);
+    CK(cudaMemsetAsync(work, 0, sizeof(unsigned long long) * nb, st));
+    if (m) k_bucket_work<<<grid_for(m), kBlock, 0, st>>>(row_key, rowptr, nullptr, m, (int32_t)G, work);
+    if (n) k_bucket_work<<<grid_for(n), kBlock, 0, st>>>(col_key, nullptr, col_len, n, (int32_t)G, work);
+    std::vector<unsigned long long> work_h(nb);
+    CK(cudaMemcpyAsync(work_h.data(), work, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<int32_t> owner_h(nb, 0);
+    unsigned long long total = 0, before = 0;
+    for (auto w : work_h) total += w;
+    for (int64_t q = 0; q < nb; ++q) {
+      owner_h[q] = total ? (int32_t)std::min<unsigned long long>(N - 1, (unsigned __int128)before * N / total) : 0;
+      before += work_h[q];
+    }
+    CK(cudaMemcpyAsync(owner_dev, owner_h.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    // ---- local orders: rows by (owner, is_ineq, bucket, id), columns by (owner, bucket, id)
+    uint64_t *rk_a = nullptr, *rk_b = nullptr, *ck_a = nullptr, *ck_b = nullptr;
+    uint32_t *ro_a = nullptr, *ro_b = nullptr, *co_a = nullptr, *co_b = nullptr;
+    if (int rc = tmp.get(&rk_a, m)) return rc;
+    if (int rc = tmp.get(&rk_b, m)) return rc;
+    if (int rc = tmp.get(&ro_a, m)) return rc;
+    if (int rc = tmp.get(&ro_b, m)) return rc;
+    if (int rc = tmp.get(&ck_a, n)) return rc;
+    if (int rc = tmp.get(&ck_b, n)) return rc;
+    if (int rc = tmp.get(&co_a, n)) return rc;
+    if (int rc = tmp.get(&co_b, n)) return rc;
+    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * N, st));
+    if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rowptr, nullptr, rk_a, ro_a, counts, counts + N);
+    if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, nullptr, col_len, ck_a, co_a, counts + 2 * N, nullptr);
+    const int end_bit = 44 + bits_for((uint64_t)2 * N + 1);
+    cub::DoubleBuffer<uint64_t> rk(rk_a, rk_b), ck(ck_a, ck_b);
+    cub::DoubleBuffer<uint32_t> rov(ro_a, ro_b), cov(co_a, co_b);
+    if (int rc = sort_pairs(h, rk, rov, m, end_bit)) return rc;
+    if (int rc = sort_pairs(h, ck, cov, n, end_bit)) return rc;
+    row_order = rov.Current();
+    col_order = cov.Current();
+    std::vector<int32_t> counts_h(3 * N);
+    if (int rc = read_i32(h, counts, counts_h.data(), 3 * N)) return rc;
+    for (int r = 0; r < N; ++r) {
+      row_start[r + 1] = row_start[r] + counts_h[r];
+      eq_count[r] = counts_h[N + r];
+      col_start[r + 1] = col_start[r] + counts_h[2 * N + r];
+    }
+    if (int rc = tmp.get(&row_pos, m)) return rc;
+    if (int rc = tmp.get(&col_pos, n)) return rc;
+    if (m) k_invert<<<grid_for(m), kBlock, 0, st>>>(row_order, m, row_pos);
+    if (n) k_invert<<<grid_for(n), kBlock, 0, st>>>(col_order, n, col_pos);
+    rs = row_start[me]; re = row_start[me + 1]; cs = col_start[me]; ce = col_start[me + 1];
+    tmp.release(rk_a); tmp.release(rk_b); tmp.release(ck_a); tmp.release(ck_b);
+    if (row_order == ro_a) tmp.release(ro_b); else tmp.release(ro_a);
+    if (col_order == co_a) tmp.release(co_b); else tmp.release(co_a);
+    tmp.release(row_key); tmp.release(col_key); tmp.release(col_len); tmp.release(work);
+    // ---- ghosts of this rank
+    int32_t *gcol_flag = nullptr, *grow_flag = nullptr;
+    if (int rc = tmp.get(&gcol_flag, n + 1)) return rc;
+    if (int rc = tmp.get(&grow_flag, m + 1)) return rc;
+    if (int rc = tmp.get(&gcol_scan, n + 1)) return rc;
+    if (int rc = tmp.get(&grow_scan, m + 1)) return rc;
+    CK(cudaMemsetAsync(gcol_flag, 0, sizeof(int32_t) * (n + 1), st));
+    CK(cudaMemsetAsync(grow_flag, 0, sizeof(int32_t) * (m + 1), st));
+    if (nnz && N > 1) k_mark_ghosts<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, gcol_flag, grow_flag);
+    if (int rc = exclusive_scan(h, gcol_flag, gcol_scan, n + 1)) return rc;
+    if (int rc = exclusive_scan(h, grow_flag, grow_scan, m + 1)) return rc;
+    std::vector<int32_t> cb(N + 1), rb(N + 1);
+    for (int r = 0; r <= N; ++r) {
+      if (int rc = read_i32(h, gcol_scan + col_start[r], &cb[r], 1)) return rc;
+      if (int rc = read_i32(h, grow_scan + row_start[r], &rb[r], 1)) return rc;
+    }
+    n_ghost = cb[N];
+    m_ghost = rb[N];
+    for (int r = 0; r < N; ++r) {
+      h->hx.recv_count[r] = cb[r + 1] - cb[r];
+      h->hx.recv_off[r] = cb[r];
+      h->hy.recv_count[r] = rb[r + 1] - rb[r];
+      h->hy.recv_off[r] = rb[r];
+    }
+    // ---- local -> original id maps (owned, then ghosts in exchange order)
+    const int64_t nloc = ce - cs, mloc = re - rs;
+    if (int rc = alloc_array(h, &h->col_old, nloc + n_ghost)) return rc;
+    if (int rc = alloc_array(h, &h->row_old, mloc + m_ghost)) return rc;
+    if (nloc) k_copy_u32_i32<<<grid_for(nloc), kBlock, 0, st>>>(col_order + cs, nloc, h->col_old);
+    if (mloc) k_copy_u32_i32<<<grid_for(mloc), kBlock, 0, st>>>(row_order + rs, mloc, h->row_old);
+    if (n_ghost) k_compact<<<grid_for(n), kBlock, 0, st>>>(gcol_flag, gcol_scan, n, col_order, 0, h->col_old + nloc);
+    if (m_ghost) k_compact<<<grid_for(m), kBlock, 0, st>>>(grow_flag, grow_scan, m, row_order, 0, h->row_old + mloc);
+    CK(cudaStreamSynchronize(st));
+    tmp.release(gcol_flag);
+    tmp.release(grow_flag);
+    // ---- what to send to every peer
+    if (N > 1) {
+      int32_t *sx_flag = nullptr, *sy_flag = nullptr, *sx_scan = nullptr, *sy_scan = nullptr;
+      if (int rc = tmp.get(&sx_flag, nloc + 1)) return rc;
+      if (int rc = tmp.get(&sy_flag, mloc + 1)) return rc;
+      if (int rc = tmp.get(&sx_scan, nloc + 1)) return rc;
+      if (int rc = tmp.get(&sy_scan, mloc + 1)) return rc;
+      std::vector<std::vector<int32_t>> sx_lists(N), sy_lists(N);
+      int32_t *list_dev = nullptr;
+      if (int rc = tmp.get(&list_dev, std::max(nloc, mloc) + 1)) return rc;
+      for (int t = 0; t < N; ++t) {
+        if (t == me) continue;
+        CK(cudaMemsetAsync(sx_flag, 0, sizeof(int32_t) * (nloc + 1), st));
+        CK(cudaMemsetAsync(sy_flag, 0, sizeof(int32_t) * (mloc + 1), st));
+        if (nnz) k_mark_sends<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce,
+                                                              row_start[t], row_start[t + 1], col_start[t], col_start[t + 1],
+                                                              sx_flag, sy_flag);
+        if (int rc = exclusive_scan(h, sx_flag, sx_scan, nloc + 1)) return rc;
+        if (int rc = exclusive_scan(h, sy_flag, sy_scan, mloc + 1)) return rc;
+        int32_t cx = 0, cy = 0;
+        if (int rc = read_i32(h, sx_scan + nloc, &cx, 1)) return rc;
+        if (int rc = read_i32(h, sy_scan + mloc, &cy, 1)) return rc;
+        if (cx) {
+          k_compact<<<grid_for(nloc), kBlock, 0, st>>>(sx_flag, sx_scan, nloc, nullptr, 0, list_dev);
+          sx_lists[t].resize(cx);
+          if (int rc = read_i32(h, list_dev, sx_lists[t].data(), cx)) return rc;
+        }
+        if (cy) {
+          k_compact<<<grid_for(mloc), kBlock, 0, st>>>(sy_flag, sy_scan, mloc, nullptr, 0, list_dev);
+          sy_lists[t].resize(cy);
+          if (int rc = read_i32(h, list_dev, sy_lists[t].data(), cy)) return rc;
+        }
+      }
+      for (int pass = 0; pass < 2; ++pass) {
+        Halo &H = pass ? h->hy : h->hx;
+        auto &lists = pass ? sy_lists : sx_lists;
+        std::vector<int32_t> flat;
+        for (int t = 0; t < N; ++t) {
+          H.send_off[t] = (int64_t)flat.size();
+          H.send_count[t] = (int64_t)lists[t].size();
+          flat.insert(flat.end(), lists[t].begin(), lists[t].end());
+        }
+        H.send_total = (int64_t)flat.size();
+        if (int rc = alloc_array(h, &H.send_idx, H.send_total)) return rc;
+        if (int rc = alloc_array(h, &H.send_buf, H.send_total)) return rc;
+        if (H.send_total) CK(cudaMemcpy(H.send_idx, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice));
+      }
+      tmp.release(sx_flag); tmp.release(sy_flag); tmp.release(sx_scan); tmp.release(sy_scan); tmp.release(list_dev);
+    }
+  }
+  const int64_t nloc = ce - cs, mloc = re - rs;
+  h->n = nloc;
+  h->m = mloc;
+  h->m_eq = reorder ? eq_count[me] : m_eq;
+  h->hx.owned = nloc;
+  h->hx.ghost = n_ghost;
+  h->hy.owned = mloc;
+  h->hy.ghost = m_ghost;
+
+  if (h->dict) {  // an entry word must hold index + code below the eq / pad bits
+    const int idx_bits = bits_for((uint64_t)std::max<int64_t>(std::max(nloc + n_ghost, mloc + m_ghost), 2) - 1);
+    const int code_bits = bits_for((uint64_t)std::max(h->ndict, 2) - 1);
+    if (idx_bits + code_bits <= 30) {
+      for (Sell *S : {&h->A, &h->AT}) {
+        S->dict = reinterpret_cast<const double *>(h->dict);
+        S->idx_bits = idx_bits;
+        S->ndict = h->ndict;
+      }
+    } else {
+      h->dict = nullptr;  // (stays allocated, simply unused)
+      h->ndict = 0;
+    }
+  }
+  // ---- this rank's rows of A -> SELL-32
+  if (!reorder) {
+    h->nnz_rows = nnz;
+    if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
+  } else {
+    int64_t *len = nullptr, *lrowptr = nullptr;
+    if (int rc = tmp.get(&len, mloc + 1)) return rc;
+    if (int rc = tmp.get(&lrowptr, mloc + 1)) return rc;
+    k_local_row_len<<<grid_for(mloc + 1), kBlock, 0, st>>>(row_order, rs, mloc, rowptr, len);
+    if (int rc = exclusive_scan(h, len, lrowptr, mloc + 1)) return rc;
+    int64_t lnnz = 0;
+    CK(cudaMemcpyAsync(&lnnz, lrowptr + mloc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->nnz_rows = lnnz;
+    int32_t *lidx = nullptr;
+    double *lval = nullptr;
+    if (int rc = tmp.get(&lidx, lnnz)) return rc;
+    if (int rc = tmp.get(&lval, lnnz)) return rc;
+    if (mloc) k_local_rows_fill<<<grid_for(mloc), kBlock, 0, st>>>(row_order, rs, mloc, rowptr, indices, values, col_pos,
+                                                                  cs, ce, gcol_scan, lrowptr, lidx, lval);
+    if (int rc = build_sell(h, lrowptr, lidx, lval, mloc, &h->A)) return rc;
+    tmp.release(len); tmp.release(lrowptr); tmp.release(lidx); tmp.release(lval);
+  }
+  // ---- this rank's columns of A as rows of A^T.  A stable radix sort of the entries (taken in CSR
+  //      order) by column keeps, inside each column, the original row order — exactly the
+  //      accumulation order of scipy's csc_matvec.
+  {
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *ids_b = nullptr;
+    if (int rc = tmp.get(&keys_a, nnz)) return rc;
+    if (int rc = tmp.get(&keys_b, nnz)) return rc;
+    if (int rc = tmp.get(&ids_b, nnz)) return rc;
+    if (nnz) {
+      if (reorder) k_entry_col_pos<<<grid_for(nnz), kBlock, 0, st>>>(indices, col_pos, nnz, keys_a);
+      else CK(cudaMemcpyAsync(keys_a, indices, sizeof(uint32_t) * nnz, cudaMemcpyDeviceToDevice, st));
+    }
+    cub::DoubleBuffer<uint32_t> keys(keys_a, keys_b), ids(entry_id, ids_b);
+    if (int rc = sort_pairs(h, keys, ids, nnz, bits_for((uint64_t)std::max<int64_t>(n, 1)))) return rc;
+    int64_t *lcolptr = nullptr;
+    if (int rc = tmp.get(&lcolptr, nloc + 1)) return rc;
+    k_lower_bounds<<<grid_for(nloc + 1), kBlock, 0, st>>>(keys.Current(), nnz, cs, nloc, lcolptr);
+    int64_t first = 0, last = 0;
+    CK(cudaMemcpyAsync(&first, lcolptr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last, lcolptr + nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t lnnz = last - first;
+    h->nnz_cols = lnnz;
+    if (first) k_subtract_base<<<grid_for(nloc + 1), kBlock, 0, st>>>(lcolptr, nloc + 1, first);
+    const uint32_t *sorted_ids = ids.Current();
+    if (keys.Current() == keys_a) tmp.release(keys_b); else tmp.release(keys_a);
+    int32_t *t_idx = nullptr;
+    double *t_val = nullptr;
+    if (int rc = tmp.get(&t_idx, lnnz)) return rc;
+    if (int rc = tmp.get(&t_val, lnnz)) return rc;
+    if (lnnz) {
+      if (reorder) {
+        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(sorted_ids, row_of, values, first, lnnz, row_pos, rs, re,
+                                                             grow_scan, m_eq, t_idx, t_val);
+      } else {
+        // identity layout: row_pos / grow_scan do not exist; local row == original row
+        k_local_cols_fill<<<grid_for(lnnz), kBlock, 0, st>>>(sorted_ids, row_of, values, first, lnnz, nullptr, 0,
+                                                             (int32_t)m, nullptr, m_eq, t_idx, t_val);
+      }
+    }
+    CK(cudaStreamSynchronize(st));
+    tmp.release(keys_a); tmp.release(keys_b); tmp.release(ids_b); tmp.release(entry_id); tmp.release(row_of);
+    tmp.release(indices); tmp.release(values); tmp.release(rowptr);
+    if (int rc = build_sell(h, lcolptr, t_idx, t_val, nloc, &h->AT)) return rc;
+    tmp.release(lcolptr); tmp.release(t_idx); tmp.release(t_val);
+  }
+  // ---- vectors in local layout
+  for (double **v : {&h->c, &h->T, &h->lb, &h->ub, &h->best})
+    if (int rc = alloc_array(h, v, nloc)) return rc;
+  const bool want_p2p = N > 1 && !(h->flags & CPPPD_FLAG_NO_P2P);
+  for (double **v : {&h->x, &h->dbuf})
+    if (int rc = alloc_array(h, v, nloc + n_ghost)) return rc;
+  for (double **v : {&h->b, &h->sigma})
+    if (int rc = alloc_array(h, v, mloc)) return rc;
+  if (want_p2p) {  // the two vectors with peer-written ghost tails: plain cudaMalloc, exportable by IPC
+    CK(cudaMalloc(&h->xbar, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1)));
+    h->p2p.own.push_back(h->xbar);
+    CK(cudaMalloc(&h->y, sizeof(double) * std::max<int64_t>(mloc + m_ghost, 1)));
+    h->p2p.own.push_back(h->y);
+    h->device_bytes += 8 * (nloc + n_ghost + mloc + m_ghost);
+  } else {
+    if (int rc = alloc_array(h, &h->xbar, nloc + n_ghost)) return rc;
+    if (int rc = alloc_array(h, &h->y, mloc + m_ghost)) return rc;
+  }
+  if (int rc = upload_local(h, tmp, P->c, n, h->col_old, nloc, h->c)) return rc;
+  if (int rc = upload_local(h, tmp, P->lb, n, h->col_old, nloc, h->lb)) return rc;
+  if (int rc = upload_local(h, tmp, P->ub, n, h->col_old, nloc, h->ub)) return rc;
+  if (int rc = upload_local(h, tmp, P->b, m, h->row_old, mloc, h->b)) return rc;
+  if (P->x0) {
+    if (int rc = upload_local(h, tmp, P->x0, n, h->col_old, nloc + n_ghost, h->x)) return rc;
+  } else {
+    CK(cudaMemsetAsync(h->x, 0, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1), st));
+  }
+  CK(cudaMemcpyAsync(h->xbar, h->x, sizeof(double) * (nloc + n_ghost), cudaMemcpyDeviceToDevice, st));  // x3 = x (:190)
+  CK(cudaMemsetAsync(h->dbuf, 0, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1), st));
+  CK(cudaMemsetAsync(h->y, 0, sizeof(double) * std::max<int64_t>(mloc + m_ghost, 1), st));              // :166,:177
+  // ---- preconditioners (:122-179): complete columns / rows are local, so no exchange is needed
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  if (h->AT.nslices)
+    k_precond_cols<<<grid_for(h->AT.nslices * 32), kBlock, 0, st>>>(view(h->AT), nloc, has_eq, has_ineq, 2.0 - h->alpha, h->T);
+  if (h->A.nslices)
+    k_precond_rows<<<grid_for(h->A.nslices * 32), kBlock, 0, st>>>(view(h->A), mloc, h->alpha, h->sigma);
+  h->vc = Vec{h->c, 0};
+  h->vT = Vec{h->T, 0};
+  h->vlb = Vec{h->lb, 0};
+  h->vub = Vec{h->ub, 0};
+  h->vb = Vec{h->b, 0};
+  h->vsigma = Vec{h->sigma, 0};
+  if (h->flags & CPPPD_FLAG_CONST_VECTORS) {
+    struct { Vec *v; double *p; int64_t count; int bit; } cand[] = {
+        {&h->vb, h->b, mloc, 0}, {&h->vsigma, h->sigma, mloc, 1}, {&h->vlb, h->lb, nloc, 2},
+        {&h->vub, h->ub, nloc, 3}, {&h->vc, h->c, nloc, 4},      {&h->vT, h->T, nloc, 5}};
+    int *flag = nullptr;
+    if (int rc = tmp.get(&flag, 1)) return rc;
+    for (auto &cd : cand) {
+      if (cd.count == 0) continue;
+      int host_flag = 0;
+      CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+      k_not_constant<<<std::min(grid_for(cd.count), h->sm_count * 8), kBlock, 0, st>>>(cd.p, cd.count, flag);
+      CK(cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      double first = 0;
+      CK(cudaMemcpyAsync(&first, cd.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (!host_flag) {
+        *cd.v = Vec{nullptr, first};
+        h->const_mask |= 1 << cd.bit;
+      }
+    }
+  }
+  // ---- stats plumbing
+  h->stat_blocks_c = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(nloc), (int64_t)h->sm_count * 8));
+  h->stat_blocks_r = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(h->A.nslices * 32), (int64_t)h->sm_count * 8));
+  if (int rc = alloc_array(h, &h->colpart, (int64_t)h->stat_blocks_c * kColQ)) return rc;
+  if (int rc = alloc_array(h, &h->rowpart, (int64_t)h->stat_blocks_r * kRowQ)) return rc;
+  if (int rc = alloc_array(h, &h->stat_local, kStatQ)) return rc;
+  if (int rc = alloc_array(h, &h->stat_all, (int64_t)kStatQ * N)) return rc;
+  if (int rc = alloc_array(h, &h->stats_dev, 1)) return rc;
+  k_init_stats<<<1, 1, 0, st>>>(h->stats_dev);
+  CK(cudaMallocHost(&h->stats_host, sizeof(cpppd_stats)));
+  memset(h->stats_host, 0, sizeof(cpppd_stats));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  if (want_p2p)
+    if (int rc = setup_p2p(h)) return rc;
+  return 0;
+}
+
+// Refresh the ghost part of a distributed vector: every rank sends the owned entries its peers
+// need and receives its ghosts straight into vec[owned ...].
+int exchange(cpppd_solver *h, double *vec, Halo &H) {
+  if (h->world == 1) return 0;
+  if (H.send_total) k_pack<<<grid_for(H.send_total), kBlock, 0, h->stream>>>(vec, H.send_idx, H.send_total, H.send_buf);
+  NK(g_nccl.GroupStart());
+  for (int t = 0; t < h->world; ++t) {
+    if (H.send_count[t]) NK(g_nccl.Send(H.send_buf + H.send_off[t], (size_t)H.send_count[t], ncclFloat64, t, h->comm, h->stream));
+    if (H.recv_count[t]) NK(g_nccl.Recv(vec + H.owned + H.recv_off[t], (size_t)H.recv_count[t], ncclFloat64, t, h->comm, h->stream));
+  }
+  NK(g_nccl.GroupEnd());
+  return 0;
+}
+
+template <bool kWriteD, bool kDict>
+void launch_primal_t(cpppd_solver *h) {
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  k_primal<kWriteD, kDict><<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(
+      view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
+      h->one_plus_theta);
+}
+
+int launch_primal(cpppd_solver *h, bool write_d) {
+  if (h->AT.nslices) {
+    const bool dict = h->AT.dict != nullptr;
+    if (write_d) dict ? launch_primal_t<true, true>(h) : launch_primal_t<true, false>(h);
+    else dict ? launch_primal_t<false, true>(h) : launch_primal_t<false, false>(h);
+  }
+  return h->p2p.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
+}
+
+int launch_dual(cpppd_solver *h) {
+  if (h->A.nslices) {
+    const int grid = grid_for(h->A.nslices * 32);
+    if (h->A.dict)
+      k_dual<true><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+    else
+      k_dual<false><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+  }
+  return h->p2p.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
+}
+
+int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
+  auto it = h->graphs.find(k);
+  if (it != h->graphs.end()) {
+    *out = it->second;
+    return 0;
+  }
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = 0;
+  for (int64_t i = 0; i < k && !rc; ++i) {
+    rc = launch_primal(h, false);
+    if (!rc) rc = launch_dual(h);
+  }
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  if (rc) return rc;
+  CK(e);
+  cudaGraphExec_t ge = nullptr;
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  cudaGraphDestroy(g);
+  h->graphs[k] = ge;
+  *out = ge;
+  return 0;
+}
+
+int run_iterations(cpppd_solver *h, int64_t k) {
+  const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH) && (h->world == 1 || h->p2p.active || (h->flags & CPPPD_FLAG_GRAPH_COMM));
+  while (k > 0) {
+    int64_t step = std::min<int64_t>(k, kGraphChunk);
+    if (use_graph && step >= 2) {
+      cudaGraphExec_t ge = nullptr;
+      if (int rc = get_graph(h, step, &ge)) return rc;
+      CK(cudaGraphLaunch(ge, h->stream));
+    } else {
+      for (int64_t i = 0; i < step; ++i) {
+        if (int rc = launch_primal(h, false)) return rc;
+        if (int rc = launch_dual(h)) return rc;
+      }
+      CK(cudaGetLastError());
+    }
+    k -= step;
+    h->niter += step;
+  }
+  return 0;
+}
+
+}  // namespace

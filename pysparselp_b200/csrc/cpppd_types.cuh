@@ -1,0 +1,313 @@
+// Types, constants, error / allocation plumbing and the NCCL loader.
+// Part of libcpppd (single translation unit, included by cpppd.cu).
+#pragma once
+
+#include "../../include/cpppd.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <climits>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int kSlice = 32;       // SELL slice height C (= warp size)
+constexpr int kBlock = 256;      // threads per CTA for the streaming kernels (8 slices)
+constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
+constexpr int kColQ = 4;         // column-pass partial sums per CTA
+constexpr int kRowQ = 7;         // row-pass partial sums per CTA
+constexpr int kStatQ = kColQ + kRowQ;
+constexpr int32_t kEqBit = 0x40000000;   // A^T entries: set when the source row is an equality
+constexpr int32_t kIdxMask = 0x3fffffff;
+// padding entry of a slice: negative, and its masked index is 0 so that a gather the compiler
+// hoists above the `idx >= 0` test still reads a valid address
+constexpr int32_t kPad = INT32_MIN;
+constexpr int kMaxWorld = 64;
+
+thread_local std::string g_create_error;
+
+struct Sell {
+  int64_t nrows = 0, nslices = 0, padded = 0;
+  int64_t uniform_width = -1;    // >= 0 when every slice has this width (slice_ptr is then implicit)
+  int64_t *slice_ptr = nullptr;  // nslices+1 element offsets
+  int32_t *idx = nullptr;        // padded entries, kPad = padding
+  double *val = nullptr;         // nullptr in dictionary mode
+  // dictionary mode (CPPPD_FLAG_VALUE_DICT): the matrix takes <= 256 distinct values; an entry is one
+  // 32-bit word  [pad:1][eq:1][code][index]  and its value is dict[code] (the exact original double)
+  const double *dict = nullptr;
+  int idx_bits = 30, ndict = 0;
+};
+
+struct SellView {
+  const int64_t *__restrict__ slice_ptr;
+  const int32_t *__restrict__ idx;
+  const double *__restrict__ val;
+  int64_t nrows, nslices;
+  int64_t uniform_width;  // -1: read slice_ptr
+  const double *__restrict__ dict;
+  int32_t idx_mask;       // low bits of an entry word that hold the gather index
+  int32_t idx_bits, code_mask, ndict;
+};
+
+// a vector operand that may have been folded into a scalar (CPPPD_FLAG_CONST_VECTORS)
+struct Vec {
+  const double *p;
+  double c;
+  __device__ __forceinline__ double at(int64_t i) const { return p ? __ldcs(p + i) : c; }
+};
+
+// first / one-past-last element offset of slice s
+__device__ __forceinline__ void slice_range(const SellView &S, int64_t s, int64_t &p0, int64_t &p1) {
+  if (S.uniform_width >= 0) {
+    p0 = s * S.uniform_width * 32;
+    p1 = p0 + S.uniform_width * 32;
+  } else {
+    p0 = __ldg(S.slice_ptr + s);
+    p1 = __ldg(S.slice_ptr + s + 1);
+  }
+}
+
+// value of the entry stored at position p whose index word is w (non-hot kernels)
+__device__ __forceinline__ double entry_value(const SellView &S, int64_t p, int32_t w) {
+  return S.dict ? S.dict[(w >> S.idx_bits) & S.code_mask] : S.val[p];
+}
+
+struct StatsDev {  // device-resident, copied verbatim into cpppd_stats
+  cpppd_stats s;
+};
+
+// Halo of one distributed vector: which owned entries go to which peer, where ghosts land.
+struct Halo {
+  int64_t owned = 0, ghost = 0, send_total = 0;
+  std::vector<int64_t> send_count, send_off, recv_count, recv_off;  // per peer rank
+  int32_t *send_idx = nullptr;  // send_total local indices (owned part), grouped by peer
+  double *send_buf = nullptr;   // send_total staging values
+};
+
+// Peer-memory halo exchange (world > 1): the ghost tails of xbar / y live in cudaMalloc'ed memory
+// that every neighbour maps through CUDA IPC; a push kernel stores the halo values straight into the
+// neighbours' ghost slots over NVLink and then raises a per-neighbour flag, a wait kernel spins on
+// the local flags.  No staging buffer, no NCCL call, and the whole iteration is graph-capturable.
+struct PeerPtrs {
+  double *vec[kMaxWorld];
+  unsigned long long *flags[kMaxWorld];
+};
+struct SyncState {
+  unsigned long long push_stamp[2];  // halos pushed so far        ([0] xbar, [1] y)
+  unsigned long long wait_stamp[2];  // halos consumed so far
+  unsigned int ticket[2];            // CTA arrival counter of k_push
+};
+struct P2P {
+  bool active = false;
+  PeerPtrs ptrs[2];                  // [0]: peers' xbar, [1]: peers' y (+ their flag arrays)
+  unsigned long long *flags = nullptr;  // 2 * world stamps written by the peers
+  SyncState *state = nullptr;
+  int32_t *push_peer[2] = {nullptr, nullptr};
+  int64_t *push_dst[2] = {nullptr, nullptr};
+  unsigned long long send_mask[2] = {0, 0}, recv_mask[2] = {0, 0};
+  std::vector<void *> opened, own;
+};
+
+// NCCL is resolved at run time (dlopen) so that the library loads without it on one GPU.
+struct NcclApi {
+  void *dl = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+const char *load_nccl() {
+  if (g_nccl.dl) return nullptr;
+  const char *env = getenv("CPPPD_NCCL_LIB");
+  void *dl = nullptr;
+  if (env && *env) dl = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) dl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) dl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!dl) return "cannot dlopen libnccl.so.2 (set CPPPD_NCCL_LIB)";
+#define SYM(field, name)                                       \
+  g_nccl.field = (decltype(g_nccl.field))dlsym(dl, name);      \
+  if (!g_nccl.field) return "libnccl lacks symbol " name;
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(Send, "ncclSend")
+  SYM(Recv, "ncclRecv")
+  SYM(AllGather, "ncclAllGather")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.dl = dl;
+  return nullptr;
+}
+
+}  // namespace
+
+struct cpppd_solver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // global problem
+  int64_t n_glob = 0, m_eq_glob = 0, m_ineq_glob = 0, m_glob = 0, nnz_glob = 0;
+  // this rank's share (== global on one GPU)
+  int64_t n = 0, m = 0, m_eq = 0, nnz_rows = 0, nnz_cols = 0;
+  int rank = 0, world = 1;
+  bool identity_layout = true;  // local index == original index (one GPU, no reordering)
+  int32_t *col_old = nullptr;   // n + ghosts : original column id of a local column
+  int32_t *row_old = nullptr;   // m + ghosts : original row id of a local row
+  Halo hx, hy;                  // xbar-like vectors (columns) / y-like vectors (rows)
+  ncclComm_t comm = nullptr;
+  P2P p2p;
+  double alpha = 1, theta = 1, one_plus_theta = 2;
+  uint32_t flags = 0;
+  int64_t granule = 0;
+  cpppd_alloc_fn alloc = nullptr;
+  cpppd_free_fn free_fn = nullptr;
+  void *alloc_user = nullptr;
+  std::vector<void *> owned;
+  int64_t device_bytes = 0;
+  Sell A, AT;
+  double *c = nullptr, *T = nullptr, *lb = nullptr, *ub = nullptr, *x = nullptr, *xbar = nullptr;
+  double *b = nullptr, *sigma = nullptr, *y = nullptr, *dbuf = nullptr, *best = nullptr;
+  Vec vc{nullptr, 0}, vT{nullptr, 0}, vlb{nullptr, 0}, vub{nullptr, 0}, vb{nullptr, 0}, vsigma{nullptr, 0};
+  int const_mask = 0;               // bit0 b, bit1 sigma, bit2 lb, bit3 ub, bit4 c, bit5 T folded to scalars
+  unsigned long long *dict = nullptr;  // sorted bit patterns of the distinct matrix values (dictionary mode)
+  int ndict = 0;
+  double *colpart = nullptr, *rowpart = nullptr, *xr_scratch = nullptr;
+  double *stat_local = nullptr, *stat_all = nullptr;  // kStatQ / world*kStatQ
+  int stat_blocks_c = 0, stat_blocks_r = 0;
+  StatsDev *stats_dev = nullptr;
+  cpppd_stats *stats_host = nullptr;
+  int64_t niter = 0;
+  bool mid_iteration = false;  // primal step issued, dual step pending
+  bool stats_pending = false;
+  bool have_d = false;
+  int sm_count = 148;
+  std::map<int64_t, cudaGraphExec_t> graphs;
+  std::string err;
+  int sticky = 0;
+};
+
+namespace {
+
+int fail(cpppd_solver *h, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) {
+    h->err = buf;
+    if (code == CPPPD_ERR_CUDA || code == CPPPD_ERR_COMM) h->sticky = code;
+  }
+  g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(h, CPPPD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+#define NK(call)                                                                                    \
+  do {                                                                                              \
+    ncclResult_t r_ = (call);                                                                       \
+    if (r_ != ncclSuccess)                                                                          \
+      return fail(h, CPPPD_ERR_COMM, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(r_),    \
+                  __FILE__, __LINE__);                                                              \
+  } while (0)
+
+#define CHECK_HANDLE(h)                                  \
+  do {                                                   \
+    if (!(h)) return CPPPD_ERR_INVALID;                  \
+    if ((h)->sticky) return (h)->sticky;                 \
+    cudaSetDevice((h)->device);                          \
+  } while (0)
+
+void *dev_alloc(cpppd_solver *h, size_t bytes, bool persistent) {
+  if (bytes == 0) bytes = 256;
+  void *p = nullptr;
+  if (h->alloc) {
+    p = h->alloc(bytes, h->alloc_user);
+  } else if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    p = nullptr;
+  }
+  if (p && persistent) {
+    h->owned.push_back(p);
+    h->device_bytes += (int64_t)bytes;
+  }
+  return p;
+}
+
+void dev_free(cpppd_solver *h, void *p) {
+  if (!p) return;
+  if (h->alloc) {
+    if (h->free_fn) h->free_fn(p, h->alloc_user);
+  } else {
+    cudaFree(p);
+  }
+}
+
+template <typename T>
+int alloc_array(cpppd_solver *h, T **out, int64_t count, bool persistent = true) {
+  *out = static_cast<T *>(dev_alloc(h, sizeof(T) * (size_t)std::max<int64_t>(count, 1), persistent));
+  if (!*out) return fail(h, CPPPD_ERR_NOMEM, "device allocation of %lld bytes failed", (long long)(sizeof(T) * count));
+  return 0;
+}
+
+// temporaries of setup(): freed on scope exit
+struct Scratch {
+  cpppd_solver *h;
+  std::vector<void *> ptrs;
+  explicit Scratch(cpppd_solver *h_) : h(h_) {}
+  ~Scratch() { for (void *p : ptrs) dev_free(h, p); }
+  template <typename T>
+  int get(T **out, int64_t count) {
+    int rc = alloc_array(h, out, count, false);
+    if (!rc) ptrs.push_back(*out);
+    return rc;
+  }
+  // frees now and NULLs the caller's variable: the allocator may hand the same address out again,
+  // so a stale copy of the pointer must never reach release() a second time
+  template <typename T>
+  void release(T *&p) {
+    if (!p) return;
+    for (auto &q : ptrs)
+      if (q == (void *)p) {
+        dev_free(h, q);
+        q = nullptr;
+        break;
+      }
+    p = nullptr;
+  }
+};
+
+inline int grid_for(int64_t items, int block = kBlock) { return (int)std::max<int64_t>(1, (items + block - 1) / block); }
+
+}  // namespace
