@@ -39,7 +39,8 @@ def is_stale():
 def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, "-ldl"]
+    defines = os.environ.get("CPPPD_NVCC_DEFINES", "").split()  # e.g. "-DCPPPD_GATHER_CHUNK=3 -DCPPPD_MIN_BLOCKS=6"
+    cmd = [find_nvcc()] + NVCC_FLAGS + defines + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))

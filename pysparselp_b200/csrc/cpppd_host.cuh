@@ -683,7 +683,7 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
 template <bool kWriteD, bool kDict>
 void launch_primal_t(cpppd_solver *h) {
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-  k_primal<kWriteD, kDict><<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(
+  k_primal<kWriteD, kDict, kGatherChunk><<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(
       view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
       h->one_plus_theta);
 }
@@ -701,9 +701,9 @@ int launch_dual(cpppd_solver *h) {
   if (h->A.nslices) {
     const int grid = grid_for(h->A.nslices * 32);
     if (h->A.dict)
-      k_dual<true><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+      k_dual<true, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
     else
-      k_dual<false><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+      k_dual<false, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
   }
   return h->p2p.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
 }

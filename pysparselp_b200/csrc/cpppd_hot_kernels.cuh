@@ -12,8 +12,8 @@ namespace {
 // together with the slice entries; matrix entries are read once (ld.global.cs).
 // kDict: entries are single 32-bit words [pad][eq][code][index]; values come from a <= 256 entry
 // dictionary staged in shared memory.
-template <bool kWriteD, bool kDict>
-__global__ void __launch_bounds__(kBlock, 8)
+template <bool kWriteD, bool kDict, int kChunk>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
 k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
          double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int has_eq, int has_ineq,
          double theta, double one_plus_theta) {
@@ -41,14 +41,28 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
     const double *vp = AT.val + p0 + lane;
     const int width = (int)((p1 - p0) >> 5);
     const int32_t mask = AT.idx_mask;
-#pragma unroll 4
-    for (int k = 0; k < width; ++k) {
-      const int32_t r = __ldcs(ip + k * kSlice);
-      double a;
-      if (kDict) a = sdict[(r >> AT.idx_bits) & AT.code_mask]; else a = __ldcs(vp + k * kSlice);
-      if (r >= 0) {
-        const double t = __dmul_rn(a, __ldg(y + (r & mask)));
-        if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+    // entries are taken kChunk at a time: all index (and value) loads of a chunk are issued first,
+    // then all gathers, then the sequential accumulation — so a row of any width (also 2 or 3) keeps
+    // kChunk independent gathers in flight instead of one load-use chain per entry
+#pragma unroll 1
+    for (int k0 = 0; k0 < width; k0 += kChunk) {
+      int32_t r[kChunk];
+      double a[kChunk], g[kChunk];
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        const bool ok = k0 + u < width;
+        r[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
+        a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) g[u] = r[u] >= 0 ? __ldg(y + (r[u] & mask)) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        if (r[u] >= 0) {
+          const double av = kDict ? sdict[(r[u] >> AT.idx_bits) & AT.code_mask] : a[u];
+          const double t = __dmul_rn(av, g[u]);
+          if (r[u] & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+        }
       }
     }
   }
@@ -66,8 +80,8 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
 }
 
 // Dual half-iteration (:231-240, :333-341).  Thread i owns row i of A.
-template <bool kDict>
-__global__ void __launch_bounds__(kBlock, 8)
+template <bool kDict, int kChunk>
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
 k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__restrict__ y, int64_t m,
        int64_t m_eq) {
   __shared__ double sdict[kDict ? 256 : 1];
@@ -94,12 +108,25 @@ k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__
     const double *vp = A.val + p0 + lane;
     const int width = (int)((p1 - p0) >> 5);
     const int32_t mask = A.idx_mask;
-#pragma unroll 4
-    for (int k = 0; k < width; ++k) {
-      const int32_t jc = __ldcs(ip + k * kSlice);
-      double a;
-      if (kDict) a = sdict[(jc >> A.idx_bits) & A.code_mask]; else a = __ldcs(vp + k * kSlice);
-      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + (jc & mask))));
+#pragma unroll 1
+    for (int k0 = 0; k0 < width; k0 += kChunk) {  // see k_primal: loads of a chunk first, then gathers, then sums
+      int32_t jc[kChunk];
+      double a[kChunk], g[kChunk];
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        const bool ok = k0 + u < width;
+        jc[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
+        a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) g[u] = jc[u] >= 0 ? __ldg(xbar + (jc[u] & mask)) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        if (jc[u] >= 0) {
+          const double av = kDict ? sdict[(jc[u] >> A.idx_bits) & A.code_mask] : a[u];
+          acc = __dadd_rn(acc, __dmul_rn(av, g[u]));
+        }
+      }
     }
   }
   if (!live) return;

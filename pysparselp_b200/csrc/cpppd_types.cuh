@@ -27,6 +27,16 @@ namespace {
 constexpr int kSlice = 32;       // SELL slice height C (= warp size)
 constexpr int kBlock = 256;      // threads per CTA for the streaming kernels (8 slices)
 constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
+// tuning knobs of the hot kernels (override with -DCPPPD_GATHER_CHUNK=.. -DCPPPD_MIN_BLOCKS=.. through
+// the CPPPD_NVCC_DEFINES environment variable of pysparselp_b200/build.py)
+#ifndef CPPPD_GATHER_CHUNK
+#define CPPPD_GATHER_CHUNK 4
+#endif
+#ifndef CPPPD_MIN_BLOCKS
+#define CPPPD_MIN_BLOCKS 8
+#endif
+constexpr int kGatherChunk = CPPPD_GATHER_CHUNK;  // entries of a row whose gathers are in flight together
+constexpr int kMinBlocks = CPPPD_MIN_BLOCKS;      // CTAs per SM the hot kernels are compiled for (register cap)
 constexpr int kColQ = 4;         // column-pass partial sums per CTA
 constexpr int kRowQ = 7;         // row-pass partial sums per CTA
 constexpr int kStatQ = kColQ + kRowQ;
