@@ -74,7 +74,10 @@ enum {
   /* world_size > 1: exchange the halos with NCCL send/recv instead of the peer-memory push kernels */
   CPPPD_FLAG_NO_P2P = 1u << 5,
   /* one GPU: never renumber, whatever the padding */
-  CPPPD_FLAG_NO_REORDER = 1u << 6
+  CPPPD_FLAG_NO_REORDER = 1u << 6,
+  /* world_size > 1, peer-memory halos: exchange them with separate push / wait kernels instead of
+   * inside k_primal / k_dual */
+  CPPPD_FLAG_NO_FUSED_HALO = 1u << 7
 };
 
 typedef struct {

@@ -22,6 +22,7 @@ FLAG_REORDER = 1 << 3
 FLAG_GRAPH_COMM = 1 << 4
 FLAG_NO_P2P = 1 << 5
 FLAG_NO_REORDER = 1 << 6
+FLAG_NO_FUSED_HALO = 1 << 7
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 

@@ -162,6 +162,8 @@ int detect_dictionary(cpppd_solver *h, Scratch &tmp, const double *values, int64
   return 0;
 }
 
+int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const std::vector<int64_t> &dst_base_y);
+
 // What every rank publishes so that its neighbours can write into its ghost slots.
 struct PeerRecord {
   cudaIpcMemHandle_t xbar, y, flags;
@@ -221,6 +223,7 @@ int setup_p2p(cpppd_solver *h) {
     pp.ptrs[0].flags[t] = pp.ptrs[1].flags[t] = (unsigned long long *)pf;
   }
   // per-entry destinations of the two send lists
+  std::vector<int64_t> dst_base[2] = {std::vector<int64_t>(N, 0), std::vector<int64_t>(N, 0)};
   for (int kind = 0; kind < 2; ++kind) {
     Halo &H = kind ? h->hy : h->hx;
     std::vector<int32_t> peer(H.send_total);
@@ -229,6 +232,7 @@ int setup_p2p(cpppd_solver *h) {
       if (H.send_count[t]) pp.send_mask[kind] |= 1ull << t;
       if (H.recv_count[t]) pp.recv_mask[kind] |= 1ull << t;
       const int64_t base = (kind ? all[t].owned_y : all[t].owned_x) + (kind ? all[t].recv_off_y[me] : all[t].recv_off_x[me]);
+      dst_base[kind][t] = base;
       for (int64_t k = 0; k < H.send_count[t]; ++k) {
         peer[H.send_off[t] + k] = t;
         dst[H.send_off[t] + k] = base + k;
@@ -241,6 +245,7 @@ int setup_p2p(cpppd_solver *h) {
       CK(cudaMemcpy(pp.push_dst[kind], dst.data(), sizeof(int64_t) * H.send_total, cudaMemcpyHostToDevice));
     }
   }
+  if (int rc = setup_fused(h, dst_base[0], dst_base[1])) return rc;
   // nobody may push before every rank has initialised its vectors and flags
   NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
   CK(cudaStreamSynchronize(st));
@@ -258,6 +263,54 @@ int exchange_p2p(cpppd_solver *h, int kind) {
                                                             H.send_total, pp.ptrs[kind], kind, h->world, h->rank,
                                                             pp.send_mask[kind], pp.state);
   if (pp.recv_mask[kind]) k_wait<<<1, kMaxWorld, 0, h->stream>>>(pp.flags, kind, h->world, pp.recv_mask[kind], pp.state);
+  return 0;
+}
+
+// device tables for the halo exchange fused into k_primal / k_dual
+int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const std::vector<int64_t> &dst_base_y) {
+  P2P &pp = h->p2p;
+  cudaStream_t st = h->stream;
+  const int N = h->world;
+  Scratch tmp(h);
+  for (int kind = 0; kind < 2; ++kind) {  // kind 0: k_primal over A^T produces xbar; kind 1: k_dual over A produces y
+    const Sell &S = kind ? h->A : h->AT;
+    const Halo &out = kind ? h->hy : h->hx;
+    const int64_t owned_other = kind ? h->hx.owned : h->hy.owned;  // entry indices >= this are ghosts
+    const int64_t ns = S.nslices;
+    unsigned int *role32 = nullptr;
+    unsigned char *role = nullptr;
+    if (int rc = tmp.get(&role32, ns + 1)) return rc;
+    if (int rc = alloc_array(h, &role, ns + 1)) return rc;
+    CK(cudaMemsetAsync(role32, 0, sizeof(unsigned int) * (ns + 1), st));
+    const int64_t items = std::max<int64_t>(ns * 32, out.send_total);
+    if (items) k_slice_roles<<<grid_for(items), kBlock, 0, st>>>(view(S), owned_other, out.send_idx, out.send_total, role32);
+    k_narrow_roles<<<grid_for(ns + 1), kBlock, 0, st>>>(role32, ns + 1, role);
+    FusedComm cm;
+    memset(&cm, 0, sizeof cm);
+    cm.role = role;
+    cm.send_idx = out.send_idx;
+    const std::vector<int64_t> &dst_base = kind ? dst_base_y : dst_base_x;
+    for (int t = 0; t < N; ++t) {
+      cm.off[t] = out.send_off[t];
+      cm.cnt[t] = out.send_count[t];
+      cm.dst_base[t] = dst_base[t];
+      cm.peer_vec[t] = pp.ptrs[kind].vec[t];
+      cm.peer_flags[t] = pp.ptrs[kind].flags[t];
+    }
+    cm.my_flags = pp.flags;
+    cm.st = pp.state;
+    cm.world = N;
+    cm.me = h->rank;
+    cm.kind_out = kind;
+    cm.kind_in = 1 - kind;
+    cm.send_mask = pp.send_mask[kind];
+    cm.recv_mask_in = pp.recv_mask[1 - kind];
+    if (int rc = alloc_array(h, &pp.fused[kind], 1)) return rc;
+    CK(cudaMemcpyAsync(pp.fused[kind], &cm, sizeof cm, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    tmp.release(role32);
+  }
+  pp.use_fused = !(h->flags & CPPPD_FLAG_NO_FUSED_HALO);
   return 0;
 }
 
@@ -681,31 +734,39 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
 }
 
 template <bool kWriteD, bool kDict>
-void launch_primal_t(cpppd_solver *h) {
+void launch_primal_t(cpppd_solver *h, const FusedComm *cm) {
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
   k_primal<kWriteD, kDict, kGatherChunk><<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(
       view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
-      h->one_plus_theta);
+      h->one_plus_theta, cm);
 }
 
+// Primal half + xbar halo.  world > 1: fused (the kernel waits, pushes and signals by itself over peer
+// memory), or k_push / k_wait kernels (CPPPD_FLAG_NO_FUSED_HALO), or NCCL send/recv (CPPPD_FLAG_NO_P2P).
 int launch_primal(cpppd_solver *h, bool write_d) {
+  P2P &pp = h->p2p;
+  const FusedComm *cm = pp.use_fused ? pp.fused[0] : nullptr;
   if (h->AT.nslices) {
     const bool dict = h->AT.dict != nullptr;
-    if (write_d) dict ? launch_primal_t<true, true>(h) : launch_primal_t<true, false>(h);
-    else dict ? launch_primal_t<false, true>(h) : launch_primal_t<false, false>(h);
+    if (write_d) dict ? launch_primal_t<true, true>(h, cm) : launch_primal_t<true, false>(h, cm);
+    else dict ? launch_primal_t<false, true>(h, cm) : launch_primal_t<false, false>(h, cm);
   }
-  return h->p2p.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
+  if (cm) return 0;
+  return pp.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
 }
 
 int launch_dual(cpppd_solver *h) {
+  P2P &pp = h->p2p;
+  const FusedComm *cm = pp.use_fused ? pp.fused[1] : nullptr;
   if (h->A.nslices) {
     const int grid = grid_for(h->A.nslices * 32);
     if (h->A.dict)
-      k_dual<true, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+      k_dual<true, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
     else
-      k_dual<false, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq);
+      k_dual<false, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
   }
-  return h->p2p.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
+  if (cm) return 0;
+  return pp.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
 }
 
 int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {

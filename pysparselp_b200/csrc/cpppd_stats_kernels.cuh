@@ -152,15 +152,6 @@ __global__ void k_init_stats(StatsDev *st) {
   st->s.best_integer_energy = INFINITY;  // :192
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // Halo push over peer memory: entry k of the send list goes to peer push_peer[k], element
 // push_dst[k] of that peer's vector (its ghost slot).  The last CTA to finish raises, on every
 // neighbour it sent to, the flag [kind * world + me] to the new stamp (release at system scope after
@@ -194,6 +185,29 @@ __global__ void k_wait(const unsigned long long *__restrict__ flags, int kind, i
   }
   __syncthreads();
   if (t == 0) st->wait_stamp[kind] = want;
+}
+
+// role byte of every slice (see FusedComm): bit 0 = holds a row that is sent, bit 1 = reads a ghost
+__global__ void k_slice_roles(SellView S, int64_t owned_other, const int32_t *__restrict__ send_idx,
+                              int64_t send_total, unsigned int *__restrict__ role32) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < send_total) atomicOr(role32 + (send_idx[t] >> 5), 1u);
+  const int64_t s = t >> 5;
+  if (s >= S.nslices) return;
+  const int lane = threadIdx.x & 31;
+  int64_t p0, p1;
+  slice_range(S, s, p0, p1);
+  bool ghost = false;
+  for (int64_t p = p0 + lane; p < p1; p += kSlice) {
+    const int32_t w = S.idx[p];
+    if (w >= 0 && (w & S.idx_mask) >= owned_other) ghost = true;
+  }
+  if (__any_sync(0xffffffffu, ghost) && lane == 0) atomicOr(role32 + s, 2u);
+}
+
+__global__ void k_narrow_roles(const unsigned int *__restrict__ role32, int64_t count, unsigned char *__restrict__ role) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < count) role[s] = (unsigned char)role32[s];
 }
 
 // halo staging: buf[k] = vec[idx[k]]

@@ -111,6 +111,7 @@ struct Halo {
 // that every neighbour maps through CUDA IPC; a push kernel stores the halo values straight into the
 // neighbours' ghost slots over NVLink and then raises a per-neighbour flag, a wait kernel spins on
 // the local flags.  No staging buffer, no NCCL call, and the whole iteration is graph-capturable.
+struct FusedComm;
 struct PeerPtrs {
   double *vec[kMaxWorld];
   unsigned long long *flags[kMaxWorld];
@@ -128,6 +129,9 @@ struct P2P {
   int32_t *push_peer[2] = {nullptr, nullptr};
   int64_t *push_dst[2] = {nullptr, nullptr};
   unsigned long long send_mask[2] = {0, 0}, recv_mask[2] = {0, 0};
+  // halo exchange fused into k_primal ([0], produces xbar) and k_dual ([1], produces y)
+  FusedComm *fused[2] = {nullptr, nullptr};
+  bool use_fused = false;
   std::vector<void *> opened, own;
 };
 
