@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CPPPD_ABI_VERSION 2
+#define CPPPD_ABI_VERSION 3
 
 typedef struct cpppd_solver *cpppd_handle;
 
@@ -113,6 +113,8 @@ typedef struct {
   int32_t world_size;   /* <= 1: single GPU */
   const void *comm_id;  /* 128 bytes, required when world_size > 1 */
   int64_t partition_granule; /* locality bucket width in columns; <= 0: default */
+  void *comm;           /* optional cpppd_comm created by cpppd_comm_create(): reused (and not destroyed) by
+                           this solver instead of building a new communicator from comm_id */
 } cpppd_problem;
 
 /* The numbers the reference's stats block produces (ChambollePockPPD.py:242-291). */
@@ -173,6 +175,11 @@ const char *cpppd_last_error(cpppd_handle h);
 int cpppd_abi_version(void);
 /* 128-byte NCCL unique id for a new multi-GPU solve (call on one rank, broadcast, pass as comm_id). */
 int cpppd_comm_unique_id(void *out128);
+/* A communicator that outlives one solver: building one costs far more than a short solve, so the
+ * Python front keeps one per process group and passes it through cpppd_problem.comm. */
+typedef struct cpppd_comm_s *cpppd_comm;
+int cpppd_comm_create(const void *id128, int32_t rank, int32_t world_size, int32_t device, cpppd_comm *out);
+int cpppd_comm_destroy(cpppd_comm comm);
 
 /* -- the iteration (ChambollePockPPD.py:195-343) ----------------------------------- */
 /* k full iterations: [x,xbar <- primal(y)] ; [y <- dual(xbar)], asynchronous. */

@@ -24,6 +24,9 @@ import scipy.sparse as sp
 
 from . import _cabi
 
+# (process group, device) -> cpppd_comm, kept for the life of the process
+_COMM_CACHE = {}
+
 
 def _as_f64(v, size, name):
     a = np.ascontiguousarray(v, dtype=np.float64).ravel()
@@ -99,9 +102,9 @@ class CpPpdSolver:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.rank, self.world = 0, 1
-        comm_id = None
+        comm = None
         if process_group is not None:
-            comm_id = self._negotiate_comm_id(process_group, dev)
+            comm = self._shared_comm(process_group, dev)
         a = sp.csr_matrix(a) if not sp.isspmatrix_csr(a) else a
         m, n = a.shape
         self.n, self.m, self.m_eq = n, m, int(m_eq)
@@ -117,7 +120,7 @@ class CpPpdSolver:
         indptr = np.ascontiguousarray(a.indptr)
         if indptr.dtype not in (np.int32, np.int64):
             indptr = indptr.astype(np.int64)
-        self._keep = (c, lb, ub, b, x0, data, indices, indptr, comm_id)
+        self._keep = (c, lb, ub, b, x0, data, indices, indptr)
         self._buffers = _TorchBuffers(dev)
         p = _cabi.Problem()
         p.abi_version = _cabi.ABI_VERSION
@@ -139,7 +142,8 @@ class CpPpdSolver:
         p.free = self._buffers.free_cb
         p.alloc_user = None
         p.rank, p.world_size = self.rank, self.world
-        p.comm_id = None if comm_id is None else comm_id.ctypes.data
+        p.comm_id = None
+        p.comm = comm
         p.partition_granule = int(partition_granule)
         handle = C.c_void_p()
         with torch.cuda.device(dev):
@@ -147,8 +151,9 @@ class CpPpdSolver:
         self.handle = handle
         self._keep = None  # host arrays are only read during create
 
-    def _negotiate_comm_id(self, group, dev):
-        """One NCCL communicator per solve: rank 0 draws the id, torch.distributed broadcasts it."""
+    def _shared_comm(self, group, dev):
+        """NCCL communicator of (process group, device), built once and kept for later solves: rank 0
+        draws the id, torch.distributed broadcasts it, cpppd_comm_create joins."""
         import os
 
         import torch
@@ -159,6 +164,9 @@ class CpPpdSolver:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world == 1:
             return None
+        key = ("WORLD" if group is dist.group.WORLD else id(group), dev.index)
+        if key in _COMM_CACHE:
+            return _COMM_CACHE[key]
         if "CPPPD_NCCL_LIB" not in os.environ:  # use the NCCL that torch itself loaded
             try:
                 import nvidia.nccl
@@ -174,7 +182,13 @@ class CpPpdSolver:
         on_gpu = dist.get_backend(group) == "nccl"
         t = torch.from_numpy(ident).to(dev) if on_gpu else torch.from_numpy(ident)
         dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
-        return t.cpu().numpy().copy()
+        ident = t.cpu().numpy().copy()
+        comm = C.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib, None, self.lib.cpppd_comm_create(ident.ctypes.data, self.rank, self.world, dev.index,
+                                                                   C.byref(comm)))
+        _COMM_CACHE[key] = comm
+        return comm
 
     def layout(self, columns=True):
         """(owned original ids, ghost original ids) of this rank, local order."""

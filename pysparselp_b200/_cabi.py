@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
@@ -38,7 +38,7 @@ class Problem(C.Structure):
         ("stream", C.c_void_p), ("flags", C.c_uint32), ("sort_window", C.c_int32),
         ("alloc", ALLOC_FN), ("free", FREE_FN), ("alloc_user", C.c_void_p),
         ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.c_void_p),
-        ("partition_granule", C.c_int64),
+        ("partition_granule", C.c_int64), ("comm", C.c_void_p),
     ]
 
 
@@ -77,6 +77,8 @@ class Info(C.Structure):
 SYMBOLS = {
     "cpppd_abi_version": (C.c_int, []),
     "cpppd_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "cpppd_comm_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cpppd_comm_destroy": (C.c_int, [C.c_void_p]),
     "cpppd_create": (C.c_int, [C.POINTER(Problem), C.POINTER(C.c_void_p)]),
     "cpppd_destroy": (C.c_int, [C.c_void_p]),
     "cpppd_last_error": (C.c_char_p, [C.c_void_p]),

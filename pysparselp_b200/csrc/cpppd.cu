@@ -93,6 +93,34 @@ int cpppd_comm_unique_id(void *out128) {
   return 0;
 }
 
+int cpppd_comm_create(const void *id128, int32_t rank, int32_t world_size, int32_t device, cpppd_comm *out) {
+  cpppd_solver *h = nullptr;
+  if (!id128 || !out || world_size < 2 || rank < 0 || rank >= world_size) return fail(h, CPPPD_ERR_INVALID, "bad argument");
+  *out = nullptr;
+  if (const char *e = load_nccl()) return fail(h, CPPPD_ERR_COMM, "%s", e);
+  CK(cudaSetDevice(device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  cpppd_comm_s *c = new cpppd_comm_s();
+  c->rank = rank;
+  c->world = world_size;
+  c->device = device;
+  ncclResult_t r = g_nccl.CommInitRank(&c->comm, world_size, id, rank);
+  if (r != ncclSuccess) {
+    delete c;
+    return fail(h, CPPPD_ERR_COMM, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+  }
+  *out = c;
+  return 0;
+}
+
+int cpppd_comm_destroy(cpppd_comm comm) {
+  if (!comm) return 0;
+  if (comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm->comm);
+  delete comm;
+  return 0;
+}
+
 int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   cpppd_solver *h = nullptr;
   if (!P || !out) return fail(h, CPPPD_ERR_INVALID, "null argument");
@@ -107,7 +135,8 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   if (P->indptr_bits != 32 && P->indptr_bits != 64) return fail(h, CPPPD_ERR_INVALID, "indptr_bits must be 32 or 64");
   const int world = P->world_size <= 0 ? 1 : P->world_size;
   if (world > kMaxWorld || P->rank < 0 || P->rank >= world) return fail(h, CPPPD_ERR_INVALID, "bad rank / world_size");
-  if (world > 1 && !P->comm_id) return fail(h, CPPPD_ERR_INVALID, "world_size > 1 needs comm_id (cpppd_comm_unique_id)");
+  if (world > 1 && !P->comm_id && !P->comm)
+    return fail(h, CPPPD_ERR_INVALID, "world_size > 1 needs comm_id (cpppd_comm_unique_id) or comm (cpppd_comm_create)");
   const int64_t m = P->m_eq + P->m_ineq;
   if (!P->indptr || (P->nnz && (!P->indices || !P->values)) || (P->n && (!P->c || !P->lb || !P->ub)) || (m && !P->b))
     return fail(h, CPPPD_ERR_INVALID, "null array pointer");
@@ -155,7 +184,15 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
       }
       h->own_stream = true;
     }
-    if (world > 1) {
+    if (world > 1 && P->comm) {
+      cpppd_comm_s *shared = static_cast<cpppd_comm_s *>(P->comm);
+      if (shared->world != world || shared->rank != h->rank || shared->device != h->device) {
+        rc = fail(h, CPPPD_ERR_INVALID, "cpppd_problem.comm was created for another rank / world size / device");
+        break;
+      }
+      h->comm = shared->comm;
+      h->own_comm = false;
+    } else if (world > 1) {
       if (const char *e = load_nccl()) {
         rc = fail(h, CPPPD_ERR_COMM, "%s", e);
         break;
@@ -191,7 +228,7 @@ int cpppd_destroy(cpppd_handle h) {
   }
   for (void *p : h->p2p.opened) cudaIpcCloseMemHandle(p);
   for (void *p : h->p2p.own) cudaFree(p);
-  if (h->comm) g_nccl.CommDestroy(h->comm);
+  if (h->comm && h->own_comm) g_nccl.CommDestroy(h->comm);
   for (void *p : h->owned) dev_free(h, p);
   if (h->stats_host) cudaFreeHost(h->stats_host);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

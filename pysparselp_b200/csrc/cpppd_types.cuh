@@ -179,6 +179,11 @@ const char *load_nccl() {
 
 }  // namespace
 
+struct cpppd_comm_s {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+};
+
 struct cpppd_solver {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -193,6 +198,7 @@ struct cpppd_solver {
   int32_t *row_old = nullptr;   // m + ghosts : original row id of a local row
   Halo hx, hy;                  // xbar-like vectors (columns) / y-like vectors (rows)
   ncclComm_t comm = nullptr;
+  bool own_comm = true;         // false: borrowed from a cpppd_comm (cpppd_problem.comm)
   P2P p2p;
   double alpha = 1, theta = 1, one_plus_theta = 2;
   uint32_t flags = 0;
