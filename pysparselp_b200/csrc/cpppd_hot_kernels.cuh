@@ -7,6 +7,7 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // halo exchange fused into the hot kernels (multi-GPU, peer memory over NVLink)
 // ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -15,7 +16,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-
+#else  // CPU emulation of the kernels (tests/emul): one thread at a time, plain accesses
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
+#endif
 
 // Device-resident description of the halo a kernel produces (kind_out) and consumes (kind_in).
 // role[s] of a slice: bit 0 = some row of the slice is sent to a neighbour, bit 1 = some row reads a

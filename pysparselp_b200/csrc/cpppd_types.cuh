@@ -22,30 +22,9 @@
 #include <string>
 #include <vector>
 
-namespace {
+#include "cpppd_device_types.cuh"
 
-constexpr int kSlice = 32;       // SELL slice height C (= warp size)
-constexpr int kBlock = 256;      // threads per CTA for the streaming kernels (8 slices)
-constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
-// tuning knobs of the hot kernels (override with -DCPPPD_GATHER_CHUNK=.. -DCPPPD_MIN_BLOCKS=.. through
-// the CPPPD_NVCC_DEFINES environment variable of pysparselp_b200/build.py)
-#ifndef CPPPD_GATHER_CHUNK
-#define CPPPD_GATHER_CHUNK 4
-#endif
-#ifndef CPPPD_MIN_BLOCKS
-#define CPPPD_MIN_BLOCKS 8
-#endif
-constexpr int kGatherChunk = CPPPD_GATHER_CHUNK;  // entries of a row whose gathers are in flight together
-constexpr int kMinBlocks = CPPPD_MIN_BLOCKS;      // CTAs per SM the hot kernels are compiled for (register cap)
-constexpr int kColQ = 4;         // column-pass partial sums per CTA
-constexpr int kRowQ = 7;         // row-pass partial sums per CTA
-constexpr int kStatQ = kColQ + kRowQ;
-constexpr int32_t kEqBit = 0x40000000;   // A^T entries: set when the source row is an equality
-constexpr int32_t kIdxMask = 0x3fffffff;
-// padding entry of a slice: negative, and its masked index is 0 so that a gather the compiler
-// hoists above the `idx >= 0` test still reads a valid address
-constexpr int32_t kPad = INT32_MIN;
-constexpr int kMaxWorld = 64;
+namespace {
 
 thread_local std::string g_create_error;
 
@@ -60,40 +39,6 @@ struct Sell {
   const double *dict = nullptr;
   int idx_bits = 30, ndict = 0;
 };
-
-struct SellView {
-  const int64_t *__restrict__ slice_ptr;
-  const int32_t *__restrict__ idx;
-  const double *__restrict__ val;
-  int64_t nrows, nslices;
-  int64_t uniform_width;  // -1: read slice_ptr
-  const double *__restrict__ dict;
-  int32_t idx_mask;       // low bits of an entry word that hold the gather index
-  int32_t idx_bits, code_mask, ndict;
-};
-
-// a vector operand that may have been folded into a scalar (CPPPD_FLAG_CONST_VECTORS)
-struct Vec {
-  const double *p;
-  double c;
-  __device__ __forceinline__ double at(int64_t i) const { return p ? __ldcs(p + i) : c; }
-};
-
-// first / one-past-last element offset of slice s
-__device__ __forceinline__ void slice_range(const SellView &S, int64_t s, int64_t &p0, int64_t &p1) {
-  if (S.uniform_width >= 0) {
-    p0 = s * S.uniform_width * 32;
-    p1 = p0 + S.uniform_width * 32;
-  } else {
-    p0 = __ldg(S.slice_ptr + s);
-    p1 = __ldg(S.slice_ptr + s + 1);
-  }
-}
-
-// value of the entry stored at position p whose index word is w (non-hot kernels)
-__device__ __forceinline__ double entry_value(const SellView &S, int64_t p, int32_t w) {
-  return S.dict ? S.dict[(w >> S.idx_bits) & S.code_mask] : S.val[p];
-}
 
 struct StatsDev {  // device-resident, copied verbatim into cpppd_stats
   cpppd_stats s;
@@ -115,11 +60,6 @@ struct FusedComm;
 struct PeerPtrs {
   double *vec[kMaxWorld];
   unsigned long long *flags[kMaxWorld];
-};
-struct SyncState {
-  unsigned long long push_stamp[2];  // halos pushed so far        ([0] xbar, [1] y)
-  unsigned long long wait_stamp[2];  // halos consumed so far
-  unsigned int ticket[2];            // CTA arrival counter of k_push
 };
 struct P2P {
   bool active = false;
