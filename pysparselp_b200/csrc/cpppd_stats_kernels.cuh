@@ -152,6 +152,7 @@ __global__ void k_init_stats(StatsDev *st) {
   st->s.best_integer_energy = INFINITY;  // :192
 }
 
+#ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -160,6 +161,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#else  // host build of the sources for the CPU emulator (tests/emul): single OS thread, plain accesses
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
+#endif
 
 // Halo push over peer memory: entry k of the send list goes to peer push_peer[k], element
 // push_dst[k] of that peer's vector (its ghost slot).  The last CTA to finish raises, on every
