@@ -188,7 +188,6 @@ def _check():
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from conftest import case_args
-    from oracle.cpppd_oracle import chambolle_pock_ppd_oracle
 
     dist.init_process_group("gloo")
     for name in ("potts50", "sc105", "random_small"):

@@ -85,110 +85,50 @@ class _TorchBuffers:
         self.live.pop(ptr, None)
 
 
-class CpPpdSolver:
-    """Live solver state on one GPU (thin wrapper over a ``cpppd_handle``)."""
+def prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule):
+    """``cpppd_problem`` with the host-side fields filled from numpy / scipy operands.
 
-    def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
-                 sort_window=1, process_group=None, partition_granule=0):
-        import torch
+    Returns ``(problem, keepalive)``; the arrays in ``keepalive`` must outlive ``cpppd_create``.
+    Device, stream, allocator and multi-GPU fields are left to the caller.
+    """
+    a = sp.csr_matrix(a) if not sp.isspmatrix_csr(a) else a
+    m, n = a.shape
+    c = _as_f64(c, n, "c")
+    lb = _as_f64(lb, n, "lb")
+    ub = _as_f64(ub, n, "ub")
+    b = _as_f64(b, m, "b")
+    x0 = None if x0 is None else _as_f64(x0, n, "x0")
+    data = np.ascontiguousarray(a.data, dtype=np.float64)
+    indices = np.ascontiguousarray(a.indices)
+    if indices.dtype != np.int32:
+        indices = indices.astype(np.int32)
+    indptr = np.ascontiguousarray(a.indptr)
+    if indptr.dtype not in (np.int32, np.int64):
+        indptr = indptr.astype(np.int64)
+    p = _cabi.Problem()
+    p.abi_version = _cabi.ABI_VERSION
+    p.n, p.m_eq, p.m_ineq, p.nnz = n, int(m_eq), m - int(m_eq), int(indptr[-1]) if m else 0
+    p.indptr = indptr.ctypes.data
+    p.indices = indices.ctypes.data
+    p.values = data.ctypes.data
+    p.indptr_bits = 32 if indptr.dtype == np.int32 else 64
+    p.index_bits = 32
+    p.c, p.b, p.lb, p.ub = c.ctypes.data, b.ctypes.data, lb.ctypes.data, ub.ctypes.data
+    p.x0 = None if x0 is None else x0.ctypes.data
+    p.alpha, p.theta = float(alpha), float(theta)
+    p.one_plus_theta = float(1 + theta)
+    p.flags = int(flags)
+    p.sort_window = 0
+    p.partition_granule = int(partition_granule)
+    p.rank, p.world_size = 0, 1
+    return p, (c, lb, ub, b, x0, data, indices, indptr)
 
-        self.lib = _cabi.load_library()
-        if not torch.cuda.is_available():
-            raise RuntimeError("pysparselp_b200 needs a CUDA device (B200); there is no CPU fallback")
-        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        if dev.type != "cuda":
-            raise ValueError("device must be a CUDA device")
-        if dev.index is None:
-            dev = torch.device("cuda", torch.cuda.current_device())
-        self.device = dev
-        self.rank, self.world = 0, 1
-        comm = None
-        if process_group is not None:
-            comm = self._shared_comm(process_group, dev)
-        a = sp.csr_matrix(a) if not sp.isspmatrix_csr(a) else a
-        m, n = a.shape
-        self.n, self.m, self.m_eq = n, m, int(m_eq)
-        c = _as_f64(c, n, "c")
-        lb = _as_f64(lb, n, "lb")
-        ub = _as_f64(ub, n, "ub")
-        b = _as_f64(b, m, "b")
-        x0 = None if x0 is None else _as_f64(x0, n, "x0")
-        data = np.ascontiguousarray(a.data, dtype=np.float64)
-        indices = np.ascontiguousarray(a.indices)
-        if indices.dtype != np.int32:
-            indices = indices.astype(np.int32)
-        indptr = np.ascontiguousarray(a.indptr)
-        if indptr.dtype not in (np.int32, np.int64):
-            indptr = indptr.astype(np.int64)
-        self._keep = (c, lb, ub, b, x0, data, indices, indptr)
-        self._buffers = _TorchBuffers(dev)
-        p = _cabi.Problem()
-        p.abi_version = _cabi.ABI_VERSION
-        p.device = dev.index
-        p.n, p.m_eq, p.m_ineq, p.nnz = n, int(m_eq), m - int(m_eq), int(indptr[-1]) if m else 0
-        p.indptr = indptr.ctypes.data
-        p.indices = indices.ctypes.data
-        p.values = data.ctypes.data
-        p.indptr_bits = 32 if indptr.dtype == np.int32 else 64
-        p.index_bits = 32
-        p.c, p.b, p.lb, p.ub = c.ctypes.data, b.ctypes.data, lb.ctypes.data, ub.ctypes.data
-        p.x0 = None if x0 is None else x0.ctypes.data
-        p.alpha, p.theta = float(alpha), float(theta)
-        p.one_plus_theta = float(1 + theta)
-        p.stream = torch.cuda.current_stream(dev).cuda_stream or None
-        p.flags = int(flags)
-        p.sort_window = int(sort_window)
-        p.alloc = self._buffers.alloc_cb
-        p.free = self._buffers.free_cb
-        p.alloc_user = None
-        p.rank, p.world_size = self.rank, self.world
-        p.comm_id = None
-        p.comm = comm
-        p.partition_granule = int(partition_granule)
-        handle = C.c_void_p()
-        with torch.cuda.device(dev):
-            _cabi.check(self.lib, None, self.lib.cpppd_create(C.byref(p), C.byref(handle)))
-        self.handle = handle
-        self._keep = None  # host arrays are only read during create
 
-    def _shared_comm(self, group, dev):
-        """NCCL communicator of (process group, device), built once and kept for later solves: rank 0
-        draws the id, torch.distributed broadcasts it, cpppd_comm_create joins."""
-        import os
+class SolverHandle:
+    """Methods of a live ``cpppd_handle`` (``self.lib``, ``self.handle``, ``self.n``, ``self.m``)."""
 
-        import torch
-        import torch.distributed as dist
-
-        if group is True:
-            group = dist.group.WORLD
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        if self.world == 1:
-            return None
-        key = ("WORLD" if group is dist.group.WORLD else id(group), dev.index)
-        if key in _COMM_CACHE:
-            return _COMM_CACHE[key]
-        if "CPPPD_NCCL_LIB" not in os.environ:  # use the NCCL that torch itself loaded
-            try:
-                import nvidia.nccl
-
-                cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
-                if os.path.isfile(cand):
-                    os.environ["CPPPD_NCCL_LIB"] = cand
-            except Exception:
-                pass
-        ident = np.zeros(128, dtype=np.uint8)
-        if self.rank == 0:
-            _cabi.check(self.lib, None, self.lib.cpppd_comm_unique_id(ident.ctypes.data))
-        on_gpu = dist.get_backend(group) == "nccl"
-        t = torch.from_numpy(ident).to(dev) if on_gpu else torch.from_numpy(ident)
-        dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
-        ident = t.cpu().numpy().copy()
-        comm = C.c_void_p()
-        with torch.cuda.device(dev):
-            _cabi.check(self.lib, None, self.lib.cpppd_comm_create(ident.ctypes.data, self.rank, self.world, dev.index,
-                                                                   C.byref(comm)))
-        _COMM_CACHE[key] = comm
-        return comm
+    def _result_buffer(self, size):
+        return np.empty(size, dtype=np.float64)
 
     def layout(self, columns=True):
         """(owned original ids, ghost original ids) of this rank, local order."""
@@ -244,14 +184,7 @@ class CpPpdSolver:
 
     # -- state ------------------------------------------------------------------------------
     def _get(self, which, size):
-        # large results land in pinned host memory (torch's caching host allocator): the D2H copy
-        # then runs at PCIe speed instead of going through a pageable staging buffer
-        if size >= (1 << 16):
-            import torch
-
-            out = torch.empty(size, dtype=torch.float64, pin_memory=True).numpy()
-        else:
-            out = np.empty(size, dtype=np.float64)
+        out = self._result_buffer(size)
         self._call(self.lib.cpppd_get_vector, which, out.ctypes.data)
         return out
 
@@ -299,7 +232,6 @@ class CpPpdSolver:
         if getattr(self, "handle", None):
             self.lib.cpppd_destroy(self.handle)
             self.handle = None
-            self._buffers.live.clear()
 
     def __del__(self):
         try:
@@ -312,6 +244,97 @@ class CpPpdSolver:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class CpPpdSolver(SolverHandle):
+    """Live solver state on one GPU: the only way the product creates a ``cpppd_handle``."""
+
+    def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
+                 process_group=None, partition_granule=0):
+        import torch
+
+        self.lib = _cabi.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("pysparselp_b200 needs a CUDA device (B200); there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.rank, self.world = 0, 1
+        comm = None
+        if process_group is not None:
+            comm = self._shared_comm(process_group, dev)
+        p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule)
+        self.n, self.m, self.m_eq = int(p.n), int(p.m_eq + p.m_ineq), int(p.m_eq)
+        self._buffers = _TorchBuffers(dev)
+        p.device = dev.index
+        p.stream = torch.cuda.current_stream(dev).cuda_stream or None
+        p.alloc = self._buffers.alloc_cb
+        p.free = self._buffers.free_cb
+        p.alloc_user = None
+        p.rank, p.world_size = self.rank, self.world
+        p.comm_id = None
+        p.comm = comm
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib, None, self.lib.cpppd_create(C.byref(p), C.byref(handle)))
+        del keep  # host arrays are only read during create
+        self.handle = handle
+
+    def _result_buffer(self, size):
+        # large results land in pinned host memory (torch's caching host allocator): the D2H copy
+        # then runs at PCIe speed instead of going through a pageable staging buffer
+        if size >= (1 << 16):
+            import torch
+
+            return torch.empty(size, dtype=torch.float64, pin_memory=True).numpy()
+        return np.empty(size, dtype=np.float64)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            super().close()
+            self._buffers.live.clear()
+
+    def _shared_comm(self, group, dev):
+        """NCCL communicator of (process group, device), built once and kept for later solves: rank 0
+        draws the id, torch.distributed broadcasts it, cpppd_comm_create joins."""
+        import os
+
+        import torch
+        import torch.distributed as dist
+
+        if group is True:
+            group = dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world == 1:
+            return None
+        key = ("WORLD" if group is dist.group.WORLD else id(group), dev.index)
+        if key in _COMM_CACHE:
+            return _COMM_CACHE[key]
+        if "CPPPD_NCCL_LIB" not in os.environ:  # use the NCCL that torch itself loaded
+            try:
+                import nvidia.nccl
+
+                cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
+                if os.path.isfile(cand):
+                    os.environ["CPPPD_NCCL_LIB"] = cand
+            except Exception:
+                pass
+        ident = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            _cabi.check(self.lib, None, self.lib.cpppd_comm_unique_id(ident.ctypes.data))
+        on_gpu = dist.get_backend(group) == "nccl"
+        t = torch.from_numpy(ident).to(dev) if on_gpu else torch.from_numpy(ident)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0), group=group)
+        ident = t.cpu().numpy().copy()
+        comm = C.c_void_p()
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib, None, self.lib.cpppd_comm_create(ident.ctypes.data, self.rank, self.world, dev.index,
+                                                                   C.byref(comm)))
+        _COMM_CACHE[key] = comm
+        return comm
 
 
 def stack_operator(a_eq, beq, a_ineq, b_ineq, n):
@@ -374,6 +397,48 @@ def _resolve_group(distributed):
             return dist.group.WORLD
         return None
     return distributed
+
+
+def run_schedule(solver, nb_max_iter, callback_func=None, max_time=None, force_integer=False, nb_iter_plot=10,
+                 verbose=False, start=None):
+    """The reference's ``while`` loop (``:195-343``) driven over a live solver handle.
+
+    Iterations are issued asynchronously in blocks of ``nb_iter_plot``; the host only waits at the
+    stats iterations (``niter % nb_iter_plot == 0``, including 0).  Returns ``(x, best_integer)``.
+    """
+    start = time.perf_counter() if start is None else start
+    nb_iter_plot = int(nb_iter_plot)
+    if nb_iter_plot < 1:
+        raise ValueError("nb_iter_plot must be >= 1")
+    niter = 0
+    while niter < nb_max_iter:
+        # iteration `niter` is a stats iteration (niter % nb_iter_plot == 0 by construction)
+        solver.primal_step(keep_d=True)
+        if max_time is not None:
+            solver.sync()
+        elapsed = time.perf_counter() - start
+        if max_time is not None and elapsed > max_time:
+            break
+        solver.stats_step(force_integer)
+        st = solver.read_stats()
+        if verbose:
+            print("iter%d: energy1= %r energy2=%r elapsed %r second max violated inequality:%r "
+                  "max violated equality:%r x3 has %r %% of zeros" % (
+                      niter, st["energy1"], st["energy2"], elapsed, st["max_violated_inequality"],
+                      st["max_violated_equality"], 100 * st["frac_zero_xbar"]))
+        if callback_func is not None:
+            callback_func(niter, solver.get_x(), st["energy1"], st["energy2"], elapsed,
+                          st["max_violated_equality"], st["max_violated_inequality"])
+        solver.dual_step()
+        niter += 1
+        k = min(nb_iter_plot - 1, nb_max_iter - niter)
+        if k > 0:
+            solver.iterate(k)
+            niter += k
+    x = solver.get_x()
+    last = solver.read_stats_or_none()
+    best = solver.get_best_integer() if last is not None and last["have_best_integer"] else None
+    return x, best
 
 
 def chambolle_pock_ppd(
@@ -439,37 +504,7 @@ def chambolle_pock_ppd(
         x[c < 0] = ub[c < 0]
         return x
     try:
-        nb_iter_plot = int(nb_iter_plot)
-        if nb_iter_plot < 1:
-            raise ValueError("nb_iter_plot must be >= 1")
-        niter = 0
-        while niter < nb_max_iter:
-            # iteration `niter` is a stats iteration (niter % nb_iter_plot == 0 by construction)
-            solver.primal_step(keep_d=True)
-            if max_time is not None:
-                solver.sync()
-            elapsed = time.perf_counter() - start
-            if max_time is not None and elapsed > max_time:
-                break
-            solver.stats_step(force_integer)
-            st = solver.read_stats()
-            if verbose:
-                print("iter%d: energy1= %r energy2=%r elapsed %r second max violated inequality:%r "
-                      "max violated equality:%r x3 has %r %% of zeros" % (
-                          niter, st["energy1"], st["energy2"], elapsed, st["max_violated_inequality"],
-                          st["max_violated_equality"], 100 * st["frac_zero_xbar"]))
-            if callback_func is not None:
-                callback_func(niter, solver.get_x(), st["energy1"], st["energy2"], elapsed,
-                              st["max_violated_equality"], st["max_violated_inequality"])
-            solver.dual_step()
-            niter += 1
-            k = min(nb_iter_plot - 1, nb_max_iter - niter)
-            if k > 0:
-                solver.iterate(k)
-                niter += k
-        x = solver.get_x()
-        last = solver.read_stats_or_none()
-        best = solver.get_best_integer() if last is not None and last["have_best_integer"] else None
+        x, best = run_schedule(solver, nb_max_iter, callback_func, max_time, force_integer, nb_iter_plot, verbose, start)
     except BaseException:
         solver.close()
         raise

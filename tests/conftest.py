@@ -24,7 +24,7 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
-    if has_gpu:
+    if has_gpu or os.environ.get("CPPPD_EMULATE_GPU_TESTS"):  # see tests/emul/patch_plugin.py
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:

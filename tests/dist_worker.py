@@ -18,7 +18,6 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 
 def main():
-    import scipy.sparse as sp
     import torch
     import torch.distributed as dist
 

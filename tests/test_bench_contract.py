@@ -5,8 +5,6 @@ import os
 import subprocess
 import sys
 
-import pytest
-
 from conftest import ROOT
 
 

@@ -1,0 +1,154 @@
+"""CPU: the WHOLE CUDA library (setup, transpose, SELL build, preconditioners, hot kernels, stats block,
+CUDA-graph replay, renumbering, compression) compiled for the host by tests/emul/make_emul.py and driven
+through the C ABI with the product's own schedule — the same assertions as tests/test_gpu_parity.py,
+without a GPU.  This checks the logic of every kernel and of the host code; what only hardware can show
+(memory model, scheduling, performance) stays with the `-m gpu` tests."""
+import numpy as np
+import pytest
+
+from conftest import CASE_PARAMS, GOLDEN_CASES, case_args
+from emul.cabi_driver import emulated_chambolle_pock_ppd, make_emulated_solver
+from pysparselp_b200 import _cabi
+
+FLAG_SETS = {
+    "plain": 0,
+    "renumbered": _cabi.FLAG_REORDER,
+    "compressed": _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS,
+    "all": _cabi.FLAG_REORDER | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS,
+}
+
+
+def rel_inf(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def curves_close(got, want):
+    assert got.shape == want.shape and np.array_equal(got[:, 0], want[:, 0])
+    for col in range(1, want.shape[1]):
+        g, w = got[:, col], want[:, col]
+        assert np.array_equal(np.isnan(g), np.isnan(w))
+        inf = np.isinf(w)
+        assert np.array_equal(g[inf], w[inf])
+        fin = np.isfinite(w)
+        floor = 1e-6 * max(np.max(np.abs(w[fin])) if fin.any() else 0.0, 1e-30)
+        assert np.all(np.abs(g[fin] - w[fin]) <= 1e-6 * np.abs(w[fin]) + (floor if col in (1, 2) else 0.0))
+
+
+@pytest.mark.parametrize("variant", list(FLAG_SETS))
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_emulated_library_vs_golden(name, variant):
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    trace = []
+    x, best, solver = emulated_chambolle_pock_ppd(
+        *args, nb_max_iter=100, nb_iter_plot=10, flags=FLAG_SETS[variant], partition_granule=32,
+        callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)), **kw)
+    try:
+        y = solver.get_y()
+        T, sigma = solver.get_preconditioners()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        s_gold = np.concatenate([g[k] for k in ("diag_sigma_eq", "diag_sigma_ineq") if k in g])
+        assert solver.niter == 100
+        assert np.array_equal(T == 1.0, g["diag_t"] == 1.0)
+        if "alpha" not in kw:
+            assert np.array_equal(T, g["diag_t"]) and np.array_equal(sigma, s_gold)
+            assert np.array_equal(x, g["x_100"]) and np.array_equal(y, y_gold)
+        else:
+            assert rel_inf(x, g["x_100"]) <= 1e-9 and rel_inf(y, y_gold) <= 1e-9
+        curves_close(np.array(trace), g["trace_10"])
+        assert (best is None) == (g["best_100"].size == 0)
+    finally:
+        solver.close()
+
+
+@pytest.mark.parametrize("name", ["potts50", "sc105"])
+def test_emulated_force_integer_bookkeeping(name):
+    args, g = case_args(name)
+    trace = []
+    x, best, solver = emulated_chambolle_pock_ppd(
+        *args, nb_max_iter=300, nb_iter_plot=20, force_integer=True,
+        callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)))
+    solver.close()
+    assert np.array_equal(x, g["x_300_fi"])
+    curves_close(np.array(trace), g["trace_20_fi"])
+    assert best is not None and np.array_equal(best, g["best_300_fi"])
+
+
+def test_emulated_partition_matches_python_restatement():
+    import scipy.sparse as sp
+
+    from oracle import partition_oracle as po
+    from pysparselp_b200 import generators
+
+    for lp, m_eq in ((generators.potts_lp(20), 0), (generators.random_sparse_lp(300, 400, n_eq=70, seed=4)[0], 70)):
+        solver = make_emulated_solver(*generators.lp_args(lp), flags=_cabi.FLAG_REORDER, partition_granule=32)
+        cols, ghost_c = solver.layout(columns=True)
+        rows, ghost_r = solver.layout(columns=False)
+        info = solver.info()
+        solver.close()
+        blocks = [a for a in (lp.a_eq, lp.a_ineq) if a is not None]
+        a = sp.vstack(blocks).tocsr() if len(blocks) > 1 else blocks[0]
+        part = po.partition(a.indptr, a.indices, a.shape[1], m_eq, 1, granule=32)
+        assert ghost_c.size == 0 and ghost_r.size == 0
+        assert np.array_equal(cols, part["col_order"]) and np.array_equal(rows, part["row_order"])
+        assert info["nnz"] == a.nnz and info["a_padded_entries"] >= a.nnz
+
+
+def test_emulated_automatic_renumbering_on_padding():
+    """A pattern whose row lengths vary wildly is renumbered automatically (padding > 15 %), results unchanged."""
+    import scipy.sparse as sp
+
+    from oracle.cpppd_oracle import chambolle_pock_ppd_oracle
+
+    rng = np.random.default_rng(11)
+    n, m = 200, 260
+    rows = []
+    for i in range(m):
+        k = 1 if i % 7 else 25
+        cols = rng.choice(n, size=k, replace=False)
+        rows.append((cols, np.round(rng.standard_normal(k), 1) + 0.05))
+    indptr = np.concatenate(([0], np.cumsum([r[0].size for r in rows])))
+    a = sp.csr_matrix((np.concatenate([r[1] for r in rows]), np.concatenate([r[0] for r in rows]), indptr), shape=(m, n))
+    c = rng.standard_normal(n)
+    lb, ub = -np.ones(n), np.ones(n)
+    args = (c, sp.csr_matrix((0, n)), np.empty(0), a, None, rng.random(m), lb, ub)
+    xo, _ = chambolle_pock_ppd_oracle(*args, nb_max_iter=40, nb_iter_plot=10**6)
+    # one locality bucket (granule >= n): inside it rows / columns are grouped by length (sigma sorting)
+    x, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=40, nb_iter_plot=10**6, partition_granule=4096)
+    cols, _ = solver.layout(columns=True)
+    info = solver.info()
+    solver.close()
+    assert np.array_equal(x, xo)
+    assert not np.array_equal(cols, np.arange(n)), "heavy padding should have triggered the renumbering"
+    padded_sorted = info["a_padded_entries"] + info["at_padded_entries"]
+    x2, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=40, nb_iter_plot=10**6, flags=_cabi.FLAG_NO_REORDER)
+    cols2, _ = solver.layout(columns=True)
+    padded_identity = sum(solver.info()[k] for k in ("a_padded_entries", "at_padded_entries"))
+    solver.close()
+    assert np.array_equal(x2, xo) and np.array_equal(cols2, np.arange(n))
+    assert padded_identity > 1.15 * 2 * a.nnz and padded_sorted < 0.7 * padded_identity
+
+
+def test_emulated_abi_errors():
+    import ctypes as C
+
+    import scipy.sparse as sp
+
+    from emul.cabi_driver import emulated_library
+
+    lib = emulated_library()
+    a = sp.csr_matrix(np.array([[1.0, -1.0], [0.5, 2.0]]))
+    with pytest.raises(_cabi.CpppdError, match="column index"):
+        bad = a.copy()
+        bad.indices = np.array([0, 5, 0, 1], dtype=np.int32)
+        make_emulated_solver(np.ones(2), None, None, bad, None, np.zeros(2), np.zeros(2), np.ones(2))
+    s = make_emulated_solver(np.ones(2), None, None, a, None, np.zeros(2), np.zeros(2), np.ones(2))
+    with pytest.raises(_cabi.CpppdError, match="primal step"):
+        s.dual_step()
+    with pytest.raises(_cabi.CpppdError):
+        s.stats_step()
+    s.primal_step(keep_d=True)
+    with pytest.raises(_cabi.CpppdError, match="dual_step"):
+        s.iterate(3)
+    s.close()
+    assert lib.cpppd_destroy(None) == 0

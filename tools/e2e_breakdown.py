@@ -1,7 +1,7 @@
 """Where does an end-to-end call spend its time? (scratch tool)"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from bench import build_workload
 from pysparselp_b200 import generators
 from pysparselp_b200.ChambollePockPPD import make_solver, chambolle_pock_ppd

@@ -6,7 +6,7 @@ Writes profiles/<tag>_kernels.csv (one line per captured launch with the metrics
 is argued from), profiles/<tag>_launches.txt (per-kernel share of the launch list) and refreshes
 profiles/ncu_summary.json (per-kernel DRAM bytes per launch, read by bench.py for roofline.traffic).
 """
-import argparse, csv, io, json, os, subprocess, sys, collections
+import argparse, csv, io, json, os, subprocess, collections
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRICS = [
