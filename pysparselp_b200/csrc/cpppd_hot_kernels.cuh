@@ -16,9 +16,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-#else  // CPU emulation of the kernels (tests/emul): one thread at a time, plain accesses
-inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return *p; }
-inline void st_release_sys(unsigned long long *p, unsigned long long v) { *p = v; }
+#else  // host build of the sources for the CPU emulator (tests/emul): ranks are OS threads
+inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #endif
 
 // Device-resident description of the halo a kernel produces (kind_out) and consumes (kind_in).

@@ -33,7 +33,8 @@ def emulated_library():
 
 
 class EmulatedSolver(SolverHandle):
-    def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, flags=0, partition_granule=0):
+    def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, flags=0, partition_granule=0,
+                 rank=0, world=1, comm_id=None):
         self.lib = emulated_library()
         p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule)
         self.n, self.m, self.m_eq = int(p.n), int(p.m_eq + p.m_ineq), int(p.m_eq)
@@ -41,6 +42,8 @@ class EmulatedSolver(SolverHandle):
         p.stream = None
         p.alloc = C.cast(None, _cabi.ALLOC_FN)
         p.free = C.cast(None, _cabi.FREE_FN)
+        p.rank, p.world_size = rank, world
+        p.comm_id = None if comm_id is None else comm_id.ctypes.data
         handle = C.c_void_p()
         _cabi.check(self.lib, None, self.lib.cpppd_create(C.byref(p), C.byref(handle)))
         del keep
@@ -48,13 +51,13 @@ class EmulatedSolver(SolverHandle):
 
 
 def make_emulated_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, flags=0,
-                         partition_granule=0):
+                         partition_granule=0, rank=0, world=1, comm_id=None):
     if a_eq is not None and a_eq.shape[0] == 0:
         a_eq, beq = None, None
     a_ineq, b_ineq = one_sided_rows(a_ineq, b_lower, b_upper)
     a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, np.size(c))
     return EmulatedSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, flags=flags,
-                          partition_granule=partition_granule)
+                          partition_granule=partition_granule, rank=rank, world=world, comm_id=comm_id)
 
 
 def emulated_chambolle_pock_ppd(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1,
@@ -66,3 +69,40 @@ def emulated_chambolle_pock_ppd(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, 
                                   flags=flags, partition_granule=partition_granule)
     x, best = run_schedule(solver, nb_max_iter, callback_func, max_time, force_integer, nb_iter_plot, False, start)
     return x, best, solver
+
+
+def new_comm_id():
+    """128-byte id of a fresh emulated communicator (the in-process NCCL of tests/emul/emul_nccl.cpp)."""
+    import os
+
+    os.environ["CPPPD_NCCL_LIB"] = make_emul.LIB  # libcpppd resolves "NCCL" inside the emulated library itself
+    ident = np.zeros(128, dtype=np.uint8)
+    _cabi.check(emulated_library(), None, emulated_library().cpppd_comm_unique_id(ident.ctypes.data))
+    return ident
+
+
+def run_ranks(world, body, timeout_s=600):
+    """Run ``body(rank, world, comm_id)`` on one Python thread per emulated rank (ctypes releases the GIL inside
+    the library, so the ranks really run concurrently); returns the list of results, re-raises the first error."""
+    import threading
+
+    comm_id = new_comm_id()
+    results, errors = [None] * world, []
+
+    def runner(r):
+        try:
+            results[r] = body(r, world, comm_id)
+        except BaseException as e:  # noqa: BLE001 - reported to the test
+            errors.append((r, e))
+
+    threads = [threading.Thread(target=runner, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    deadline = time.time() + timeout_s
+    for t in threads:
+        t.join(max(0.0, deadline - time.time()))
+    if any(t.is_alive() for t in threads):
+        raise TimeoutError("emulated ranks did not finish (dead-lock?); errors so far: %r" % (errors,))
+    if errors:
+        raise errors[0][1]
+    return results

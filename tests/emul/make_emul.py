@@ -94,7 +94,8 @@ def sources():
 
 def build(force=False, defines=()):
     srcs = [os.path.join(CSRC, f) for f in sources()] + [os.path.join(ROOT, "include", "cpppd.h")] + [
-        os.path.join(HERE, "shim", f) for f in ("cuda_runtime.h", "nccl.h", os.path.join("cub", "cub.cuh"))] + [__file__]
+        os.path.join(HERE, "shim", f) for f in ("cuda_runtime.h", "nccl.h", os.path.join("cub", "cub.cuh"))] + [
+        os.path.join(HERE, "emul_nccl.cpp"), __file__]
     if not force and os.path.isfile(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
@@ -108,7 +109,7 @@ def build(force=False, defines=()):
             fh.write(text)
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-w",
            "-I", os.path.join(HERE, "shim")] + list(defines) + os.environ.get("CPPPD_NVCC_DEFINES", "").split() + [
-        "-o", LIB, os.path.join(OUT_DIR, "cpppd.cpp"), "-ldl"]
+        "-o", LIB, os.path.join(OUT_DIR, "cpppd.cpp"), os.path.join(HERE, "emul_nccl.cpp"), "-ldl", "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("emulated build failed:\n" + res.stderr[-6000:])

@@ -6,10 +6,12 @@
 // Execution model: blocks run one after the other; the threads of a block are fibers (ucontext) that are
 // resumed round-robin, so __syncthreads() and the warp shuffles are real rendezvous between the 256
 // "threads" of a CTA.  Streams are synchronous, events are wall-clock, a captured graph is the recorded
-// list of launches.  One device, no peer access, no NCCL: world_size 1 only.
+// list of launches.  All emulator state is thread_local: one OS thread plays one rank ("GPU"), peer memory
+// is the shared address space, and tests/emul/emul_nccl.cpp supplies an in-process NCCL.
 //
 // Nothing in the product includes or loads this; the product has no CPU path.
 #pragma once
+#include <sched.h>
 #include <ucontext.h>
 
 #include <chrono>
@@ -25,7 +27,7 @@
 // ---------------------------------------------------------------------------------- device language
 struct EmulDim3 { unsigned x = 1, y = 1, z = 1; };
 namespace emul {
-inline EmulDim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+inline thread_local EmulDim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 }
 #define threadIdx emul::g_threadIdx
 #define blockIdx emul::g_blockIdx
@@ -38,7 +40,7 @@ inline EmulDim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 
 namespace emul {
 
@@ -67,7 +69,7 @@ struct BlockState {
   char *stacks = nullptr;
   bool progress = false;
 };
-inline BlockState g_block;
+inline thread_local BlockState g_block;
 
 inline void yield() { swapcontext(&g_block.fibers[g_block.current].ctx, &g_block.main_ctx); }
 
@@ -136,7 +138,7 @@ inline void run_block(int nthreads, const std::function<void()> &body) {
 
 // ---- graphs: a capture records the launches instead of running them
 struct Graph { std::vector<std::function<void()>> nodes; };
-inline Graph *g_capturing = nullptr;
+inline thread_local Graph *g_capturing = nullptr;
 
 inline void run_grid(unsigned grid, unsigned block, const std::function<void()> &body) {
   g_gridDim.x = grid;
@@ -179,9 +181,14 @@ inline int __any_sync(unsigned, int pred) {
   for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-inline void __threadfence() {}
-inline void __threadfence_system() {}
-inline void __nanosleep(unsigned) { emul::yield(); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+// a spinning thread waits for another *rank* (another OS thread): not a dead-lock of this block
+inline void __nanosleep(unsigned) {
+  emul::g_block.progress = true;
+  sched_yield();
+  emul::yield();
+}
 
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
@@ -245,6 +252,7 @@ inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, int) 
 inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
 inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t g) { delete g; return cudaSuccess; }
 inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) { for (auto &n : g->nodes) n(); return cudaSuccess; }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorEmul; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorEmul; }
+// all emulated ranks are threads of one process: an IPC handle is the pointer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }

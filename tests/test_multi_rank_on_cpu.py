@@ -1,0 +1,65 @@
+"""CPU: the multi-GPU code of the real library (partition, ghost lists, halo exchange over "peer memory",
+NCCL transport, distributed stats, vector assembly) with world_size 2 and 3 — every rank is an OS thread
+running the CPU-emulated library (tests/emul), peer memory is the shared address space, NCCL is
+tests/emul/emul_nccl.cpp.  Same assertions as tests/dist_worker.py makes on real GPUs."""
+import numpy as np
+import pytest
+
+from conftest import CASE_PARAMS, case_args
+from emul.cabi_driver import make_emulated_solver, run_ranks
+from oracle import partition_oracle as po
+from pysparselp_b200 import _cabi
+from pysparselp_b200.ChambollePockPPD import one_sided_rows, run_schedule, stack_operator
+
+TRANSPORTS = {"fused_in_kernels": 0, "push_wait_kernels": _cabi.FLAG_NO_FUSED_HALO, "nccl": _cabi.FLAG_NO_P2P}
+
+
+def solve_on_ranks(args, world, flags, nb_max_iter, nb_iter_plot, force_integer=False, **kw):
+    def body(rank, world, comm_id):
+        trace = []
+        solver = make_emulated_solver(*args, flags=flags, partition_granule=32, rank=rank, world=world,
+                                      comm_id=comm_id, **kw)
+        x, best = run_schedule(solver, nb_max_iter, lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)),
+                               None, force_integer, nb_iter_plot)
+        out = dict(x=x, best=best, trace=np.array(trace), y=solver.get_y(), T=solver.get_preconditioners()[0],
+                   cols=solver.layout(True), rows=solver.layout(False), info=solver.info())
+        solver.close()
+        return out
+
+    return run_ranks(world, body)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("transport", list(TRANSPORTS))
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["potts50", "sc105", "random_small"])
+def test_multi_rank_iterates_bit_identical(name, world, transport):
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    res = solve_on_ranks(args, world, TRANSPORTS[transport], 100, 10, **kw)
+    y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+    c, a_eq, beq, a_in, b_lo, b_up, lb, ub = args
+    a_in1, b_in1 = one_sided_rows(a_in, b_lo, b_up)
+    A, b, m_eq = stack_operator(a_eq if a_eq is not None and a_eq.shape[0] else None, beq, a_in1, b_in1, c.size)
+    part = po.partition(A.indptr, A.indices, A.shape[1], m_eq, world, granule=32)
+    for rank, r in enumerate(res):
+        assert np.array_equal(r["x"], g["x_100"]) and np.array_equal(r["y"], y_gold) and np.array_equal(r["T"], g["diag_t"])
+        assert np.allclose(r["trace"], g["trace_10"], rtol=1e-6, atol=1e-9, equal_nan=True)
+        assert r["info"]["world_size"] == world and r["info"]["rank"] == rank
+        own_c, ghost_c = r["cols"]
+        own_r, ghost_r = r["rows"]
+        assert np.array_equal(own_c, part["col_order"][part["col_start"][rank]: part["col_start"][rank + 1]])
+        assert np.array_equal(own_r, part["row_order"][part["row_start"][rank]: part["row_start"][rank + 1]])
+        gc, gr = po.ghosts(A.indptr, A.indices, part, rank)
+        assert np.array_equal(ghost_c, gc) and np.array_equal(ghost_r, gr)
+
+
+@pytest.mark.timeout(900)
+def test_multi_rank_force_integer_and_compression():
+    args, g = case_args("potts50")
+    flags = _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS
+    res = solve_on_ranks(args, 2, flags, 300, 20, force_integer=True)
+    for r in res:
+        assert np.array_equal(r["x"], g["x_300_fi"])
+        assert r["best"] is not None and np.array_equal(r["best"], g["best_300_fi"])
+        assert r["info"]["value_bytes"] == 0
