@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CPPPD_ABI_VERSION 3
+#define CPPPD_ABI_VERSION 4
 
 typedef struct cpppd_solver *cpppd_handle;
 
@@ -128,6 +128,11 @@ typedef struct {
   double max_violated_equality_rounded;/* max |A_eq xr - b_eq|      (:280-282)                */
   double best_integer_energy;          /* running minimum over feasible xr (:289-291)         */
   double frac_zero_xbar;               /* mean(xbar == 0)           (:308)                    */
+  /* what SparseLP.solve()'s per-callback curves need, so that x can stay on the device
+   * (reference SparseLP.py:186-204, :1074-1089) */
+  double max_bound_violation;          /* max(max(lb - x), max(x - ub))                       */
+  double distance_to_ground_truth;     /* mean |gt - x[idx]|        (cpppd_set_ground_truth)  */
+  double distance_to_ground_truth_rounded; /* mean |gt - round(x[idx])|                       */
   int32_t feasible;                    /* exact test of :284                                   */
   int32_t improved;                    /* xr became the best integer solution at this block   */
   int32_t have_best_integer;           /* a best integer solution exists                       */
@@ -210,6 +215,9 @@ int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_
 int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst);
 int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src); /* X, XBAR, Y only */
 int cpppd_get_info(cpppd_handle h, cpppd_info *out);
+/* Ground truth for the distance curves of the stats block: values[k] is compared with x[indices[k]]
+ * (original column ids).  count = 0 removes it.  With world_size > 1 every rank passes the full list. */
+int cpppd_set_ground_truth(cpppd_handle h, const int32_t *indices, const double *values, int64_t count);
 /* Partition of this rank: number of owned and ghost columns (columns != 0) or rows (columns == 0)
  * and, when ids is not NULL, their original indices in local order (owned first, then ghosts in
  * exchange order).  A pure function of (indptr, indices, m_eq, world_size, granule):

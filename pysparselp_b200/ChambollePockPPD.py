@@ -210,6 +210,14 @@ class SolverHandle:
     def get_best_integer(self):
         return self._get(_cabi.VEC_BEST_INTEGER, self.n)
 
+    def set_ground_truth(self, indices, values):
+        """Ground truth for the distance curves of the stats block: values[k] vs x[indices[k]]."""
+        idx = np.ascontiguousarray(np.ravel(indices), dtype=np.int32)
+        val = np.ascontiguousarray(np.ravel(values), dtype=np.float64)
+        if idx.size != val.size:
+            raise ValueError("ground truth indices and values differ in size")
+        self._call(self.lib.cpppd_set_ground_truth, idx.ctypes.data, val.ctypes.data, idx.size)
+
     def set_x(self, v):
         self._set(_cabi.VEC_X, v, self.n)
 
@@ -400,11 +408,12 @@ def _resolve_group(distributed):
 
 
 def run_schedule(solver, nb_max_iter, callback_func=None, max_time=None, force_integer=False, nb_iter_plot=10,
-                 verbose=False, start=None):
+                 verbose=False, start=None, stats_func=None):
     """The reference's ``while`` loop (``:195-343``) driven over a live solver handle.
 
     Iterations are issued asynchronously in blocks of ``nb_iter_plot``; the host only waits at the
     stats iterations (``niter % nb_iter_plot == 0``, including 0).  Returns ``(x, best_integer)``.
+    ``stats_func(niter, stats, elapsed)`` receives the whole stats block without x leaving the device.
     """
     start = time.perf_counter() if start is None else start
     nb_iter_plot = int(nb_iter_plot)
@@ -426,6 +435,8 @@ def run_schedule(solver, nb_max_iter, callback_func=None, max_time=None, force_i
                   "max violated equality:%r x3 has %r %% of zeros" % (
                       niter, st["energy1"], st["energy2"], elapsed, st["max_violated_inequality"],
                       st["max_violated_equality"], 100 * st["frac_zero_xbar"]))
+        if stats_func is not None:
+            stats_func(niter, st, elapsed)
         if callback_func is not None:
             callback_func(niter, solver.get_x(), st["energy1"], st["energy2"], elapsed,
                           st["max_violated_equality"], st["max_violated_inequality"])

@@ -25,7 +25,7 @@ import time
 import numpy as np
 import scipy.sparse as sp
 
-from .ChambollePockPPD import chambolle_pock_ppd
+from .ChambollePockPPD import chambolle_pock_ppd, make_solver, run_schedule
 
 solving_methods = ("chambolle_pock_ppd",)
 
@@ -399,7 +399,9 @@ class SparseLP:
         (:1018-1028, :1064-1093).  As in the reference, the ``callback_func`` argument
         is shadowed by the internal curve recorder and never called; ``plot_solution``
         is the user hook.  ``solver_options`` are forwarded to ``chambolle_pock_ppd`` as
-        extra keyword-only arguments (``device=``, ``deterministic=`` ...).
+        extra keyword-only arguments (``device=``, ``flags=`` ...).  When no variable is fixed and
+        ``plot_solution`` is None the curves are evaluated on the device (``device_curves=False`` forces
+        the reference's host-side evaluation, which downloads x at every callback).
         """
         if method not in solving_methods:
             if method in _reference_only_methods:
@@ -450,25 +452,63 @@ class SparseLP:
         def reduced_callback(niter, solution, energy1, energy2, duration, mv_eq, mv_ineq):
             record(niter, to_full(solution), energy1, energy2, duration, mv_eq, mv_ineq)
 
-        x, best_integer_solution = chambolle_pock_ppd(
-            reduced.costsvector,
-            reduced.a_equalities,
-            reduced.b_equalities,
-            reduced.a_inequalities,
-            reduced.b_lower,
-            reduced.b_upper,
-            reduced.lower_bounds,
-            reduced.upper_bounds,
-            x0=None,
-            alpha=1,
-            theta=1,
-            nb_max_iter=nb_iter,
-            callback_func=reduced_callback,
-            max_time=max_time,
-            save_problem=False,
-            nb_iter_plot=nb_iter_plot,
-            **solver_options,
-        )
+        solver_args = (reduced.costsvector, reduced.a_equalities, reduced.b_equalities, reduced.a_inequalities,
+                       reduced.b_lower, reduced.b_upper, reduced.lower_bounds, reduced.upper_bounds)
+        want_device_curves = solver_options.pop("device_curves", True)
+        device_curves = want_device_curves and plot_solution is None and reduced.nb_variables == self.nb_variables
+        if device_curves:
+            # No variable was eliminated (x_full == x) and nobody asked to see x: every per-callback curve
+            # of the reference (:1074-1091) is evaluated on the device inside the stats block and x never
+            # leaves the GPU before the end.  Values equal the host path up to the summation order of the
+            # two distance means.
+            solve_kw = {k: solver_options[k] for k in ("device", "flags", "distributed", "partition_granule")
+                        if k in solver_options}
+            solver = make_solver(*solver_args, x0=None, alpha=1, theta=1, **solve_kw)
+            best_integer_solution = None
+            if solver is None:
+                device_curves = False
+            else:
+                try:
+                    if ground_truth is not None:
+                        solver.set_ground_truth(ground_truth_indices, ground_truth)
+
+                    def record_stats(niter, st, duration):
+                        if ground_truth is not None:
+                            self.distance_to_ground_truth.append(st["distance_to_ground_truth"])
+                            self.distanceToGroundTruthAfterRounding.append(st["distance_to_ground_truth_rounded"])
+                        self.itrn_curve.append(niter)
+                        self.opttime_curve.append(duration)
+                        self.dopttime_curve.append(duration)
+                        self.dobj_curve.append(st["energy2"])
+                        self.pobj_curve.append(st["energy1"])
+                        # max_constraint_violation (:186-204) from the device maxima, folded in its order
+                        worst = max(0, st["max_bound_violation"])
+                        if self.nb_equality_constraints() > 0:
+                            worst = max(worst, st["max_violated_equality_rounded"])
+                        if self.nb_inequality_constraints() > 0:
+                            worst = max(worst, st["max_violated_inequality"])
+                        self.max_violated_constraint.append(worst)
+                        self.max_violated_equality.append(st["max_violated_equality"])
+                        self.max_violated_inequality.append(st["max_violated_inequality"])
+
+                    x, best_integer_solution = run_schedule(solver, nb_iter, None, max_time, False, nb_iter_plot,
+                                                            bool(solver_options.get("verbose", False)), start,
+                                                            stats_func=record_stats)
+                finally:
+                    solver.close()
+        if not device_curves:
+            x, best_integer_solution = chambolle_pock_ppd(
+                *solver_args,
+                x0=None,
+                alpha=1,
+                theta=1,
+                nb_max_iter=nb_iter,
+                callback_func=reduced_callback,
+                max_time=max_time,
+                save_problem=False,
+                nb_iter_plot=nb_iter_plot,
+                **solver_options,
+            )
         x = to_full(x)
         self.best_integer_solution = None if best_integer_solution is None else to_full(best_integer_solution)
         elapsed = time.perf_counter() - start

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
@@ -48,6 +48,8 @@ class Stats(C.Structure):
         ("max_violated_equality", C.c_double), ("max_violated_inequality", C.c_double),
         ("energy_rounded", C.c_double), ("max_violated_equality_rounded", C.c_double),
         ("best_integer_energy", C.c_double), ("frac_zero_xbar", C.c_double),
+        ("max_bound_violation", C.c_double), ("distance_to_ground_truth", C.c_double),
+        ("distance_to_ground_truth_rounded", C.c_double),
         ("feasible", C.c_int32), ("improved", C.c_int32), ("have_best_integer", C.c_int32),
         ("reserved", C.c_int32),
     ]
@@ -93,6 +95,7 @@ SYMBOLS = {
     "cpppd_get_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_set_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
+    "cpppd_set_ground_truth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "cpppd_get_layout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "cpppd_iteration_count": (C.c_int64, [C.c_void_p]),
 }

@@ -275,13 +275,16 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
     if (int rc = exchange(h, xr, h->hx)) return rc;
   k_stats_rows<<<h->stat_blocks_r, kBlock, 0, h->stream>>>(view(h->A), h->x, h->dbuf, h->xbar, xr, h->vb, h->y, h->m,
                                                           h->m_eq, force_integer, h->rowpart);
-  k_stats_local<<<1, kBlock, 0, h->stream>>>(h->colpart, h->stat_blocks_c, h->rowpart, h->stat_blocks_r, h->stat_local);
+  if (h->gt_local)
+    k_stats_gt<<<h->stat_blocks_g, kBlock, 0, h->stream>>>(h->gt_idx, h->gt_val, h->gt_local, h->x, h->gtpart);
+  k_stats_local<<<1, kBlock, 0, h->stream>>>(h->colpart, h->stat_blocks_c, h->rowpart, h->stat_blocks_r, h->gtpart,
+                                             h->gt_local ? h->stat_blocks_g : 0, h->stat_local);
   const double *all = h->stat_local;
   if (h->world > 1) {
     NK(g_nccl.AllGather(h->stat_local, h->stat_all, kStatQ, ncclFloat64, h->comm, h->stream));
     all = h->stat_all;
   }
-  k_stats_final<<<1, 32, 0, h->stream>>>(all, h->world, h->n_glob, has_eq, has_ineq, h->niter, h->stats_dev);
+  k_stats_final<<<1, 32, 0, h->stream>>>(all, h->world, h->n_glob, has_eq, has_ineq, h->niter, h->gt_total, h->stats_dev);
   k_snapshot_best<<<std::max(1, std::min(grid_for(h->n), h->sm_count * 8)), kBlock, 0, h->stream>>>(h->stats_dev, xr,
                                                                                                   h->best, h->n);
   CK(cudaMemcpyAsync(h->stats_host, h->stats_dev, sizeof(cpppd_stats), cudaMemcpyDeviceToHost, h->stream));
@@ -385,6 +388,45 @@ int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src) {
   if (int rc = upload_local(h, tmp, host_src, is_col ? h->n_glob : h->m_glob, is_col ? h->col_old : h->row_old, local, p))
     return rc;
   CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int cpppd_set_ground_truth(cpppd_handle h, const int32_t *indices, const double *values, int64_t count) {
+  CHECK_HANDLE(h);
+  if (count < 0 || (count && (!indices || !values))) return fail(h, CPPPD_ERR_INVALID, "bad ground truth");
+  h->gt_local = h->gt_total = 0;
+  if (count == 0) return 0;
+  // keep the entries whose column this rank owns, in local numbering
+  std::vector<int32_t> local_of(h->n_glob, -1);
+  if (h->identity_layout) {
+    for (int64_t j = 0; j < h->n_glob; ++j) local_of[j] = (int32_t)j;
+  } else {
+    std::vector<int32_t> col_old(h->n);
+    if (h->n) CK(cudaMemcpyAsync(col_old.data(), h->col_old, sizeof(int32_t) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int64_t lj = 0; lj < h->n; ++lj) local_of[col_old[lj]] = (int32_t)lj;
+  }
+  std::vector<int32_t> idx;
+  std::vector<double> val;
+  for (int64_t k = 0; k < count; ++k) {
+    if (indices[k] < 0 || indices[k] >= h->n_glob) return fail(h, CPPPD_ERR_INVALID, "ground truth index out of range");
+    const int32_t lj = local_of[indices[k]];
+    if (lj >= 0) {
+      idx.push_back(lj);
+      val.push_back(values[k]);
+    }
+  }
+  h->gt_total = count;
+  h->gt_local = (int64_t)idx.size();
+  if (h->gt_local) {
+    h->stat_blocks_g = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(h->gt_local), (int64_t)h->sm_count * 8));
+    if (int rc = alloc_array(h, &h->gt_idx, h->gt_local)) return rc;
+    if (int rc = alloc_array(h, &h->gt_val, h->gt_local)) return rc;
+    if (int rc = alloc_array(h, &h->gtpart, (int64_t)h->stat_blocks_g * kGtQ)) return rc;
+    CK(cudaMemcpyAsync(h->gt_idx, idx.data(), sizeof(int32_t) * idx.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->gt_val, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
   return 0;
 }
 

@@ -22,9 +22,12 @@ constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
 #endif
 constexpr int kGatherChunk = CPPPD_GATHER_CHUNK;  // entries of a row whose gathers are in flight together
 constexpr int kMinBlocks = CPPPD_MIN_BLOCKS;      // CTAs per SM the hot kernels are compiled for (register cap)
-constexpr int kColQ = 4;         // column-pass partial sums per CTA
-constexpr int kRowQ = 7;         // row-pass partial sums per CTA
-constexpr int kStatQ = kColQ + kRowQ;
+constexpr int kColQ = 5;         // column-pass partials per CTA: 4 sums + max bound violation
+constexpr int kRowQ = 7;         // row-pass partials per CTA: 4 sums + 3 maxima
+constexpr int kGtQ = 2;          // ground-truth pass: sum |gt - x|, sum |gt - round(x)|
+constexpr int kStatQ = kColQ + kRowQ + kGtQ;
+// entries of the per-rank stats vector that are folded with a (NaN-propagating) max instead of a sum
+__host__ __device__ constexpr bool stat_is_max(int q) { return q == 4 || (q >= kColQ + 4 && q < kColQ + kRowQ); }
 constexpr int32_t kEqBit = 0x40000000;   // A^T entries: set when the source row is an equality
 constexpr int32_t kIdxMask = 0x3fffffff;
 // padding entry of a slice: negative, and its masked index is 0 so that a gather the compiler

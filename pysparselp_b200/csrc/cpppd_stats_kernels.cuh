@@ -7,16 +7,17 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // stats block (:248-291)
 // ------------------------------------------------------------------------------------------
-// Column pass: c.x, c.x4, c.xr, #(xbar == 0); turns the d buffer into x4 in place and
-// (force_integer) stores xr into xr_out.
+// Column pass: c.x, c.x4, c.xr, #(xbar == 0), max(lb - x, x - ub); turns the d buffer into x4 in place
+// and (force_integer) stores xr into xr_out.
 __global__ void __launch_bounds__(kBlock)
 k_stats_cols(Vec c, const double *__restrict__ x, const double *__restrict__ xbar, Vec lb, Vec ub,
              double *__restrict__ d_x4, double *__restrict__ xr_out, int64_t n, int force_integer,
              double *__restrict__ part) {
-  double v[kColQ] = {0.0, 0.0, 0.0, 0.0};
+  double v[kColQ] = {0.0, 0.0, 0.0, 0.0, -INFINITY};
   for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < n; j += (int64_t)gridDim.x * kBlock) {
     const double cj = c.at(j), xj = x[j];
-    const double x4 = d_x4[j] < 0.0 ? ub.at(j) : lb.at(j);  // x4 = lb; x4[d < 0] = ub[d < 0]  (:260-261)
+    const double lj = lb.at(j), uj = ub.at(j);
+    const double x4 = d_x4[j] < 0.0 ? uj : lj;  // x4 = lb; x4[d < 0] = ub[d < 0]  (:260-261)
     d_x4[j] = x4;
     double xr = xj;
     if (force_integer) {
@@ -27,8 +28,10 @@ k_stats_cols(Vec c, const double *__restrict__ x, const double *__restrict__ xba
     v[1] = __dadd_rn(v[1], __dmul_rn(cj, x4));
     v[2] = __dadd_rn(v[2], __dmul_rn(cj, xr));
     v[3] = __dadd_rn(v[3], xbar[j] == 0.0 ? 1.0 : 0.0);
+    // bound part of SparseLP.max_constraint_violation (reference SparseLP.py:189-190)
+    v[4] = nan_max(v[4], nan_max(__dsub_rn(lj, xj), __dsub_rn(xj, uj)));
   }
-  block_reduce_write<kColQ>(v, 0u, part + (int64_t)blockIdx.x * kColQ);
+  block_reduce_write<kColQ>(v, 0x10u, part + (int64_t)blockIdx.x * kColQ);
 }
 
 // Row pass: A x, A x4, A xbar, A xr per row -> energy terms and violation maxima.
@@ -77,16 +80,36 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
   block_reduce_write<kRowQ>(v, 0x70u, part + (int64_t)blockIdx.x * kRowQ);
 }
 
+// Ground-truth pass (solve()'s distance curves, reference SparseLP.py:1074-1082): for the entries of the
+// ground truth this rank owns, sum |gt - x[idx]| and sum |gt - round(x[idx])|.
+__global__ void __launch_bounds__(kBlock)
+k_stats_gt(const int32_t *__restrict__ gt_idx, const double *__restrict__ gt_val, int64_t count,
+           const double *__restrict__ x, double *__restrict__ part) {
+  double v[kGtQ] = {0.0, 0.0};
+  for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < count; k += (int64_t)gridDim.x * kBlock) {
+    const double xv = x[gt_idx[k]], g = gt_val[k];
+    v[0] = __dadd_rn(v[0], fabs(__dsub_rn(g, xv)));
+    v[1] = __dadd_rn(v[1], fabs(__dsub_rn(g, rint(xv))));
+  }
+  block_reduce_write<kGtQ>(v, 0u, part + (int64_t)blockIdx.x * kGtQ);
+}
+
 // One CTA: fold this rank's per-CTA partials in a fixed order into kStatQ numbers.
 __global__ void __launch_bounds__(kBlock)
 k_stats_local(const double *__restrict__ colpart, int nbc, const double *__restrict__ rowpart, int nbr,
-              double *__restrict__ out) {
-  double cv[kColQ] = {0.0, 0.0, 0.0, 0.0};
+              const double *__restrict__ gtpart, int nbg, double *__restrict__ out) {
+  double cv[kColQ] = {0.0, 0.0, 0.0, 0.0, -INFINITY};
+  double gv[kGtQ] = {0.0, 0.0};
+  for (int bi = threadIdx.x; bi < nbg; bi += kBlock)
+#pragma unroll
+    for (int q = 0; q < kGtQ; ++q) gv[q] = __dadd_rn(gv[q], gtpart[(int64_t)bi * kGtQ + q]);
   const double ninf = -INFINITY;
   double rv[kRowQ] = {0.0, 0.0, 0.0, 0.0, ninf, ninf, ninf};
-  for (int bi = threadIdx.x; bi < nbc; bi += kBlock)
+  for (int bi = threadIdx.x; bi < nbc; bi += kBlock) {
 #pragma unroll
-    for (int q = 0; q < kColQ; ++q) cv[q] = __dadd_rn(cv[q], colpart[(int64_t)bi * kColQ + q]);
+    for (int q = 0; q < 4; ++q) cv[q] = __dadd_rn(cv[q], colpart[(int64_t)bi * kColQ + q]);
+    cv[4] = nan_max(cv[4], colpart[(int64_t)bi * kColQ + 4]);
+  }
   for (int bi = threadIdx.x; bi < nbr; bi += kBlock) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) rv[q] = __dadd_rn(rv[q], rowpart[(int64_t)bi * kRowQ + q]);
@@ -94,23 +117,25 @@ k_stats_local(const double *__restrict__ colpart, int nbc, const double *__restr
     for (int q = 4; q < kRowQ; ++q) rv[q] = nan_max(rv[q], rowpart[(int64_t)bi * kRowQ + q]);
   }
   __shared__ double fin[kStatQ];
-  block_reduce_write<kColQ>(cv, 0u, fin);
+  block_reduce_write<kColQ>(cv, 0x10u, fin);
   __syncthreads();
   block_reduce_write<kRowQ>(rv, 0x70u, fin + kColQ);
+  __syncthreads();
+  block_reduce_write<kGtQ>(gv, 0u, fin + kColQ + kRowQ);
   __syncthreads();
   if (threadIdx.x < kStatQ) out[threadIdx.x] = fin[threadIdx.x];
 }
 
 // One thread: fold the ranks' numbers in rank order, then apply :248-291's scalar logic.
 __global__ void k_stats_final(const double *__restrict__ all, int world, int64_t n_glob, int has_eq, int has_ineq,
-                              int64_t niter, StatsDev *out) {
+                              int64_t niter, int64_t gt_count, StatsDev *out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double fin[kStatQ];
   for (int q = 0; q < kStatQ; ++q) fin[q] = all[q];
   for (int r = 1; r < world; ++r)
     for (int q = 0; q < kStatQ; ++q) {
       const double v = all[r * kStatQ + q];
-      fin[q] = (q >= kColQ + 4) ? nan_max(fin[q], v) : __dadd_rn(fin[q], v);
+      fin[q] = stat_is_max(q) ? nan_max(fin[q], v) : __dadd_rn(fin[q], v);
     }
   cpppd_stats &s = out->s;
   double e1 = fin[0], e2 = fin[1];
@@ -130,6 +155,9 @@ __global__ void k_stats_final(const double *__restrict__ all, int world, int64_t
   s.max_violated_inequality = fin[kColQ + 6];  // -inf when there is no inequality row
   s.energy_rounded = fin[2];
   s.frac_zero_xbar = n_glob > 0 ? fin[3] / (double)n_glob : 0.0;
+  s.max_bound_violation = fin[4];
+  s.distance_to_ground_truth = gt_count > 0 ? fin[kColQ + kRowQ + 0] / (double)gt_count : 0.0;
+  s.distance_to_ground_truth_rounded = gt_count > 0 ? fin[kColQ + kRowQ + 1] / (double)gt_count : 0.0;
   const int feasible = (s.max_violated_equality_rounded == 0.0) && (s.max_violated_inequality <= 0.0);
   s.feasible = feasible;
   s.improved = 0;

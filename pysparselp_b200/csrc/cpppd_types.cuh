@@ -157,6 +157,10 @@ struct cpppd_solver {
   int ndict = 0;
   double *colpart = nullptr, *rowpart = nullptr, *xr_scratch = nullptr;
   double *stat_local = nullptr, *stat_all = nullptr;  // kStatQ / world*kStatQ
+  int32_t *gt_idx = nullptr;    // local column ids of the ground-truth entries this rank owns
+  double *gt_val = nullptr, *gtpart = nullptr;
+  int64_t gt_local = 0, gt_total = 0;
+  int stat_blocks_g = 0;
   int stat_blocks_c = 0, stat_blocks_r = 0;
   StatsDev *stats_dev = nullptr;
   cpppd_stats *stats_host = nullptr;

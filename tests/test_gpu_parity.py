@@ -340,3 +340,25 @@ def test_lossless_compression_keeps_iterates_bit_identical(name):
     assert_curves_close(trace, g["trace_20_fi"])
     if g["best_300_fi"].size:
         assert best is not None and np.array_equal(best, g["best_300_fi"])
+
+
+def test_solve_curves_on_device_equal_host_curves():
+    """SparseLP.solve(): curves evaluated inside the stats block (x stays on the GPU) vs the reference-style
+    host evaluation (x downloaded at every callback)."""
+    from pysparselp_b200.examples.example_pott_segmentation import build_linear_program
+
+    out = {}
+    for device_curves in (True, False):
+        lp, gt, gti, _ = build_linear_program(50, 0.5, 500)
+        x, _ = lp.solve(method="chambolle_pock_ppd", nb_iter=3001, nb_iter_plot=500, ground_truth=gt,
+                        ground_truth_indices=gti, device_curves=device_curves)
+        out[device_curves] = (x, {k: np.array(getattr(lp, k), dtype=float) for k in (
+            "distance_to_ground_truth", "distanceToGroundTruthAfterRounding", "pobj_curve", "dobj_curve",
+            "max_violated_constraint", "max_violated_equality", "max_violated_inequality")})
+    (xd, cd), (xh, ch) = out[True], out[False]
+    assert np.array_equal(xd, xh)
+    for k in ch:
+        if k.startswith("distance"):
+            assert np.allclose(cd[k], ch[k], rtol=1e-13, atol=1e-15), k
+        else:
+            assert np.array_equal(cd[k], ch[k], equal_nan=True), k

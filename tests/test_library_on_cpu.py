@@ -152,3 +152,55 @@ def test_emulated_abi_errors():
         s.iterate(3)
     s.close()
     assert lib.cpppd_destroy(None) == 0
+
+
+@pytest.mark.parametrize("case", ["potts50", "sc105"])
+def test_solve_curves_on_device_equal_host_curves(case, monkeypatch):
+    """SparseLP.solve(): the per-callback curves evaluated inside the stats block (x stays on the device)
+    equal the reference-style host evaluation (x downloaded at every callback), and the reference goldens."""
+    import json
+    import os
+
+    import pysparselp_b200.ChambollePockPPD as front
+    from conftest import GOLDEN
+    from emul.patch_plugin import _Adapter
+
+    monkeypatch.setattr(front, "CpPpdSolver", _Adapter)
+    with open(os.path.join(GOLDEN, "reference_curves.json")) as f:
+        ref = json.load(f)
+
+    def build():
+        if case == "potts50":
+            from pysparselp_b200.examples.example_pott_segmentation import build_linear_program
+
+            lp, gt, gti, _ = build_linear_program(50, 0.5, 500)
+            return lp, gt, gti, ref["potts50"]
+        from pysparselp_b200.netlib import get_problem
+        from pysparselp_b200.SparseLP import SparseLP
+
+        d = get_problem("SC105")
+        gt = d["solution"]
+        lp = SparseLP()
+        lp.add_variables_array(len(d["cost_vector"]), lower_bounds=d["lower_bounds"],
+                               upper_bounds=np.minimum(d["upper_bounds"], np.max(gt) * 2), costs=d["cost_vector"])
+        lp.add_equality_constraints_sparse(d["a_eq"], d["b_eq"])
+        lp.add_inequality_constraints_sparse(d["a_ineq"], d["b_lower"], d["b_upper"])
+        lp.convert_to_one_sided_inequality_system()
+        return lp, gt, np.arange(len(gt)), ref["SC105"]
+
+    curves = {}
+    for device_curves in (True, False):
+        lp, gt, gti, golden = build()
+        x, _ = lp.solve(method="chambolle_pock_ppd", nb_iter=1501, nb_iter_plot=500, ground_truth=gt,
+                        ground_truth_indices=gti, device_curves=device_curves)
+        curves[device_curves] = (x, {k: np.array(getattr(lp, k), dtype=float) for k in (
+            "distance_to_ground_truth", "distanceToGroundTruthAfterRounding", "pobj_curve", "dobj_curve",
+            "max_violated_constraint", "max_violated_equality", "max_violated_inequality", "itrn_curve")})
+    (xd, cd), (xh, ch) = curves[True], curves[False]
+    assert np.array_equal(xd, xh)
+    for k in ch:
+        if k.startswith("distance"):
+            assert np.allclose(cd[k], ch[k], rtol=1e-13, atol=1e-15), k
+        else:
+            assert np.array_equal(cd[k], ch[k], equal_nan=True), k
+    np.testing.assert_almost_equal(cd["distance_to_ground_truth"], golden[: len(cd["distance_to_ground_truth"])])

@@ -63,3 +63,34 @@ def test_multi_rank_force_integer_and_compression():
         assert np.array_equal(r["x"], g["x_300_fi"])
         assert r["best"] is not None and np.array_equal(r["best"], g["best_300_fi"])
         assert r["info"]["value_bytes"] == 0
+
+
+@pytest.mark.timeout(900)
+def test_multi_rank_device_curves():
+    """cpppd_set_ground_truth with world_size 2: every rank sums the entries it owns, the stats all-gather
+    adds them up — distances and the bound violation equal the numpy evaluation on the assembled x."""
+    args, g = case_args("potts50")
+    gt = g["ground_truth"].astype(float).ravel()
+    idx = np.arange(gt.size)
+    lb, ub = args[6], args[7]
+
+    def body(rank, world, comm_id):
+        solver = make_emulated_solver(*args, partition_granule=32, rank=rank, world=world, comm_id=comm_id)
+        solver.set_ground_truth(idx, gt)
+        seen = []
+
+        def on_stats(niter, st, elapsed):
+            x = solver.get_x()  # collective: every rank calls it at the same point
+            seen.append((st["distance_to_ground_truth"], float(np.mean(np.abs(gt - x[idx]))),
+                         st["distance_to_ground_truth_rounded"], float(np.mean(np.abs(gt - np.round(x[idx])))),
+                         st["max_bound_violation"], float(max(np.max(lb - x), np.max(x - ub)))))
+
+        run_schedule(solver, 60, None, None, False, 20, stats_func=on_stats)
+        solver.close()
+        return np.array(seen)
+
+    for seen in run_ranks(2, body):
+        assert seen.shape == (3, 6)
+        assert np.allclose(seen[:, 0], seen[:, 1], rtol=1e-13, atol=1e-16)
+        assert np.allclose(seen[:, 2], seen[:, 3], rtol=1e-13, atol=1e-16)
+        assert np.array_equal(seen[:, 4], seen[:, 5])
