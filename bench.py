@@ -319,6 +319,7 @@ def run_b200(a):
         "bound": "hbm", "kernel": dom[0], "achieved": dom[2] / (dom[1] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": dom[2] / (dom[1] * 1e-3) / 1e9 / peak, "traffic": load_ncu_traffic(dom[0]),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[2], "avg_launch_ms": dom[1],
+        "traffic_source": "profiles/ncu_summary.json (ncu --set full of variant 1, round-1 v2 capture)",
         "kernels": {"k_primal": {"ms": kp, "algorithmic_GBs": bp / (kp * 1e-3) / 1e9},
                     "k_dual": {"ms": kd, "algorithmic_GBs": bd / (kd * 1e-3) / 1e9}},
         "iteration": {"algorithmic_bytes": info["bytes_per_iteration_algorithmic"],
@@ -377,8 +378,10 @@ def run_b200(a):
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
                             "preconditioners on device, iterate, read x back"},
-            # k_primal + k_dual per iteration; with N > 1 also the two k_pack halo-staging kernels
-            "gpu_launches": (2 if world == 1 else 4) * a.steps * a.iters_per_step,
+            # k_primal + k_dual per iteration; with N > 1 also k_push + k_wait after each of them (peer memory)
+            # or one k_pack before each NCCL send/recv group
+            "gpu_launches": (2 if world == 1 else (4 if a.flags & 32 else 6)) * a.steps * a.iters_per_step,
+            "kernel_variants": kernel_variants(info),
             "clocks": clocks.summary(),
             "partition": None if world == 1 else {k: info[k] for k in (
             "n_local", "m_local", "n_ghost", "m_ghost", "nnz_local_rows", "nnz_local_cols",
@@ -390,6 +393,20 @@ def run_b200(a):
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+VARIANT_NAMES = ("loop-unroll4/8cta", "chunk2/8cta", "chunk4/6cta", "chunk4/4cta", "chunk8/4cta")
+
+
+def kernel_variants(info):
+    """Which compiled variant of each hot kernel cpppd_create kept, and the per-launch times it measured."""
+    out = {"autotuned": bool(info["autotuned"])}
+    for kernel, key in (("k_primal", "primal_variant"), ("k_dual", "dual_variant")):
+        v = info[key]
+        out[kernel] = {"variant": v, "name": VARIANT_NAMES[v - 1] if 1 <= v <= len(VARIANT_NAMES) else None,
+                       "create_time_ms_per_launch": dict(zip(VARIANT_NAMES, info["variant_ms"][kernel]))
+                       if info["autotuned"] else None}
+    return out
 
 
 def load_ncu_traffic(kernel):

@@ -36,7 +36,9 @@
 extern "C" {
 #endif
 
-#define CPPPD_ABI_VERSION 4
+#define CPPPD_ABI_VERSION 5
+
+#define CPPPD_KERNEL_VARIANTS 5
 
 typedef struct cpppd_solver *cpppd_handle;
 
@@ -75,9 +77,12 @@ enum {
   CPPPD_FLAG_NO_P2P = 1u << 5,
   /* one GPU: never renumber, whatever the padding */
   CPPPD_FLAG_NO_REORDER = 1u << 6,
-  /* world_size > 1, peer-memory halos: exchange them with separate push / wait kernels instead of
-   * inside k_primal / k_dual */
-  CPPPD_FLAG_NO_FUSED_HALO = 1u << 7
+  /* world_size > 1, peer-memory halos: let k_primal / k_dual wait for, store and signal the halos
+   * themselves instead of the separate push / wait kernels (experimental: validated on the CPU
+   * emulation of the library only) */
+  CPPPD_FLAG_FUSED_HALO = 1u << 7,
+  /* never time the kernel variants at creation: use variant 1 (see cpppd_problem.kernel_variant) */
+  CPPPD_FLAG_NO_AUTOTUNE = 1u << 8
 };
 
 typedef struct {
@@ -102,7 +107,11 @@ typedef struct {
   double one_plus_theta;/* (1 + theta) as evaluated by the host language (:226)            */
   void *stream;         /* cudaStream_t to issue on, or NULL for an internal stream        */
   uint32_t flags;       /* CPPPD_FLAG_* */
-  int32_t sort_window;  /* reserved (0): length sorting is part of the renumbering, see CPPPD_FLAG_REORDER */
+  int32_t kernel_variant; /* 0: automatic — LPs with >= 2^22 entries time every variant of k_primal / k_dual on
+                             their own operands during cpppd_create and keep the fastest, smaller ones use
+                             variant 1.  Otherwise bits 0-7 force the variant of k_primal and bits 8-15 that of
+                             k_dual (1 .. CPPPD_KERNEL_VARIANTS; bits 8-15 zero: same as k_primal).  All
+                             variants produce bit-identical iterates; they differ in loads kept in flight. */
   cpppd_alloc_fn alloc; /* may be NULL */
   cpppd_free_fn free;   /* may be NULL */
   void *alloc_user;
@@ -151,12 +160,16 @@ typedef struct {
   int32_t sm_count;
   int32_t world_size;
   int32_t rank;
-  int32_t reserved;
+  int32_t primal_variant;    /* kernel variant in use for k_primal (1-based) */
   int64_t n_local, m_local, m_eq_local;  /* columns / rows / equality rows owned by this rank      */
   int64_t n_ghost, m_ghost;              /* ghost columns (xbar) / ghost rows (y) kept by this rank */
   int64_t nnz_local_rows, nnz_local_cols;/* entries of the owned rows of A / owned columns of A     */
   int64_t halo_send_bytes_per_iteration; /* bytes this rank sends per iteration (xbar + y halos)    */
   int64_t partition_granule;
+  int32_t dual_variant;      /* kernel variant in use for k_dual (1-based) */
+  int32_t autotuned;         /* 1 when the variants were timed at creation */
+  /* milliseconds per launch measured at creation for k_primal ([0][v-1]) and k_dual ([1][v-1]); 0 = not timed */
+  float variant_ms[2][CPPPD_KERNEL_VARIANTS];
 } cpppd_info;
 
 typedef enum {

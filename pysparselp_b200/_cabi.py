@@ -10,7 +10,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
+KERNEL_VARIANTS = 5
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
@@ -22,7 +23,8 @@ FLAG_REORDER = 1 << 3
 FLAG_GRAPH_COMM = 1 << 4
 FLAG_NO_P2P = 1 << 5
 FLAG_NO_REORDER = 1 << 6
-FLAG_NO_FUSED_HALO = 1 << 7
+FLAG_FUSED_HALO = 1 << 7
+FLAG_NO_AUTOTUNE = 1 << 8
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 
@@ -35,7 +37,7 @@ class Problem(C.Structure):
         ("indptr_bits", C.c_int32), ("index_bits", C.c_int32),
         ("c", C.c_void_p), ("b", C.c_void_p), ("lb", C.c_void_p), ("ub", C.c_void_p), ("x0", C.c_void_p),
         ("alpha", C.c_double), ("theta", C.c_double), ("one_plus_theta", C.c_double),
-        ("stream", C.c_void_p), ("flags", C.c_uint32), ("sort_window", C.c_int32),
+        ("stream", C.c_void_p), ("flags", C.c_uint32), ("kernel_variant", C.c_int32),
         ("alloc", ALLOC_FN), ("free", FREE_FN), ("alloc_user", C.c_void_p),
         ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.c_void_p),
         ("partition_granule", C.c_int64), ("comm", C.c_void_p),
@@ -64,15 +66,18 @@ class Info(C.Structure):
         ("a_padded_entries", C.c_int64), ("at_padded_entries", C.c_int64), ("device_bytes", C.c_int64),
         ("bytes_per_iteration_algorithmic", C.c_int64), ("bytes_per_iteration_actual", C.c_int64),
         ("value_bytes", C.c_int32), ("const_vector_mask", C.c_int32), ("sm_count", C.c_int32),
-        ("world_size", C.c_int32), ("rank", C.c_int32), ("reserved", C.c_int32),
+        ("world_size", C.c_int32), ("rank", C.c_int32), ("primal_variant", C.c_int32),
         ("n_local", C.c_int64), ("m_local", C.c_int64), ("m_eq_local", C.c_int64),
         ("n_ghost", C.c_int64), ("m_ghost", C.c_int64),
         ("nnz_local_rows", C.c_int64), ("nnz_local_cols", C.c_int64),
         ("halo_send_bytes_per_iteration", C.c_int64), ("partition_granule", C.c_int64),
+        ("dual_variant", C.c_int32), ("autotuned", C.c_int32), ("variant_ms", (C.c_float * KERNEL_VARIANTS) * 2),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        out = {name: getattr(self, name) for name, _ in self._fields_ if name != "variant_ms"}
+        out["variant_ms"] = {"k_primal": list(self.variant_ms[0]), "k_dual": list(self.variant_ms[1])}
+        return out
 
 
 # every symbol include/cpppd.h declares: name -> (restype, argtypes)

@@ -163,6 +163,7 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   h->one_plus_theta = P->one_plus_theta;
   h->flags = P->flags;
   h->granule = P->partition_granule;
+  h->variant_request = P->kernel_variant;
   h->rank = P->rank;
   h->world = world;
   h->alloc = P->alloc;
@@ -307,7 +308,7 @@ int cpppd_dual_step(cpppd_handle h) {
 int cpppd_sync(cpppd_handle h) {
   CHECK_HANDLE(h);
   CK(cudaStreamSynchronize(h->stream));
-  return 0;
+  return check_halo_timeout(h);
 }
 
 int cpppd_read_stats(cpppd_handle h, cpppd_stats *out) {
@@ -315,6 +316,7 @@ int cpppd_read_stats(cpppd_handle h, cpppd_stats *out) {
   if (!out) return fail(h, CPPPD_ERR_INVALID, "null output");
   if (!h->stats_pending) return fail(h, CPPPD_ERR_STATE, "no stats step has been issued");
   CK(cudaStreamSynchronize(h->stream));
+  if (int rc = check_halo_timeout(h)) return rc;
   *out = *h->stats_host;
   return 0;
 }
@@ -335,7 +337,7 @@ int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms) {
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  return rc;
+  return rc ? rc : check_halo_timeout(h);
 }
 
 int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_ms) {
@@ -372,7 +374,8 @@ int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst) {
   bool is_col = true;
   if (int rc = vector_ptr(h, which, &p, &is_col)) return rc;
   if (!host_dst) return fail(h, CPPPD_ERR_INVALID, "null destination");
-  return fetch_vector(h, p, is_col, host_dst);
+  if (int rc = fetch_vector(h, p, is_col, host_dst)) return rc;
+  return check_halo_timeout(h);
 }
 
 int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src) {
@@ -483,6 +486,10 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   out->nnz_local_cols = h->nnz_cols;
   out->halo_send_bytes_per_iteration = 8 * (h->hx.send_total + h->hy.send_total);
   out->partition_granule = h->granule;
+  out->primal_variant = h->primal_variant + 1;
+  out->dual_variant = h->dual_variant + 1;
+  out->autotuned = h->autotuned ? 1 : 0;
+  memcpy(out->variant_ms, h->variant_ms, sizeof out->variant_ms);
   return 0;
 }
 

@@ -12,16 +12,6 @@ namespace {
 constexpr int kSlice = 32;       // SELL slice height C (= warp size)
 constexpr int kBlock = 256;      // threads per CTA for the streaming kernels (8 slices)
 constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
-// tuning knobs of the hot kernels (override with -DCPPPD_GATHER_CHUNK=.. -DCPPPD_MIN_BLOCKS=.. through
-// the CPPPD_NVCC_DEFINES environment variable of pysparselp_b200/build.py)
-#ifndef CPPPD_GATHER_CHUNK
-#define CPPPD_GATHER_CHUNK 4
-#endif
-#ifndef CPPPD_MIN_BLOCKS
-#define CPPPD_MIN_BLOCKS 8
-#endif
-constexpr int kGatherChunk = CPPPD_GATHER_CHUNK;  // entries of a row whose gathers are in flight together
-constexpr int kMinBlocks = CPPPD_MIN_BLOCKS;      // CTAs per SM the hot kernels are compiled for (register cap)
 constexpr int kColQ = 5;         // column-pass partials per CTA: 4 sums + max bound violation
 constexpr int kRowQ = 7;         // row-pass partials per CTA: 4 sums + 3 maxima
 constexpr int kGtQ = 2;          // ground-truth pass: sum |gt - x|, sum |gt - round(x)|
@@ -74,5 +64,17 @@ struct SyncState {
   unsigned long long push_stamp[2];  // halos pushed so far        ([0] xbar, [1] y)
   unsigned long long wait_stamp[2];  // halos consumed so far
   unsigned int ticket[2];            // CTA arrival counter of k_push
+  unsigned int timed_out;            // a wait gave up (see wait_for_stamp)
+  unsigned int pad;
+  unsigned long long timeout_ns;     // 0: wait for ever
 };
+
+// nanoseconds of a clock that is common to all threads of the device
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 }  // namespace

@@ -163,6 +163,24 @@ int detect_dictionary(cpppd_solver *h, Scratch &tmp, const double *values, int64
 }
 
 int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const std::vector<int64_t> &dst_base_y);
+int tune_kernels(cpppd_solver *h);
+
+// how long a halo wait may spin before it gives up (CPPPD_HALO_TIMEOUT_S, default 60 s, 0 = for ever)
+unsigned long long halo_timeout_ns() {
+  double seconds = 60.0;
+  if (const char *env = getenv("CPPPD_HALO_TIMEOUT_S")) seconds = atof(env);
+  return seconds > 0 ? (unsigned long long)(seconds * 1e9) : 0ull;
+}
+
+// after a synchronisation: did a halo wait give up?
+int check_halo_timeout(cpppd_solver *h) {
+  if (!h->p2p.active) return 0;
+  unsigned int flag = 0;
+  CK(cudaMemcpyAsync(&flag, &h->p2p.state->timed_out, sizeof flag, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (flag) return fail(h, CPPPD_ERR_COMM, "a halo wait timed out: a neighbour rank did not deliver its halo (CPPPD_HALO_TIMEOUT_S)");
+  return 0;
+}
 
 // What every rank publishes so that its neighbours can write into its ghost slots.
 struct PeerRecord {
@@ -180,7 +198,13 @@ int setup_p2p(cpppd_solver *h) {
   CK(cudaMalloc(&pp.state, sizeof(SyncState)));
   pp.own.push_back(pp.state);
   CK(cudaMemsetAsync(pp.flags, 0, sizeof(unsigned long long) * 2 * N, st));
-  CK(cudaMemsetAsync(pp.state, 0, sizeof(SyncState), st));
+  {
+    SyncState init;
+    memset(&init, 0, sizeof init);
+    init.timeout_ns = halo_timeout_ns();
+    CK(cudaMemcpyAsync(pp.state, &init, sizeof init, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
   PeerRecord mine;
   memset(&mine, 0, sizeof mine);
   CK(cudaIpcGetMemHandle(&mine.xbar, h->xbar));
@@ -245,7 +269,8 @@ int setup_p2p(cpppd_solver *h) {
       CK(cudaMemcpy(pp.push_dst[kind], dst.data(), sizeof(int64_t) * H.send_total, cudaMemcpyHostToDevice));
     }
   }
-  if (int rc = setup_fused(h, dst_base[0], dst_base[1])) return rc;
+  if (h->flags & CPPPD_FLAG_FUSED_HALO)
+    if (int rc = setup_fused(h, dst_base[0], dst_base[1])) return rc;
   // nobody may push before every rank has initialised its vectors and flags
   NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
   CK(cudaStreamSynchronize(st));
@@ -310,7 +335,7 @@ int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const s
     CK(cudaStreamSynchronize(st));
     tmp.release(role32);
   }
-  pp.use_fused = !(h->flags & CPPPD_FLAG_NO_FUSED_HALO);
+  pp.use_fused = true;
   return 0;
 }
 
@@ -714,6 +739,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   memset(h->stats_host, 0, sizeof(cpppd_stats));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
+  if (int rc = tune_kernels(h)) return rc;
   if (want_p2p)
     if (int rc = setup_p2p(h)) return rc;
   return 0;
@@ -733,40 +759,93 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
   return 0;
 }
 
-template <bool kWriteD, bool kDict>
-void launch_primal_t(cpppd_solver *h, const FusedComm *cm) {
-  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-  k_primal<kWriteD, kDict, kGatherChunk><<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(
-      view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
-      h->one_plus_theta, cm);
-}
-
-// Primal half + xbar halo.  world > 1: fused (the kernel waits, pushes and signals by itself over peer
-// memory), or k_push / k_wait kernels (CPPPD_FLAG_NO_FUSED_HALO), or NCCL send/recv (CPPPD_FLAG_NO_P2P).
-int launch_primal(cpppd_solver *h, bool write_d) {
+// Primal half + xbar halo.  world > 1: k_push / k_wait kernels over peer memory (default), the kernel itself
+// waits, pushes and signals (CPPPD_FLAG_FUSED_HALO), or NCCL send/recv (CPPPD_FLAG_NO_P2P).
+int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
   P2P &pp = h->p2p;
   const FusedComm *cm = pp.use_fused ? pp.fused[0] : nullptr;
   if (h->AT.nslices) {
     const bool dict = h->AT.dict != nullptr;
-    if (write_d) dict ? launch_primal_t<true, true>(h, cm) : launch_primal_t<true, false>(h, cm);
-    else dict ? launch_primal_t<false, true>(h, cm) : launch_primal_t<false, false>(h, cm);
+    const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+    PrimalFn fn = cm ? primal_kernel_fused(write_d, dict) : primal_kernel(write_d, dict, variant >= 0 ? variant : h->primal_variant);
+    fn<<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar,
+                                                              h->dbuf, h->n, has_eq, has_ineq, h->theta, h->one_plus_theta, cm);
   }
-  if (cm) return 0;
+  if (cm || variant >= 0) return 0;
   return pp.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
 }
 
-int launch_dual(cpppd_solver *h) {
+int launch_dual(cpppd_solver *h, int variant = -1) {
   P2P &pp = h->p2p;
   const FusedComm *cm = pp.use_fused ? pp.fused[1] : nullptr;
   if (h->A.nslices) {
-    const int grid = grid_for(h->A.nslices * 32);
-    if (h->A.dict)
-      k_dual<true, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
-    else
-      k_dual<false, kGatherChunk><<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
+    const bool dict = h->A.dict != nullptr;
+    DualFn fn = cm ? dual_kernel_fused(dict) : dual_kernel(dict, variant >= 0 ? variant : h->dual_variant);
+    fn<<<grid_for(h->A.nslices * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
   }
-  if (cm) return 0;
+  if (cm || variant >= 0) return 0;
   return pp.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
+}
+
+// Choose the kernel variants (called at the end of setup(), before any neighbour may write into this
+// rank's vectors).  Forced by cpppd_problem.kernel_variant / CPPPD_KERNEL_VARIANT, or — for LPs large
+// enough for the choice to matter — measured: every variant runs on the real operands (1 warm-up + 2
+// timed launches, CUDA events), the fastest wins, and variant 0 is only given up for a gain above 2 %.
+// The iterates do not depend on the choice; the state (x, xbar, y) is put back afterwards.
+int tune_kernels(cpppd_solver *h) {
+  int request = h->variant_request;
+  if (request == 0)
+    if (const char *env = getenv("CPPPD_KERNEL_VARIANT")) request = atoi(env);
+  if (request != 0) {
+    const int p = request & 0xff, d = (request >> 8) & 0xff ? (request >> 8) & 0xff : p;
+    if (p < 1 || p > kNumVariants || d < 1 || d > kNumVariants)
+      return fail(h, CPPPD_ERR_INVALID, "kernel_variant %d: variants are 1 .. %d", request, kNumVariants);
+    h->primal_variant = p - 1;
+    h->dual_variant = d - 1;
+    return 0;
+  }
+  int64_t min_nnz = (int64_t)1 << 22;
+  if (const char *env = getenv("CPPPD_AUTOTUNE_MIN_NNZ")) min_nnz = atoll(env);
+  if ((h->flags & CPPPD_FLAG_NO_AUTOTUNE) || std::max(h->nnz_rows, h->nnz_cols) < min_nnz) return 0;
+  cudaStream_t st = h->stream;
+  Scratch tmp(h);
+  const int64_t nx = h->n + h->hx.ghost, ny = h->m + h->hy.ghost;
+  double *x_saved = nullptr;
+  if (int rc = tmp.get(&x_saved, nx)) return rc;
+  CK(cudaMemcpyAsync(x_saved, h->x, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int rc = 0;
+  for (int kind = 0; kind < 2 && !rc; ++kind) {
+    int best = 0;
+    for (int v = 0; v < kNumVariants && !rc; ++v) {
+      float ms = 0.f;
+      for (int rep = 0; rep < 3 && !rc; ++rep) {  // rep 0 warms up
+        if (rep == 1) CK(cudaEventRecord(e0, st));
+        rc = kind == 0 ? launch_primal(h, false, v) : launch_dual(h, v);
+      }
+      if (rc) break;
+      CK(cudaEventRecord(e1, st));
+      CK(cudaEventSynchronize(e1));
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      h->variant_ms[kind][v] = ms / 2;
+      if (h->variant_ms[kind][v] < h->variant_ms[kind][best]) best = v;
+    }
+    if (best != 0 && h->variant_ms[kind][best] > 0.98f * h->variant_ms[kind][0]) best = 0;
+    (kind == 0 ? h->primal_variant : h->dual_variant) = best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc) return rc;
+  h->autotuned = true;
+  // back to the initial state: x = x0, xbar = x (:190), y = 0 (:166,:177)
+  CK(cudaMemcpyAsync(h->x, x_saved, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(h->xbar, x_saved, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemsetAsync(h->y, 0, sizeof(double) * std::max<int64_t>(ny, 1), st));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  return 0;
 }
 
 int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {

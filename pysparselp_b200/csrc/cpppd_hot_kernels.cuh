@@ -21,6 +21,22 @@ inline unsigned long long ld_acquire_sys(const unsigned long long *p) { return _
 inline void st_release_sys(unsigned long long *p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #endif
 
+// Spin until *flag >= want.  A neighbour that never arrives (a crashed rank, a protocol error) must not
+// hang the GPU: after st->timeout_ns the wait gives up, records it in st->timed_out (the host turns that
+// into CPPPD_ERR_COMM at its next synchronisation) and the kernel runs on with whatever the ghosts hold.
+__device__ __forceinline__ void wait_for_stamp(const unsigned long long *flag, unsigned long long want, SyncState *st,
+                                               unsigned sleep_ns) {
+  if (ld_acquire_sys(flag) >= want) return;
+  const unsigned long long t0 = global_timer_ns(), limit = st->timeout_ns;
+  while (ld_acquire_sys(flag) < want) {
+    __nanosleep(sleep_ns);
+    if (limit && global_timer_ns() - t0 > limit) {
+      st->timed_out = 1u;
+      break;
+    }
+  }
+}
+
 // Device-resident description of the halo a kernel produces (kind_out) and consumes (kind_in).
 // role[s] of a slice: bit 0 = some row of the slice is sent to a neighbour, bit 1 = some row reads a
 // ghost entry.  Warps of such slices first wait for the neighbours' stamps of the consumed halo
@@ -45,7 +61,7 @@ __device__ __forceinline__ void comm_wait(const FusedComm *cm, int lane) {
   const unsigned long long want = cm->st->wait_stamp[cm->kind_in] + (cm->kind_in == 0 ? 1 : 0);
   for (int t = lane; t < cm->world; t += 32)
     if ((cm->recv_mask_in >> t) & 1ull)
-      while (ld_acquire_sys(cm->my_flags + cm->kind_in * cm->world + t) < want) __nanosleep(100);
+      wait_for_stamp(cm->my_flags + cm->kind_in * cm->world + t, want, cm->st, 100);
   __syncwarp();
 }
 
@@ -86,51 +102,52 @@ __device__ __forceinline__ void comm_finish(const FusedComm *cm) {
 // ------------------------------------------------------------------------------------------
 // the two hot kernels
 // ------------------------------------------------------------------------------------------
-// body of k_primal for one thread (column j of slice s)
-template <bool kWriteD, bool kDict, int kChunk>
-__device__ __forceinline__ void primal_rows(const SellView &AT, const double *__restrict__ y, const Vec &c, const Vec &T,
-                                            const Vec &lb, const Vec &ub, double *__restrict__ x,
-                                            double *__restrict__ xbar, double *__restrict__ d_out, int64_t n,
-                                            int has_eq, int has_ineq, double theta, double one_plus_theta,
-                                            const FusedComm *__restrict__ cm, const double *sdict, int64_t j, int64_t s) {
-  const int lane = threadIdx.x & 31;
-  int role = 0;
-  if (cm) {
-    role = cm->role[s];
-    if (role) comm_wait(cm, lane);
-  }
-  int64_t p0, p1;
-  slice_range(AT, s, p0, p1);
-  const bool live = j < n;
-  double cj = 0.0, tj = 0.0, xo = 0.0;
-  if (live) {
-    cj = c.at(j);
-    tj = T.at(j);
-    xo = __ldcs(x + j);
-  }
-  double s_eq = 0.0, s_in = 0.0;
-  {
-    const int32_t *ip = AT.idx + p0 + lane;
-    const double *vp = AT.val + p0 + lane;
-    const int width = (int)((p1 - p0) >> 5);
-    const int32_t mask = AT.idx_mask;
-    // entries are taken kChunk at a time: all index (and value) loads of a chunk are issued first,
-    // then all gathers, then the sequential accumulation — so a row of any width (also 2 or 3) keeps
-    // kChunk independent gathers in flight instead of one load-use chain per entry
+// Every variant of a kernel performs exactly the same floating point operations in exactly the same
+// order (a row / column sum is accumulated sequentially in stored entry order), so the iterates do not
+// depend on the variant.  What differs is how many independent loads a thread keeps in flight:
+//   kChunk == 0 : the loop of the round-1 "v2" kernels measured on hardware (unroll 4 + scalar remainder);
+//   kChunk >= 1 : entries are taken kChunk at a time — all index (and value) loads of a chunk are issued
+//                 first, then all gathers, then the sequential accumulation — so a row of any width (also
+//                 2 or 3, the Potts widths) keeps kChunk independent gathers in flight instead of one
+//                 load-use chain per entry.
+// kMinB is the CTAs/SM the variant is compiled for (register cap = 65536 / (256 * kMinB)).
+// cpppd_create() times the variants on the actual operands and keeps the fastest (cpppd_host.cuh).
+
+// sum of column j of A times y, equality and inequality rows apart (:206, :216)
+template <bool kDict, int kChunk>
+__device__ __forceinline__ void primal_sums(const SellView &AT, const double *__restrict__ y, const double *sdict,
+                                            int64_t p0, int64_t p1, int lane, double &s_eq, double &s_in) {
+  const int32_t *ip = AT.idx + p0 + lane;
+  const double *vp = AT.val + p0 + lane;
+  const int width = (int)((p1 - p0) >> 5);
+  const int32_t mask = AT.idx_mask;
+  if (kChunk == 0) {
+#pragma unroll 4
+    for (int k = 0; k < width; ++k) {
+      const int32_t r = __ldcs(ip + k * kSlice);
+      double a;
+      if (kDict) a = sdict[(r >> AT.idx_bits) & AT.code_mask]; else a = __ldcs(vp + k * kSlice);
+      if (r >= 0) {
+        const double t = __dmul_rn(a, __ldg(y + (r & mask)));
+        if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+      }
+    }
+  } else {
+    constexpr int kC = kChunk > 0 ? kChunk : 1;
 #pragma unroll 1
-    for (int k0 = 0; k0 < width; k0 += kChunk) {
-      int32_t r[kChunk];
-      double a[kChunk], g[kChunk];
+    for (int k0 = 0; k0 < width; k0 += kC) {
+      int32_t r[kC];
+      double a[kC], g[kC];
 #pragma unroll
-      for (int u = 0; u < kChunk; ++u) {
+      for (int u = 0; u < kC; ++u) {
         const bool ok = k0 + u < width;
         r[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
         a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < kChunk; ++u) g[u] = r[u] >= 0 ? __ldg(y + (r[u] & mask)) : 0.0;
+      for (int u = 0; u < kC; ++u) g[u] = r[u] >= 0 ? __ldg(y + (r[u] & mask)) : 0.0;
 #pragma unroll
-      for (int u = 0; u < kChunk; ++u) {
+      for (int u = 0; u < kC; ++u) {
         if (r[u] >= 0) {
           const double av = kDict ? sdict[(r[u] >> AT.idx_bits) & AT.code_mask] : a[u];
           const double t = __dmul_rn(av, g[u]);
@@ -139,11 +156,88 @@ __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__
       }
     }
   }
+}
+
+// row i of A times xbar (:235, :240)
+template <bool kDict, int kChunk>
+__device__ __forceinline__ double dual_sum(const SellView &A, const double *__restrict__ xbar, const double *sdict,
+                                           int64_t p0, int64_t p1, int lane) {
+  const int32_t *ip = A.idx + p0 + lane;
+  const double *vp = A.val + p0 + lane;
+  const int width = (int)((p1 - p0) >> 5);
+  const int32_t mask = A.idx_mask;
+  double acc = 0.0;
+  if (kChunk == 0) {
+#pragma unroll 4
+    for (int k = 0; k < width; ++k) {
+      const int32_t jc = __ldcs(ip + k * kSlice);
+      double a;
+      if (kDict) a = sdict[(jc >> A.idx_bits) & A.code_mask]; else a = __ldcs(vp + k * kSlice);
+      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + (jc & mask))));
+    }
+  } else {
+    constexpr int kC = kChunk > 0 ? kChunk : 1;
+#pragma unroll 1
+    for (int k0 = 0; k0 < width; k0 += kC) {
+      int32_t jc[kC];
+      double a[kC], g[kC];
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const bool ok = k0 + u < width;
+        jc[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
+        a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kC; ++u) g[u] = jc[u] >= 0 ? __ldg(xbar + (jc[u] & mask)) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        if (jc[u] >= 0) {
+          const double av = kDict ? sdict[(jc[u] >> A.idx_bits) & A.code_mask] : a[u];
+          acc = __dadd_rn(acc, __dmul_rn(av, g[u]));
+        }
+      }
+    }
+  }
+  return acc;
+}
+
+// body of k_primal for one thread (column j of slice s)
+template <bool kWriteD, bool kDict, int kChunk, bool kEarlyBounds, bool kComm>
+__device__ __forceinline__ void primal_rows(const SellView &AT, const double *__restrict__ y, const Vec &c, const Vec &T,
+                                            const Vec &lb, const Vec &ub, double *__restrict__ x,
+                                            double *__restrict__ xbar, double *__restrict__ d_out, int64_t n,
+                                            int has_eq, int has_ineq, double theta, double one_plus_theta,
+                                            const FusedComm *__restrict__ cm, const double *sdict, int64_t j, int64_t s) {
+  const int lane = threadIdx.x & 31;
+  int role = 0;
+  if (kComm) {
+    role = cm->role[s];
+    if (role) comm_wait(cm, lane);
+  }
+  int64_t p0, p1;
+  slice_range(AT, s, p0, p1);
+  const bool live = j < n;
+  // loads that do not depend on the matrix are issued first: they are in flight together with the entries
+  double cj = 0.0, tj = 0.0, xo = 0.0, l = 0.0, u = 0.0;
+  if (live) {
+    cj = c.at(j);
+    tj = T.at(j);
+    xo = __ldcs(x + j);
+    if (kEarlyBounds) {
+      l = lb.at(j);
+      u = ub.at(j);
+    }
+  }
+  double s_eq = 0.0, s_in = 0.0;
+  primal_sums<kDict, kChunk>(AT, y, sdict, p0, p1, lane, s_eq, s_in);
   if (!live) return;
   double d = cj;
   if (has_eq) d = __dadd_rn(d, s_eq);
   if (has_ineq) d = __dadd_rn(d, s_in);
-  const double l = lb.at(j), u = ub.at(j);
+  if (!kEarlyBounds) {
+    l = lb.at(j);
+    u = ub.at(j);
+  }
   double x2 = __dsub_rn(xo, __dmul_rn(tj, d));
   x2 = (l > x2) ? l : x2;  // np.maximum(x2, lb)  (NaN in x2 propagates)
   x2 = (u < x2) ? u : x2;  // np.minimum(x2, ub)
@@ -151,16 +245,16 @@ __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__
   xbar[j] = xb;
   x[j] = x2;
   if (kWriteD) d_out[j] = d;
-  if (role & 1) comm_push(cm, (int32_t)j, xb);
+  if (kComm && (role & 1)) comm_push(cm, (int32_t)j, xb);
 }
 
-// Primal half-iteration (:198-228).  Thread j owns column j of A (row j of A^T).
-// Loads that do not depend on the matrix (c, T, x) are issued first so that they are in flight
-// together with the slice entries; matrix entries are read once (ld.global.cs).
+// Primal half-iteration (:198-228).  Thread j owns column j of A (row j of A^T); matrix entries are read
+// once (ld.global.cs).
 // kDict: entries are single 32-bit words [pad][eq][code][index]; values come from a <= 256 entry
 // dictionary staged in shared memory.
-template <bool kWriteD, bool kDict, int kChunk>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+// kComm: the halo exchange is done by the kernel itself (see FusedComm); cm is not touched otherwise.
+template <bool kWriteD, bool kDict, int kChunk, int kMinB, bool kComm>
+__global__ void __launch_bounds__(kBlock, kMinB)
 k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
          double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int has_eq, int has_ineq,
          double theta, double one_plus_theta, const FusedComm *__restrict__ cm) {
@@ -171,19 +265,20 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
   }
   const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = j >> 5;
-  if (s < AT.nslices) primal_rows<kWriteD, kDict, kChunk>(AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta,
-                                                          one_plus_theta, cm, sdict, j, s);
-  if (cm) comm_finish(cm);  // every thread of the CTA gets here (no early return above)
+  if (s < AT.nslices)
+    primal_rows<kWriteD, kDict, kChunk, (kChunk > 0 && kMinB <= 6), kComm>(AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq,
+                                                                          has_ineq, theta, one_plus_theta, cm, sdict, j, s);
+  if (kComm) comm_finish(cm);  // every thread of the CTA gets here (no early return above)
 }
 
 // body of k_dual for one thread (row i of slice s)
-template <bool kDict, int kChunk>
+template <bool kDict, int kChunk, bool kComm>
 __device__ __forceinline__ void dual_rows(const SellView &A, const double *__restrict__ xbar, const Vec &b,
                                           const Vec &sigma, double *__restrict__ y, int64_t m, int64_t m_eq,
                                           const FusedComm *__restrict__ cm, const double *sdict, int64_t i, int64_t s) {
   const int lane = threadIdx.x & 31;
   int role = 0;
-  if (cm) {
+  if (kComm) {
     role = cm->role[s];
     if (role) comm_wait(cm, lane);
   }
@@ -196,44 +291,18 @@ __device__ __forceinline__ void dual_rows(const SellView &A, const double *__res
     si = sigma.at(i);
     yi = __ldcs(y + i);
   }
-  double acc = 0.0;
-  {
-    const int32_t *ip = A.idx + p0 + lane;
-    const double *vp = A.val + p0 + lane;
-    const int width = (int)((p1 - p0) >> 5);
-    const int32_t mask = A.idx_mask;
-#pragma unroll 1
-    for (int k0 = 0; k0 < width; k0 += kChunk) {  // see k_primal: loads of a chunk first, then gathers, then sums
-      int32_t jc[kChunk];
-      double a[kChunk], g[kChunk];
-#pragma unroll
-      for (int u = 0; u < kChunk; ++u) {
-        const bool ok = k0 + u < width;
-        jc[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
-        a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < kChunk; ++u) g[u] = jc[u] >= 0 ? __ldg(xbar + (jc[u] & mask)) : 0.0;
-#pragma unroll
-      for (int u = 0; u < kChunk; ++u) {
-        if (jc[u] >= 0) {
-          const double av = kDict ? sdict[(jc[u] >> A.idx_bits) & A.code_mask] : a[u];
-          acc = __dadd_rn(acc, __dmul_rn(av, g[u]));
-        }
-      }
-    }
-  }
+  const double acc = dual_sum<kDict, kChunk>(A, xbar, sdict, p0, p1, lane);
   if (!live) return;
   const double r = __dsub_rn(acc, bi);
   double yn = __dadd_rn(yi, __dmul_rn(si, r));
   if (i >= m_eq) yn = (yn < 0.0) ? 0.0 : yn;  // np.maximum(y_ineq, 0): NaN stays NaN, -0.0 stays
   y[i] = yn;
-  if (role & 1) comm_push(cm, (int32_t)i, yn);
+  if (kComm && (role & 1)) comm_push(cm, (int32_t)i, yn);
 }
 
 // Dual half-iteration (:231-240, :333-341).  Thread i owns row i of A.
-template <bool kDict, int kChunk>
-__global__ void __launch_bounds__(kBlock, kMinBlocks)
+template <bool kDict, int kChunk, int kMinB, bool kComm>
+__global__ void __launch_bounds__(kBlock, kMinB)
 k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__restrict__ y, int64_t m,
        int64_t m_eq, const FusedComm *__restrict__ cm) {
   __shared__ double sdict[kDict ? 256 : 1];
@@ -243,8 +312,56 @@ k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__
   }
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = i >> 5;
-  if (s < A.nslices) dual_rows<kDict, kChunk>(A, xbar, b, sigma, y, m, m_eq, cm, sdict, i, s);
-  if (cm) comm_finish(cm);
+  if (s < A.nslices) dual_rows<kDict, kChunk, kComm>(A, xbar, b, sigma, y, m, m_eq, cm, sdict, i, s);
+  if (kComm) comm_finish(cm);
 }
+
+// ------------------------------------------------------------------------------------------
+// variant table
+// ------------------------------------------------------------------------------------------
+struct HotVariant {
+  int chunk, min_blocks;
+  const char *name;
+};
+// index 0 is the variant every other one is measured against (and the one used without tuning)
+constexpr int kNumVariants = 5;
+constexpr HotVariant kVariants[kNumVariants] = {
+    {0, 8, "loop-unroll4/8cta"}, {2, 8, "chunk2/8cta"}, {4, 6, "chunk4/6cta"}, {4, 4, "chunk4/4cta"}, {8, 4, "chunk8/4cta"}};
+
+using PrimalFn = void (*)(SellView, const double *, Vec, Vec, Vec, Vec, double *, double *, double *, int64_t, int, int,
+                          double, double, const FusedComm *);
+using DualFn = void (*)(SellView, const double *, Vec, Vec, double *, int64_t, int64_t, const FusedComm *);
+
+template <bool kWriteD, bool kDict>
+PrimalFn primal_variant(int v) {
+  switch (v) {
+    case 1: return k_primal<kWriteD, kDict, 2, 8, false>;
+    case 2: return k_primal<kWriteD, kDict, 4, 6, false>;
+    case 3: return k_primal<kWriteD, kDict, 4, 4, false>;
+    case 4: return k_primal<kWriteD, kDict, 8, 4, false>;
+    default: return k_primal<kWriteD, kDict, 0, 8, false>;
+  }
+}
+template <bool kDict>
+DualFn dual_variant(int v) {
+  switch (v) {
+    case 1: return k_dual<kDict, 2, 8, false>;
+    case 2: return k_dual<kDict, 4, 6, false>;
+    case 3: return k_dual<kDict, 4, 4, false>;
+    case 4: return k_dual<kDict, 8, 4, false>;
+    default: return k_dual<kDict, 0, 8, false>;
+  }
+}
+inline PrimalFn primal_kernel(bool write_d, bool dict, int v) {
+  if (write_d) return dict ? primal_variant<true, true>(v) : primal_variant<true, false>(v);
+  return dict ? primal_variant<false, true>(v) : primal_variant<false, false>(v);
+}
+inline DualFn dual_kernel(bool dict, int v) { return dict ? dual_variant<true>(v) : dual_variant<false>(v); }
+// kernels that carry the halo exchange themselves (CPPPD_FLAG_FUSED_HALO): variant 0 only
+inline PrimalFn primal_kernel_fused(bool write_d, bool dict) {
+  if (write_d) return dict ? k_primal<true, true, 0, 8, true> : k_primal<true, false, 0, 8, true>;
+  return dict ? k_primal<false, true, 0, 8, true> : k_primal<false, false, 0, 8, true>;
+}
+inline DualFn dual_kernel_fused(bool dict) { return dict ? k_dual<true, 0, 8, true> : k_dual<false, 0, 8, true>; }
 
 }  // namespace

@@ -208,9 +208,7 @@ __global__ void k_wait(const unsigned long long *__restrict__ flags, int kind, i
                        unsigned long long recv_mask, SyncState *st) {
   const int t = threadIdx.x;
   const unsigned long long want = st->wait_stamp[kind] + 1;
-  if (t < world && ((recv_mask >> t) & 1ull)) {
-    while (ld_acquire_sys(flags + kind * world + t) < want) __nanosleep(200);
-  }
+  if (t < world && ((recv_mask >> t) & 1ull)) wait_for_stamp(flags + kind * world + t, want, st, 200);
   __syncthreads();
   if (t == 0) st->wait_stamp[kind] = want;
 }

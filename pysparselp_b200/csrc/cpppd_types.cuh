@@ -170,6 +170,11 @@ struct cpppd_solver {
   bool have_d = false;
   int sm_count = 148;
   std::map<int64_t, cudaGraphExec_t> graphs;
+  // kernel variants (0-based indices into kVariants): chosen at creation, see tune_kernels()
+  int variant_request = 0;  // cpppd_problem.kernel_variant
+  int primal_variant = 0, dual_variant = 0;
+  bool autotuned = false;
+  float variant_ms[2][CPPPD_KERNEL_VARIANTS] = {};
   std::string err;
   int sticky = 0;
 };

@@ -84,14 +84,15 @@ def main():
     solver.close()
     assert np.array_equal(x, xo)
     assert info["n_ghost"] <= 2 * 256 + 64 and info["m_ghost"] <= 8 * 256 + 64, info
-    # every halo transport (NCCL send/recv, push/wait kernels, fused into the kernels = default) and the
-    # compressed storage must give the same bits
+    # the other halo transport (NCCL send/recv instead of the peer-memory push / wait kernels), the compressed
+    # storage and every kernel variant must give the same bits
     from pysparselp_b200 import _cabi
 
-    for flags in (_cabi.FLAG_NO_P2P, _cabi.FLAG_NO_FUSED_HALO, _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS):
-        x2, _, solver = chambolle_pock_ppd(*args, nb_max_iter=30, nb_iter_plot=1000, return_solver=True, flags=flags)
+    for flags, variant in ((_cabi.FLAG_NO_P2P, 0), (_cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS, 0), (0, 3), (0, 5)):
+        x2, _, solver = chambolle_pock_ppd(*args, nb_max_iter=30, nb_iter_plot=1000, return_solver=True, flags=flags,
+                                           kernel_variant=variant)
         solver.close()
-        assert np.array_equal(x2, xo), flags
+        assert np.array_equal(x2, xo), (flags, variant)
     # x0 warm start in distributed mode
     rng = np.random.default_rng(3)
     args, _ = case_args("random_small")

@@ -9,6 +9,7 @@
 // before the barrier is an idempotent shared-memory fill: the block is run twice, the first time every
 // thread stops at the barrier (exception), the second time the barrier is a no-op.
 #pragma once
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -37,3 +38,9 @@ inline void __nanosleep(unsigned) {}
 inline void __syncwarp() {}
 inline void __threadfence_system() {}
 inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
+
+// device-wide nanosecond clock (%globaltimer on the GPU)
+inline unsigned long long global_timer_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}

@@ -36,47 +36,31 @@ SellView make_view(const int64_t *slice_ptr, const int32_t *idx, const double *v
 
 }  // namespace
 
-#ifdef EMUL_HAS_CHUNK
-#define PRIMAL(W, D) k_primal<W, D, kGatherChunk>
-#define DUAL(D) k_dual<D, kGatherChunk>
-#define EXTRA , nullptr
-#else
-#define PRIMAL(W, D) k_primal<W, D>
-#define DUAL(D) k_dual<D>
-#define EXTRA
-#endif
-
 extern "C" {
 
 struct EmulVec { const double *p; double c; };
 
-void emul_primal(int write_d, const int64_t *slice_ptr, const int32_t *idx, const double *val, int64_t nrows,
+void emul_primal(int variant, int write_d, const int64_t *slice_ptr, const int32_t *idx, const double *val, int64_t nrows,
                  int64_t nslices, int64_t uniform_width, const double *dict, int idx_bits, int ndict, const double *y,
                  EmulVec c, EmulVec T, EmulVec lb, EmulVec ub, double *x, double *xbar, double *d_out, int has_eq,
                  int has_ineq, double theta, double one_plus_theta) {
   SellView AT = make_view(slice_ptr, idx, val, nrows, nslices, uniform_width, dict, idx_bits, ndict);
   Vec vc{c.p, c.c}, vT{T.p, T.c}, vlb{lb.p, lb.c}, vub{ub.p, ub.c};
-  run_grid(nslices, dict != nullptr, [&] {
-    if (dict) {
-      if (write_d) PRIMAL(true, true)(AT, y, vc, vT, vlb, vub, x, xbar, d_out, nrows, has_eq, has_ineq, theta, one_plus_theta EXTRA);
-      else PRIMAL(false, true)(AT, y, vc, vT, vlb, vub, x, xbar, d_out, nrows, has_eq, has_ineq, theta, one_plus_theta EXTRA);
-    } else {
-      if (write_d) PRIMAL(true, false)(AT, y, vc, vT, vlb, vub, x, xbar, d_out, nrows, has_eq, has_ineq, theta, one_plus_theta EXTRA);
-      else PRIMAL(false, false)(AT, y, vc, vT, vlb, vub, x, xbar, d_out, nrows, has_eq, has_ineq, theta, one_plus_theta EXTRA);
-    }
-  });
+  PrimalFn fn = primal_kernel(write_d != 0, dict != nullptr, variant);
+  run_grid(nslices, dict != nullptr,
+           [&] { fn(AT, y, vc, vT, vlb, vub, x, xbar, d_out, nrows, has_eq, has_ineq, theta, one_plus_theta, nullptr); });
 }
 
-void emul_dual(const int64_t *slice_ptr, const int32_t *idx, const double *val, int64_t nrows, int64_t nslices,
+void emul_dual(int variant, const int64_t *slice_ptr, const int32_t *idx, const double *val, int64_t nrows, int64_t nslices,
                int64_t uniform_width, const double *dict, int idx_bits, int ndict, const double *xbar, EmulVec b,
                EmulVec sigma, double *y, int64_t m_eq) {
   SellView A = make_view(slice_ptr, idx, val, nrows, nslices, uniform_width, dict, idx_bits, ndict);
   Vec vb{b.p, b.c}, vs{sigma.p, sigma.c};
-  run_grid(nslices, dict != nullptr, [&] {
-    if (dict) DUAL(true)(A, xbar, vb, vs, y, nrows, m_eq EXTRA);
-    else DUAL(false)(A, xbar, vb, vs, y, nrows, m_eq EXTRA);
-  });
+  DualFn fn = dual_kernel(dict != nullptr, variant);
+  run_grid(nslices, dict != nullptr, [&] { fn(A, xbar, vb, vs, y, nrows, m_eq, nullptr); });
 }
+
+int emul_num_variants() { return kNumVariants; }
 
 int emul_constants(int which) {
   switch (which) {

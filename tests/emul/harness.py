@@ -31,10 +31,8 @@ def build(force=False):
     if not force and os.path.isfile(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    has_chunk = "kChunk" in open(os.path.join(CSRC, "cpppd_hot_kernels.cuh")).read()
-    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC"] + (
-        ["-DEMUL_HAS_CHUNK"] if has_chunk else []) + os.environ.get("CPPPD_NVCC_DEFINES", "").split() + [
-        "-o", LIB, os.path.join(HERE, "emul_kernels.cpp")]
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC",
+           "-o", LIB, os.path.join(HERE, "emul_kernels.cpp")]
     subprocess.run(cmd, check=True, capture_output=True)
     return LIB
 
@@ -80,7 +78,7 @@ class EmulSolver:
     """The solver loop with the real kernel sources on the CPU (single rank, original numbering)."""
 
     def __init__(self, c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1,
-                 value_dict=False, const_vectors=False):
+                 value_dict=False, const_vectors=False, variant=0):
         from oracle.cpppd_oracle import CpPpdOracle, one_sided_system
 
         if a_eq is not None and a_eq.shape[0] == 0:
@@ -121,6 +119,7 @@ class EmulSolver:
         self.y = np.zeros(m)
         self.d = np.zeros(n)
         self.const_vectors = const_vectors
+        self.variant = int(variant)  # 0-based index into kVariants
 
     def _vec(self, v):
         if self.const_vectors and v.size and np.all(v.view(np.uint64) == v.view(np.uint64)[0]):
@@ -135,14 +134,14 @@ class EmulSolver:
                 C.c_int(self.idx_bits), C.c_int(self.ndict))
 
     def primal(self, write_d=False):
-        lib().emul_primal(C.c_int(int(write_d)), *self._sell_args(self.AT), self.y.ctypes.data_as(C.c_void_p),
+        lib().emul_primal(C.c_int(self.variant), C.c_int(int(write_d)), *self._sell_args(self.AT), self.y.ctypes.data_as(C.c_void_p),
                           self._vec(self.c), self._vec(self.T), self._vec(self.lb), self._vec(self.ub),
                           self.x.ctypes.data_as(C.c_void_p), self.xbar.ctypes.data_as(C.c_void_p),
                           self.d.ctypes.data_as(C.c_void_p), C.c_int(self.has_eq), C.c_int(self.has_ineq),
                           C.c_double(self.theta), C.c_double(self.opt))
 
     def dual(self):
-        lib().emul_dual(*self._sell_args(self.A), self.xbar.ctypes.data_as(C.c_void_p), self._vec(self.b),
+        lib().emul_dual(C.c_int(self.variant), *self._sell_args(self.A), self.xbar.ctypes.data_as(C.c_void_p), self._vec(self.b),
                         self._vec(self.sigma), self.y.ctypes.data_as(C.c_void_p), C.c_int64(self.m_eq))
 
     def iterate(self, k):

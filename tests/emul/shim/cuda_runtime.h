@@ -11,6 +11,7 @@
 //
 // Nothing in the product includes or loads this; the product has no CPU path.
 #pragma once
+#include <chrono>
 #include <sched.h>
 #include <ucontext.h>
 
@@ -256,3 +257,9 @@ inline cudaError_t cudaGraphLaunch(cudaGraphExec_t g, cudaStream_t) { for (auto 
 inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+
+// device-wide nanosecond clock (%globaltimer on the GPU)
+inline unsigned long long global_timer_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}

@@ -13,12 +13,20 @@ def test_emulator_uses_the_product_constants():
     assert lib().emul_constants(2) == 0x40000000 and lib().emul_constants(3) == -2**31
 
 
+def test_emulator_sees_every_kernel_variant():
+    from pysparselp_b200 import _cabi
+
+    assert lib().emul_num_variants() == _cabi.KERNEL_VARIANTS
+
+
+@pytest.mark.parametrize("variant", range(5))
 @pytest.mark.parametrize("compressed", [False, True])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_hot_kernels_bit_exact_on_cpu(name, compressed):
+def test_hot_kernels_bit_exact_on_cpu(name, compressed, variant):
+    """every variant of the two kernels (loop flavour x registers) must give the same bits"""
     args, g = case_args(name)
     kw = CASE_PARAMS.get(name, {})
-    s = EmulSolver(*args, value_dict=compressed, const_vectors=compressed, **kw)
+    s = EmulSolver(*args, value_dict=compressed, const_vectors=compressed, variant=variant, **kw)
     if compressed and name == "potts50":
         assert s.dict is not None and s.dict.size == 2  # the +-1 matrix really takes the dictionary path
     s.iterate(50)
@@ -50,6 +58,7 @@ def test_hot_kernels_with_x0_and_ragged_sizes():
     args = (c, sp.csr_matrix((0, n)), np.empty(0), a, None, b_up, lb, ub)
     st = {}
     xo, _ = chambolle_pock_ppd_oracle(*args, x0=x0, nb_max_iter=60, nb_iter_plot=10**6, state_out=st)
-    s = EmulSolver(*args, x0=x0)
-    s.iterate(60)
-    assert np.array_equal(s.x, xo) and np.array_equal(s.y, st["y_ineq"]) and np.array_equal(s.xbar, st["xbar"])
+    for variant in range(5):
+        s = EmulSolver(*args, x0=x0, variant=variant)
+        s.iterate(60)
+        assert np.array_equal(s.x, xo) and np.array_equal(s.y, st["y_ineq"]) and np.array_equal(s.xbar, st["xbar"])

@@ -204,3 +204,54 @@ def test_solve_curves_on_device_equal_host_curves(case, monkeypatch):
         else:
             assert np.array_equal(cd[k], ch[k], equal_nan=True), k
     np.testing.assert_almost_equal(cd["distance_to_ground_truth"], golden[: len(cd["distance_to_ground_truth"])])
+
+
+@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 3 | (5 << 8)])
+@pytest.mark.parametrize("flags", [0, _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS])
+def test_emulated_every_kernel_variant_gives_the_same_bits(kernel_variant, flags):
+    """cpppd_problem.kernel_variant forces one of the compiled variants of k_primal / k_dual; the arithmetic of
+    a row / column sum is the same sequential chain in all of them."""
+    for name in ("potts50", "random_small"):
+        args, g = case_args(name)
+        trace = []
+        x, best, solver = emulated_chambolle_pock_ppd(
+            *args, nb_max_iter=100, nb_iter_plot=10, flags=flags, kernel_variant=kernel_variant,
+            callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)))
+        info = solver.info()
+        y = solver.get_y()
+        solver.close()
+        assert info["primal_variant"] == kernel_variant & 0xFF
+        assert info["dual_variant"] == ((kernel_variant >> 8) & 0xFF or kernel_variant & 0xFF)
+        assert not info["autotuned"]
+        assert np.array_equal(x, g["x_100"])
+        assert np.array_equal(y, np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g]))
+        curves_close(np.array(trace), g["trace_10"])
+
+
+def test_emulated_bad_kernel_variant_is_refused():
+    args, _ = case_args("sc105")
+    with pytest.raises(_cabi.CpppdError, match="kernel_variant"):
+        make_emulated_solver(*args, kernel_variant=9)
+
+
+def test_emulated_autotune_leaves_the_initial_state_untouched(monkeypatch):
+    """Timing the variants at creation runs the kernels on the real operands: x0 / xbar / y must be put back."""
+    from oracle.cpppd_oracle import chambolle_pock_ppd_oracle
+
+    monkeypatch.setenv("CPPPD_AUTOTUNE_MIN_NNZ", "0")
+    args, g = case_args("random_small")
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal(args[0].size)
+    with np.errstate(invalid="ignore"):
+        xo, _ = chambolle_pock_ppd_oracle(*args, x0=x0, nb_max_iter=64, nb_iter_plot=1000)
+    x, _, solver = emulated_chambolle_pock_ppd(*args, x0=x0, nb_max_iter=64, nb_iter_plot=1000)
+    info = solver.info()
+    solver.close()
+    assert np.array_equal(x, xo)
+    assert info["autotuned"] == 1 and 1 <= info["primal_variant"] <= 5 and 1 <= info["dual_variant"] <= 5
+    assert all(v > 0 for v in info["variant_ms"]["k_primal"]) and all(v > 0 for v in info["variant_ms"]["k_dual"])
+    # not timed when asked not to
+    x, _, solver = emulated_chambolle_pock_ppd(*args, x0=x0, nb_max_iter=64, nb_iter_plot=1000, flags=_cabi.FLAG_NO_AUTOTUNE)
+    info = solver.info()
+    solver.close()
+    assert np.array_equal(x, xo) and info["autotuned"] == 0 and info["primal_variant"] == 1

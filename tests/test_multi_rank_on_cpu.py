@@ -11,7 +11,7 @@ from oracle import partition_oracle as po
 from pysparselp_b200 import _cabi
 from pysparselp_b200.ChambollePockPPD import one_sided_rows, run_schedule, stack_operator
 
-TRANSPORTS = {"fused_in_kernels": 0, "push_wait_kernels": _cabi.FLAG_NO_FUSED_HALO, "nccl": _cabi.FLAG_NO_P2P}
+TRANSPORTS = {"push_wait_kernels": 0, "fused_in_kernels": _cabi.FLAG_FUSED_HALO, "nccl": _cabi.FLAG_NO_P2P}
 
 
 def solve_on_ranks(args, world, flags, nb_max_iter, nb_iter_plot, force_integer=False, **kw):
@@ -94,3 +94,49 @@ def test_multi_rank_device_curves():
         assert np.allclose(seen[:, 0], seen[:, 1], rtol=1e-13, atol=1e-16)
         assert np.allclose(seen[:, 2], seen[:, 3], rtol=1e-13, atol=1e-16)
         assert np.array_equal(seen[:, 4], seen[:, 5])
+
+
+@pytest.mark.timeout(900)
+def test_multi_rank_autotune_and_forced_variants(monkeypatch):
+    """Kernel variants are timed before the peer-memory rendezvous; ranks may end up with different variants and
+    still produce the same bits."""
+    monkeypatch.setenv("CPPPD_AUTOTUNE_MIN_NNZ", "0")
+    args, g = case_args("potts50")
+    for r in solve_on_ranks(args, 2, 0, 100, 10):
+        assert r["info"]["autotuned"] == 1
+        assert np.array_equal(r["x"], g["x_100"])
+    for r in solve_on_ranks(args, 3, 0, 100, 10, kernel_variant=4):
+        assert r["info"]["autotuned"] == 0 and r["info"]["dual_variant"] == 4
+        assert np.array_equal(r["x"], g["x_100"])
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("transport", ["push_wait_kernels", "fused_in_kernels"])
+def test_halo_wait_gives_up_instead_of_hanging(transport, monkeypatch):
+    """A neighbour that never delivers its halo must surface as CPPPD_ERR_COMM after CPPPD_HALO_TIMEOUT_S, not hang
+    the device."""
+    import time
+
+    monkeypatch.setenv("CPPPD_HALO_TIMEOUT_S", "0.5")
+    args, _ = case_args("potts50")
+
+    def body(rank, world, comm_id):
+        solver = make_emulated_solver(*args, flags=TRANSPORTS[transport], partition_granule=32, rank=rank, world=world,
+                                      comm_id=comm_id)
+        if rank == 1:  # this rank never iterates
+            time.sleep(3.0)
+            solver.handle = None  # (its destroy would wait for rank 0, which has given up)
+            return "idle"
+        t0 = time.time()
+        try:
+            solver.iterate(3)
+            solver.sync()
+        except _cabi.CpppdError as e:
+            assert e.code == -5 and "timed out" in str(e)
+            return time.time() - t0
+        finally:
+            solver.close()
+        return None
+
+    res = run_ranks(2, body)
+    assert res[1] == "idle" and res[0] is not None and res[0] < 30.0
