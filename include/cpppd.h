@@ -124,6 +124,10 @@ typedef struct {
   int64_t partition_granule; /* locality bucket width in columns; <= 0: default */
   void *comm;           /* optional cpppd_comm created by cpppd_comm_create(): reused (and not destroyed) by
                            this solver instead of building a new communicator from comm_id */
+  int64_t long_row_threshold; /* rows of A / columns of A with more entries than this are summed by a CTA per
+                           4096-entry segment instead of by one thread (skewed patterns: L1-SVM weight columns, dense
+                           budget rows).  0: default (2048); < 0: never.  LPs with such rows agree with the reference
+                           to rounding (fixed summation tree) instead of bit for bit; others are unaffected. */
 } cpppd_problem;
 
 /* The numbers the reference's stats block produces (ChambollePockPPD.py:242-291). */
@@ -170,6 +174,8 @@ typedef struct {
   int32_t autotuned;         /* 1 when the variants were timed at creation */
   /* milliseconds per launch measured at creation for k_primal ([0][v-1]) and k_dual ([1][v-1]); 0 = not timed */
   float variant_ms[2][CPPPD_KERNEL_VARIANTS];
+  int64_t long_rows, long_cols; /* rows / columns handled by the long-row path on this rank */
+  int64_t long_entries;         /* their entries */
 } cpppd_info;
 
 typedef enum {

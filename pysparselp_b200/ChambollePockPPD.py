@@ -13,10 +13,12 @@ Extra keyword-only arguments (defaults keep the reference behaviour):
 ``device`` (CUDA ordinal or torch.device), ``verbose`` (print the reference's per-block
 line), ``flags`` (CPPPD_FLAG_* bit mask), ``return_solver`` (also return the live
 ``CpPpdSolver`` for inspection), ``kernel_variant`` (0: pick the fastest variant of the two hot kernels
-automatically; see ``cpppd_problem.kernel_variant`` — the iterates do not depend on it), ``distributed`` (None: use the initialised torch.distributed
+automatically; see ``cpppd_problem.kernel_variant`` — the iterates do not depend on it), ``long_row_threshold`` (rows / columns with more entries are summed by
+many threads, see ``cpppd_problem.long_row_threshold``), ``distributed`` (None: use the initialised torch.distributed
 world when it has more than one rank — one process per GPU, every rank passes the same LP and
 gets the same result; False: this GPU only; or an explicit ProcessGroup).
 """
+import atexit
 import ctypes as C
 import time
 
@@ -27,6 +29,19 @@ from . import _cabi
 
 # (process group, device) -> cpppd_comm, kept for the life of the process
 _COMM_CACHE = {}
+
+
+def _destroy_cached_comms():
+    lib = _cabi._lib
+    while _COMM_CACHE and lib is not None:
+        _, comm = _COMM_CACHE.popitem()
+        try:
+            lib.cpppd_comm_destroy(comm)
+        except Exception:
+            pass
+
+
+atexit.register(_destroy_cached_comms)
 
 
 def _as_f64(v, size, name):
@@ -86,7 +101,8 @@ class _TorchBuffers:
         self.live.pop(ptr, None)
 
 
-def prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant=0):
+def prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant=0,
+                    long_row_threshold=0):
     """``cpppd_problem`` with the host-side fields filled from numpy / scipy operands.
 
     Returns ``(problem, keepalive)``; the arrays in ``keepalive`` must outlive ``cpppd_create``.
@@ -120,6 +136,7 @@ def prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_gr
     p.one_plus_theta = float(1 + theta)
     p.flags = int(flags)
     p.kernel_variant = int(kernel_variant)
+    p.long_row_threshold = int(long_row_threshold)
     p.partition_granule = int(partition_granule)
     p.rank, p.world_size = 0, 1
     return p, (c, lb, ub, b, x0, data, indices, indptr)
@@ -259,7 +276,7 @@ class CpPpdSolver(SolverHandle):
     """Live solver state on one GPU: the only way the product creates a ``cpppd_handle``."""
 
     def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
-                 process_group=None, partition_granule=0, kernel_variant=0):
+                 process_group=None, partition_granule=0, kernel_variant=0, long_row_threshold=0):
         import torch
 
         self.lib = _cabi.load_library()
@@ -275,7 +292,8 @@ class CpPpdSolver(SolverHandle):
         comm = None
         if process_group is not None:
             comm = self._shared_comm(process_group, dev)
-        p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant)
+        p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant,
+                                  long_row_threshold)
         self.n, self.m, self.m_eq = int(p.n), int(p.m_eq + p.m_ineq), int(p.m_eq)
         self._buffers = _TorchBuffers(dev)
         p.device = dev.index
@@ -372,7 +390,7 @@ def stack_operator(a_eq, beq, a_ineq, b_ineq, n):
 
 
 def make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0,
-                distributed=None, partition_granule=0, kernel_variant=0):
+                distributed=None, partition_granule=0, kernel_variant=0, long_row_threshold=0):
     """Upload an LP given with the arguments of ``chambolle_pock_ppd`` and return the live solver.
 
     Returns None when the LP has no constraint row at all (closed-form case, ``:147-151``).
@@ -390,7 +408,7 @@ def make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1
         return None
     return CpPpdSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, device=device, flags=flags,
                        process_group=_resolve_group(distributed), partition_granule=partition_granule,
-                       kernel_variant=kernel_variant)
+                       kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
 
 
 def _resolve_group(distributed):
@@ -480,6 +498,7 @@ def chambolle_pock_ppd(
     distributed=None,
     partition_granule=0,
     kernel_variant=0,
+    long_row_threshold=0,
 ):
     """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
 
@@ -512,7 +531,7 @@ def chambolle_pock_ppd(
                          "lb": lb, "ub": ub}, f)
     solver = make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
                          device=device, flags=flags, distributed=distributed, partition_granule=partition_granule,
-                         kernel_variant=kernel_variant)
+                         kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
     if solver is None:  # no constraint row: closed form, bare vector (:147-151)
         x = np.zeros_like(lb)
         x[c > 0] = lb[c > 0]

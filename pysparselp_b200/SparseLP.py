@@ -461,7 +461,8 @@ class SparseLP:
             # of the reference (:1074-1091) is evaluated on the device inside the stats block and x never
             # leaves the GPU before the end.  Values equal the host path up to the summation order of the
             # two distance means.
-            solve_kw = {k: solver_options[k] for k in ("device", "flags", "distributed", "partition_granule", "kernel_variant")
+            solve_kw = {k: solver_options[k] for k in ("device", "flags", "distributed", "partition_granule", "kernel_variant",
+                                                          "long_row_threshold")
                         if k in solver_options}
             solver = make_solver(*solver_args, x0=None, alpha=1, theta=1, **solve_kw)
             best_integer_solution = None

@@ -40,7 +40,7 @@ class Problem(C.Structure):
         ("stream", C.c_void_p), ("flags", C.c_uint32), ("kernel_variant", C.c_int32),
         ("alloc", ALLOC_FN), ("free", FREE_FN), ("alloc_user", C.c_void_p),
         ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.c_void_p),
-        ("partition_granule", C.c_int64), ("comm", C.c_void_p),
+        ("partition_granule", C.c_int64), ("comm", C.c_void_p), ("long_row_threshold", C.c_int64),
     ]
 
 
@@ -72,6 +72,7 @@ class Info(C.Structure):
         ("nnz_local_rows", C.c_int64), ("nnz_local_cols", C.c_int64),
         ("halo_send_bytes_per_iteration", C.c_int64), ("partition_granule", C.c_int64),
         ("dual_variant", C.c_int32), ("autotuned", C.c_int32), ("variant_ms", (C.c_float * KERNEL_VARIANTS) * 2),
+        ("long_rows", C.c_int64), ("long_cols", C.c_int64), ("long_entries", C.c_int64),
     ]
 
     def as_dict(self):

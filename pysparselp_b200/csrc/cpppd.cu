@@ -30,7 +30,6 @@
 // bit-identical to the reference.  Only the scalar dot products of the stats block use a
 // different (tree) order than numpy.dot.
 #include "cpppd_types.cuh"
-#include "cpppd_device.cuh"
 #include "cpppd_setup_kernels.cuh"
 #include "cpppd_hot_kernels.cuh"
 #include "cpppd_stats_kernels.cuh"
@@ -164,6 +163,7 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   h->flags = P->flags;
   h->granule = P->partition_granule;
   h->variant_request = P->kernel_variant;
+  h->long_threshold = P->long_row_threshold == 0 ? kLongDefault : P->long_row_threshold;
   h->rank = P->rank;
   h->world = world;
   h->alloc = P->alloc;
@@ -264,7 +264,7 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
   double *xr = h->x;
   if (force_integer) {
     if (!h->xr_scratch)
-      if (int rc = alloc_array(h, &h->xr_scratch, h->n + h->hx.ghost)) return rc;
+      if (int rc = alloc_array(h, &h->xr_scratch, h->x_len)) return rc;
     xr = h->xr_scratch;
   }
   k_stats_cols<<<h->stat_blocks_c, kBlock, 0, h->stream>>>(h->vc, h->x, h->xbar, h->vlb, h->vub, h->dbuf, xr, h->n,
@@ -274,6 +274,12 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
   if (int rc = exchange(h, h->dbuf, h->hx)) return rc;
   if (force_integer)
     if (int rc = exchange(h, xr, h->hx)) return rc;
+  // long rows of A: their sums against x, x4, xbar (and xr) go to the tails the row pass gathers from
+  if (int rc = long_pass(h, h->longA, h->x, h->x)) return rc;
+  if (int rc = long_pass(h, h->longA, h->dbuf, h->dbuf)) return rc;
+  if (int rc = long_pass(h, h->longA, h->xbar, h->xbar)) return rc;
+  if (force_integer)
+    if (int rc = long_pass(h, h->longA, xr, xr)) return rc;
   k_stats_rows<<<h->stat_blocks_r, kBlock, 0, h->stream>>>(view(h->A), h->x, h->dbuf, h->xbar, xr, h->vb, h->y, h->m,
                                                           h->m_eq, force_integer, h->rowpart);
   if (h->gt_local)
@@ -469,6 +475,10 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   const int64_t per_elem[6] = {h->m, h->m, h->n, h->n, h->n, h->n};
   for (int bit = 0; bit < 6; ++bit)
     if (!((h->const_mask >> bit) & 1)) vec_bytes += 8 * per_elem[bit];
+  out->long_rows = h->longA.count;
+  out->long_cols = h->longAT.count;
+  out->long_entries = h->longA.nnz + h->longAT.nnz;
+  vec_bytes += 12 * (h->longA.nnz + h->longAT.nnz) + 8 * (h->longA.nnz + h->longAT.nnz);  // entries + their gathers
   out->bytes_per_iteration_actual = (h->A.padded + h->AT.padded) * entry_bytes +
                                     (h->A.uniform_width >= 0 ? 0 : 8 * (h->A.nslices + 1)) +
                                     (h->AT.uniform_width >= 0 ? 0 : 8 * (h->AT.nslices + 1)) + vec_bytes;

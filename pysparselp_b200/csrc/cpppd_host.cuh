@@ -98,6 +98,103 @@ int read_i32(cpppd_solver *h, const int32_t *dev, int32_t *host, int64_t count) 
   return 0;
 }
 
+// Cut the rows longer than h->long_threshold out of a CSR (device arrays, int64 row pointers): see
+// cpppd_long_rows.cuh.  When there are none, *new_rowptr stays nullptr and nothing is allocated; otherwise
+// the three new_* arrays (scratch) describe the CSR to hand to build_sell and L owns the long rows.
+int split_long_rows(cpppd_solver *h, Scratch &tmp, const int64_t *rowptr, const int32_t *indices, const double *values,
+                    int64_t nrows, int virt, int64_t tail_base, LongRows *L, int64_t **new_rowptr, int32_t **new_idx,
+                    double **new_val) {
+  *new_rowptr = nullptr;
+  *new_idx = nullptr;
+  *new_val = nullptr;
+  L->virt = virt;
+  L->tail_base = tail_base;
+  if (h->long_threshold < 0 || nrows == 0) return 0;
+  cudaStream_t st = h->stream;
+  int32_t *flag = nullptr, *slot = nullptr;
+  if (int rc = tmp.get(&flag, nrows + 1)) return rc;
+  if (int rc = tmp.get(&slot, nrows + 1)) return rc;
+  k_long_flag<<<grid_for(nrows + 1), kBlock, 0, st>>>(rowptr, nrows, h->long_threshold, flag);
+  if (int rc = exclusive_scan(h, flag, slot, nrows + 1)) return rc;
+  int32_t count = 0;
+  if (int rc = read_i32(h, slot + nrows, &count, 1)) return rc;
+  if (count == 0) {
+    tmp.release(flag);
+    tmp.release(slot);
+    return 0;
+  }
+  // the long rows themselves: ids and lengths to the host (few), offsets and segments back
+  L->count = count;
+  int64_t *len_dev = nullptr;
+  if (int rc = alloc_array(h, &L->row, count)) return rc;
+  if (int rc = tmp.get(&len_dev, count)) return rc;
+  k_long_list<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, flag, slot, nrows, L->row, len_dev);
+  std::vector<int64_t> len(count), ptr(count + 1, 0), seg_ptr(count + 1, 0);
+  CK(cudaMemcpyAsync(len.data(), len_dev, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int32_t r = 0; r < count; ++r) {
+    ptr[r + 1] = ptr[r] + len[r];
+    seg_ptr[r + 1] = seg_ptr[r] + (len[r] + kLongSeg - 1) / kLongSeg;
+  }
+  L->nnz = ptr[count];
+  L->nseg = seg_ptr[count];
+  if (L->nseg >= (int64_t)INT32_MAX) return fail(h, CPPPD_ERR_INVALID, "too many long-row segments");
+  std::vector<int32_t> seg_row(L->nseg);
+  for (int32_t r = 0; r < count; ++r)
+    for (int64_t q = seg_ptr[r]; q < seg_ptr[r + 1]; ++q) seg_row[q] = r;
+  if (int rc = alloc_array(h, &L->ptr, count + 1)) return rc;
+  if (int rc = alloc_array(h, &L->seg_ptr, count + 1)) return rc;
+  if (int rc = alloc_array(h, &L->seg_row, L->nseg)) return rc;
+  if (int rc = alloc_array(h, &L->idx, L->nnz)) return rc;
+  if (int rc = alloc_array(h, &L->val, L->nnz)) return rc;
+  if (int rc = alloc_array(h, &L->partial, 2 * L->nseg)) return rc;
+  CK(cudaMemcpyAsync(L->ptr, ptr.data(), sizeof(int64_t) * (count + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(L->seg_ptr, seg_ptr.data(), sizeof(int64_t) * (count + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(L->seg_row, seg_row.data(), sizeof(int32_t) * L->nseg, cudaMemcpyHostToDevice, st));
+  k_long_copy<<<count, kBlock, 0, st>>>(rowptr, indices, values, L->row, L->ptr, L->idx, L->val);
+  // the CSR that goes into SELL: short rows as they are, long rows reduced to their virtual entries
+  int64_t *newlen = nullptr;
+  if (int rc = tmp.get(&newlen, nrows + 1)) return rc;
+  if (int rc = tmp.get(new_rowptr, nrows + 1)) return rc;
+  k_long_newlen<<<grid_for(nrows + 1), kBlock, 0, st>>>(rowptr, flag, nrows, virt, newlen);
+  if (int rc = exclusive_scan(h, newlen, *new_rowptr, nrows + 1)) return rc;
+  int64_t new_nnz = 0;
+  CK(cudaMemcpyAsync(&new_nnz, *new_rowptr + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (int rc = tmp.get(new_idx, new_nnz)) return rc;
+  if (int rc = tmp.get(new_val, new_nnz)) return rc;
+  k_long_rewrite<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, values, flag, slot, *new_rowptr, nrows, virt, tail_base,
+                                                     *new_idx, *new_val);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  tmp.release(flag);
+  tmp.release(slot);
+  tmp.release(len_dev);
+  tmp.release(newlen);
+  return 0;
+}
+
+// sums of the long rows of L against `vec`, stored behind the ghosts of `out_vec` (its tail)
+int long_pass(cpppd_solver *h, const LongRows &L, const double *vec, double *out_vec) {
+  if (L.count == 0) return 0;
+  k_long_partial<<<(int)L.nseg, kBlock, 0, h->stream>>>(L.ptr, L.seg_ptr, L.seg_row, L.idx, L.val, vec, 0.0, L.partial);
+  k_long_finish<<<grid_for(L.count * 32), kBlock, 0, h->stream>>>(L.seg_ptr, L.row, L.count, L.partial,
+                                                                 L.virt == 2 ? kLongSumsAT : kLongSumsA, 1, 1,
+                                                                 out_vec + L.tail_base);
+  return 0;
+}
+
+// preconditioner entries of the long rows (the SELL pass saw only their virtual entries)
+int long_precond(cpppd_solver *h, const LongRows &L, double power, double *out) {
+  if (L.count == 0) return 0;
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  k_long_partial<<<(int)L.nseg, kBlock, 0, h->stream>>>(L.ptr, L.seg_ptr, L.seg_row, L.idx, L.val, nullptr, power, L.partial);
+  k_long_finish<<<grid_for(L.count * 32), kBlock, 0, h->stream>>>(L.seg_ptr, L.row, L.count, L.partial,
+                                                                 L.virt == 2 ? kLongPrecondT : kLongPrecondSigma, has_eq,
+                                                                 has_ineq, out);
+  return 0;
+}
+
 int64_t default_granule(int64_t n) {
   int64_t g = 32;
   while (g < (n >> 14)) g *= 2;
@@ -147,10 +244,24 @@ int detect_dictionary(cpppd_solver *h, Scratch &tmp, const double *values, int64
   int num_h = 0;
   CK(cudaMemcpyAsync(&num_h, num, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  std::vector<unsigned long long> words;
+  if (num_h >= 1 && num_h <= 256) {
+    words.resize(num_h);
+    CK(cudaMemcpyAsync(words.data(), uniq, sizeof(unsigned long long) * num_h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->long_threshold >= 0) {  // the virtual entries of long rows (cpppd_long_rows.cuh) carry the value 1.0
+      const double one = 1.0;
+      unsigned long long one_bits;
+      memcpy(&one_bits, &one, sizeof one_bits);
+      auto pos = std::lower_bound(words.begin(), words.end(), one_bits);
+      if (pos == words.end() || *pos != one_bits) words.insert(pos, one_bits);
+      num_h = (int)words.size();
+    }
+  }
   if (num_h >= 1 && num_h <= 256) {
     if (int rc = alloc_array(h, &h->dict, 256)) return rc;
     CK(cudaMemsetAsync(h->dict, 0, sizeof(unsigned long long) * 256, st));
-    CK(cudaMemcpyAsync(h->dict, uniq, sizeof(unsigned long long) * num_h, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(h->dict, words.data(), sizeof(unsigned long long) * num_h, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
     k_dict_check<<<std::min(grid_for(nnz), h->sm_count * 16), kBlock, 0, st>>>(values, nnz, h->dict, num_h, flag);
     int miss = 0;
@@ -269,7 +380,8 @@ int setup_p2p(cpppd_solver *h) {
       CK(cudaMemcpy(pp.push_dst[kind], dst.data(), sizeof(int64_t) * H.send_total, cudaMemcpyHostToDevice));
     }
   }
-  if (h->flags & CPPPD_FLAG_FUSED_HALO)
+  // (the fused kernels wait for the halo themselves; the long-row pre-passes would read the ghosts too early)
+  if ((h->flags & CPPPD_FLAG_FUSED_HALO) && h->longA.count == 0 && h->longAT.count == 0)
     if (int rc = setup_fused(h, dst_base[0], dst_base[1])) return rc;
   // nobody may push before every rank has initialised its vectors and flags
   NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
@@ -581,7 +693,11 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   h->hy.ghost = m_ghost;
 
   if (h->dict) {  // an entry word must hold index + code below the eq / pad bits
-    const int idx_bits = bits_for((uint64_t)std::max<int64_t>(std::max(nloc + n_ghost, mloc + m_ghost), 2) - 1);
+    // gather indices reach behind the ghosts when long rows exist: at most nnz / threshold of them, with one
+    // (A) or two (A^T) tail slots each
+    const int64_t max_long = h->long_threshold < 0 ? 0 : nnz / std::max<int64_t>(h->long_threshold, 1) + 1;
+    const int idx_bits = bits_for((uint64_t)std::max<int64_t>(
+        std::max(nloc + n_ghost + max_long, mloc + m_ghost + 2 * max_long), 2) - 1);
     const int code_bits = bits_for((uint64_t)std::max(h->ndict, 2) - 1);
     if (idx_bits + code_bits <= 30) {
       for (Sell *S : {&h->A, &h->AT}) {
@@ -595,9 +711,19 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     }
   }
   // ---- this rank's rows of A -> SELL-32
+  int64_t *s_rowptr = nullptr;  // CSR without the long rows (see split_long_rows), when there are any
+  int32_t *s_idx = nullptr;
+  double *s_val = nullptr;
   if (!reorder) {
     h->nnz_rows = nnz;
-    if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
+    if (int rc = split_long_rows(h, tmp, rowptr, indices, values, m, 1, nloc + n_ghost, &h->longA, &s_rowptr, &s_idx, &s_val))
+      return rc;
+    if (s_rowptr) {
+      if (int rc = build_sell(h, s_rowptr, s_idx, s_val, m, &h->A)) return rc;
+      tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
+    } else {
+      if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
+    }
   } else {
     int64_t *len = nullptr, *lrowptr = nullptr;
     if (int rc = tmp.get(&len, mloc + 1)) return rc;
@@ -614,7 +740,14 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = tmp.get(&lval, lnnz)) return rc;
     if (mloc) k_local_rows_fill<<<grid_for(mloc), kBlock, 0, st>>>(row_order, rs, mloc, rowptr, indices, values, col_pos,
                                                                   cs, ce, gcol_scan, lrowptr, lidx, lval);
-    if (int rc = build_sell(h, lrowptr, lidx, lval, mloc, &h->A)) return rc;
+    if (int rc = split_long_rows(h, tmp, lrowptr, lidx, lval, mloc, 1, nloc + n_ghost, &h->longA, &s_rowptr, &s_idx, &s_val))
+      return rc;
+    if (s_rowptr) {
+      if (int rc = build_sell(h, s_rowptr, s_idx, s_val, mloc, &h->A)) return rc;
+      tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
+    } else {
+      if (int rc = build_sell(h, lrowptr, lidx, lval, mloc, &h->A)) return rc;
+    }
     tmp.release(len); tmp.release(lrowptr); tmp.release(lidx); tmp.release(lval);
   }
   // ---- this rank's columns of A as rows of A^T.  A stable radix sort of the entries (taken in CSR
@@ -660,45 +793,56 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     CK(cudaStreamSynchronize(st));
     tmp.release(keys_a); tmp.release(keys_b); tmp.release(ids_b); tmp.release(entry_id); tmp.release(row_of);
     tmp.release(indices); tmp.release(values); tmp.release(rowptr);
-    if (int rc = build_sell(h, lcolptr, t_idx, t_val, nloc, &h->AT)) return rc;
+    if (int rc = split_long_rows(h, tmp, lcolptr, t_idx, t_val, nloc, 2, mloc + m_ghost, &h->longAT, &s_rowptr, &s_idx, &s_val))
+      return rc;
+    if (s_rowptr) {
+      if (int rc = build_sell(h, s_rowptr, s_idx, s_val, nloc, &h->AT)) return rc;
+      tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
+    } else {
+      if (int rc = build_sell(h, lcolptr, t_idx, t_val, nloc, &h->AT)) return rc;
+    }
     tmp.release(lcolptr); tmp.release(t_idx); tmp.release(t_val);
   }
   // ---- vectors in local layout
   for (double **v : {&h->c, &h->T, &h->lb, &h->ub, &h->best})
     if (int rc = alloc_array(h, v, nloc)) return rc;
   const bool want_p2p = N > 1 && !(h->flags & CPPPD_FLAG_NO_P2P);
+  // layout of a gathered vector: [owned | ghosts | sums of the long rows that gather from it]
+  const int64_t x_len = nloc + n_ghost + h->longA.count, y_len = mloc + m_ghost + 2 * h->longAT.count;
+  h->x_len = x_len;
+  h->y_len = y_len;
   for (double **v : {&h->x, &h->dbuf})
-    if (int rc = alloc_array(h, v, nloc + n_ghost)) return rc;
+    if (int rc = alloc_array(h, v, x_len)) return rc;
   for (double **v : {&h->b, &h->sigma})
     if (int rc = alloc_array(h, v, mloc)) return rc;
   if (want_p2p) {  // the two vectors with peer-written ghost tails: plain cudaMalloc, exportable by IPC
-    CK(cudaMalloc(&h->xbar, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1)));
+    CK(cudaMalloc(&h->xbar, sizeof(double) * std::max<int64_t>(x_len, 1)));
     h->p2p.own.push_back(h->xbar);
-    CK(cudaMalloc(&h->y, sizeof(double) * std::max<int64_t>(mloc + m_ghost, 1)));
+    CK(cudaMalloc(&h->y, sizeof(double) * std::max<int64_t>(y_len, 1)));
     h->p2p.own.push_back(h->y);
-    h->device_bytes += 8 * (nloc + n_ghost + mloc + m_ghost);
+    h->device_bytes += 8 * (x_len + y_len);
   } else {
-    if (int rc = alloc_array(h, &h->xbar, nloc + n_ghost)) return rc;
-    if (int rc = alloc_array(h, &h->y, mloc + m_ghost)) return rc;
+    if (int rc = alloc_array(h, &h->xbar, x_len)) return rc;
+    if (int rc = alloc_array(h, &h->y, y_len)) return rc;
   }
   if (int rc = upload_local(h, tmp, P->c, n, h->col_old, nloc, h->c)) return rc;
   if (int rc = upload_local(h, tmp, P->lb, n, h->col_old, nloc, h->lb)) return rc;
   if (int rc = upload_local(h, tmp, P->ub, n, h->col_old, nloc, h->ub)) return rc;
   if (int rc = upload_local(h, tmp, P->b, m, h->row_old, mloc, h->b)) return rc;
-  if (P->x0) {
+  CK(cudaMemsetAsync(h->x, 0, sizeof(double) * std::max<int64_t>(x_len, 1), st));
+  if (P->x0)
     if (int rc = upload_local(h, tmp, P->x0, n, h->col_old, nloc + n_ghost, h->x)) return rc;
-  } else {
-    CK(cudaMemsetAsync(h->x, 0, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1), st));
-  }
-  CK(cudaMemcpyAsync(h->xbar, h->x, sizeof(double) * (nloc + n_ghost), cudaMemcpyDeviceToDevice, st));  // x3 = x (:190)
-  CK(cudaMemsetAsync(h->dbuf, 0, sizeof(double) * std::max<int64_t>(nloc + n_ghost, 1), st));
-  CK(cudaMemsetAsync(h->y, 0, sizeof(double) * std::max<int64_t>(mloc + m_ghost, 1), st));              // :166,:177
+  CK(cudaMemcpyAsync(h->xbar, h->x, sizeof(double) * x_len, cudaMemcpyDeviceToDevice, st));  // x3 = x (:190)
+  CK(cudaMemsetAsync(h->dbuf, 0, sizeof(double) * std::max<int64_t>(x_len, 1), st));
+  CK(cudaMemsetAsync(h->y, 0, sizeof(double) * std::max<int64_t>(y_len, 1), st));           // :166,:177
   // ---- preconditioners (:122-179): complete columns / rows are local, so no exchange is needed
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
   if (h->AT.nslices)
     k_precond_cols<<<grid_for(h->AT.nslices * 32), kBlock, 0, st>>>(view(h->AT), nloc, has_eq, has_ineq, 2.0 - h->alpha, h->T);
   if (h->A.nslices)
     k_precond_rows<<<grid_for(h->A.nslices * 32), kBlock, 0, st>>>(view(h->A), mloc, h->alpha, h->sigma);
+  if (int rc = long_precond(h, h->longAT, 2.0 - h->alpha, h->T)) return rc;
+  if (int rc = long_precond(h, h->longA, h->alpha, h->sigma)) return rc;
   h->vc = Vec{h->c, 0};
   h->vT = Vec{h->T, 0};
   h->vlb = Vec{h->lb, 0};
@@ -764,6 +908,7 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
 int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
   P2P &pp = h->p2p;
   const FusedComm *cm = pp.use_fused ? pp.fused[0] : nullptr;
+  if (int rc = long_pass(h, h->longAT, h->y, h->y)) return rc;  // long columns: their A^T y into the tail of y
   if (h->AT.nslices) {
     const bool dict = h->AT.dict != nullptr;
     const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
@@ -778,6 +923,7 @@ int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
 int launch_dual(cpppd_solver *h, int variant = -1) {
   P2P &pp = h->p2p;
   const FusedComm *cm = pp.use_fused ? pp.fused[1] : nullptr;
+  if (int rc = long_pass(h, h->longA, h->xbar, h->xbar)) return rc;  // long rows: their A xbar into the tail of xbar
   if (h->A.nslices) {
     const bool dict = h->A.dict != nullptr;
     DualFn fn = cm ? dual_kernel_fused(dict) : dual_kernel(dict, variant >= 0 ? variant : h->dual_variant);
@@ -809,7 +955,7 @@ int tune_kernels(cpppd_solver *h) {
   if ((h->flags & CPPPD_FLAG_NO_AUTOTUNE) || std::max(h->nnz_rows, h->nnz_cols) < min_nnz) return 0;
   cudaStream_t st = h->stream;
   Scratch tmp(h);
-  const int64_t nx = h->n + h->hx.ghost, ny = h->m + h->hy.ghost;
+  const int64_t nx = h->x_len, ny = h->y_len;
   double *x_saved = nullptr;
   if (int rc = tmp.get(&x_saved, nx)) return rc;
   CK(cudaMemcpyAsync(x_saved, h->x, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));

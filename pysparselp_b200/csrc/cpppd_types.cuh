@@ -23,6 +23,8 @@
 #include <vector>
 
 #include "cpppd_device_types.cuh"
+#include "cpppd_device.cuh"
+#include "cpppd_long_rows.cuh"
 
 namespace {
 
@@ -149,6 +151,9 @@ struct cpppd_solver {
   std::vector<void *> owned;
   int64_t device_bytes = 0;
   Sell A, AT;
+  LongRows longA, longAT;        // rows of A / columns of A cut out of the SELL operands (cpppd_long_rows.cuh)
+  int64_t long_threshold = 0;    // rows with more entries are long; < 0: never
+  int64_t x_len = 0, y_len = 0;  // allocated length of x-like / y-like vectors (owned + ghosts + long-row tails)
   double *c = nullptr, *T = nullptr, *lb = nullptr, *ub = nullptr, *x = nullptr, *xbar = nullptr;
   double *b = nullptr, *sigma = nullptr, *y = nullptr, *dbuf = nullptr, *best = nullptr;
   Vec vc{nullptr, 0}, vT{nullptr, 0}, vlb{nullptr, 0}, vub{nullptr, 0}, vb{nullptr, 0}, vsigma{nullptr, 0};

@@ -34,9 +34,10 @@ def emulated_library():
 
 class EmulatedSolver(SolverHandle):
     def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, flags=0, partition_granule=0,
-                 rank=0, world=1, comm_id=None, kernel_variant=0):
+                 rank=0, world=1, comm_id=None, kernel_variant=0, long_row_threshold=0):
         self.lib = emulated_library()
-        p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant)
+        p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant,
+                                  long_row_threshold)
         self.n, self.m, self.m_eq = int(p.n), int(p.m_eq + p.m_ineq), int(p.m_eq)
         p.device = 0
         p.stream = None
@@ -51,23 +52,25 @@ class EmulatedSolver(SolverHandle):
 
 
 def make_emulated_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, flags=0,
-                         partition_granule=0, rank=0, world=1, comm_id=None, kernel_variant=0):
+                         partition_granule=0, rank=0, world=1, comm_id=None, kernel_variant=0, long_row_threshold=0):
     if a_eq is not None and a_eq.shape[0] == 0:
         a_eq, beq = None, None
     a_ineq, b_ineq = one_sided_rows(a_ineq, b_lower, b_upper)
     a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, np.size(c))
     return EmulatedSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, flags=flags,
                           partition_granule=partition_granule, rank=rank, world=world, comm_id=comm_id,
-                          kernel_variant=kernel_variant)
+                          kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
 
 
 def emulated_chambolle_pock_ppd(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1,
                                 nb_max_iter=100, callback_func=None, max_time=None, force_integer=False,
-                                nb_iter_plot=10, flags=0, partition_granule=0, kernel_variant=0):
+                                nb_iter_plot=10, flags=0, partition_granule=0, kernel_variant=0,
+                                long_row_threshold=0):
     """(x, best_integer, solver) — the product schedule over the emulated library."""
     start = time.perf_counter()
     solver = make_emulated_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
-                                  flags=flags, partition_granule=partition_granule, kernel_variant=kernel_variant)
+                                  flags=flags, partition_granule=partition_granule, kernel_variant=kernel_variant,
+                                  long_row_threshold=long_row_threshold)
     x, best = run_schedule(solver, nb_max_iter, callback_func, max_time, force_integer, nb_iter_plot, False, start)
     return x, best, solver
 

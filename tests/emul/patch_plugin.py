@@ -14,9 +14,10 @@ from .cabi_driver import EmulatedSolver
 
 class _Adapter(EmulatedSolver):
     def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, device=None, flags=0, process_group=None,
-                 partition_granule=0, kernel_variant=0):
+                 partition_granule=0, kernel_variant=0, long_row_threshold=0):
         super().__init__(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, flags=flags,
-                         partition_granule=partition_granule, kernel_variant=kernel_variant)
+                         partition_granule=partition_granule, kernel_variant=kernel_variant,
+                         long_row_threshold=long_row_threshold)
 
 
 def pytest_configure(config):

@@ -191,7 +191,7 @@ def test_solve_curves_on_device_equal_host_curves(case, monkeypatch):
     curves = {}
     for device_curves in (True, False):
         lp, gt, gti, golden = build()
-        x, _ = lp.solve(method="chambolle_pock_ppd", nb_iter=1501, nb_iter_plot=500, ground_truth=gt,
+        x, _ = lp.solve(method="chambolle_pock_ppd", nb_iter=1001, nb_iter_plot=500, ground_truth=gt,
                         ground_truth_indices=gti, device_curves=device_curves)
         curves[device_curves] = (x, {k: np.array(getattr(lp, k), dtype=float) for k in (
             "distance_to_ground_truth", "distanceToGroundTruthAfterRounding", "pobj_curve", "dobj_curve",
@@ -211,7 +211,7 @@ def test_solve_curves_on_device_equal_host_curves(case, monkeypatch):
 def test_emulated_every_kernel_variant_gives_the_same_bits(kernel_variant, flags):
     """cpppd_problem.kernel_variant forces one of the compiled variants of k_primal / k_dual; the arithmetic of
     a row / column sum is the same sequential chain in all of them."""
-    for name in ("potts50", "random_small"):
+    for name in ("sc105", "random_small"):  # (tests/test_kernels_on_cpu.py runs every variant on every golden case)
         args, g = case_args(name)
         trace = []
         x, best, solver = emulated_chambolle_pock_ppd(
@@ -255,3 +255,77 @@ def test_emulated_autotune_leaves_the_initial_state_untouched(monkeypatch):
     info = solver.info()
     solver.close()
     assert np.array_equal(x, xo) and info["autotuned"] == 0 and info["primal_variant"] == 1
+
+
+# thresholds that make a handful of rows / columns long (the emulator runs one CTA of fibers per segment: slow)
+LONG_THRESHOLD = {"l1svm": 64, "sc105": 3, "random_small": 13}
+
+
+@pytest.mark.parametrize("variant", ["plain", "all"])
+@pytest.mark.parametrize("name", list(LONG_THRESHOLD))
+def test_emulated_long_rows_agree_to_rounding(name, variant):
+    """Rows / columns above cpppd_problem.long_row_threshold leave the thread-per-row kernels and are summed by a
+    CTA per segment (fixed tree): iterates within BASELINE.json's 1e-9, curves within 1e-6, masks exact."""
+    args, g = case_args(name)
+    trace = []
+    x, best, solver = emulated_chambolle_pock_ppd(
+        *args, nb_max_iter=100, nb_iter_plot=10, flags=FLAG_SETS[variant], partition_granule=32,
+        long_row_threshold=LONG_THRESHOLD[name], callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)))
+    try:
+        info = solver.info()
+        y = solver.get_y()
+        T, sigma = solver.get_preconditioners()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        s_gold = np.concatenate([g[k] for k in ("diag_sigma_eq", "diag_sigma_ineq") if k in g])
+        assert info["long_rows"] + info["long_cols"] > 0
+        assert info["long_entries"] > LONG_THRESHOLD[name] * (info["long_rows"] + info["long_cols"])
+        assert np.array_equal(T == 1.0, g["diag_t"] == 1.0) and np.array_equal(sigma == 1.0, s_gold == 1.0)
+        assert rel_inf(T, g["diag_t"]) < 1e-14 and rel_inf(sigma, s_gold) < 1e-14
+        assert rel_inf(x, g["x_100"]) <= 1e-9 and rel_inf(y, y_gold) <= 1e-9
+        curves_close(np.array(trace), g["trace_10"])
+        assert (best is None) == (g["best_100"].size == 0)
+    finally:
+        solver.close()
+
+
+def test_emulated_long_rows_with_segments_and_force_integer():
+    """Rows longer than one 4096-entry segment (several CTAs per row), a dense 'budget' row and a dense column,
+    against the oracle; the default threshold leaves the golden cases on the exact path."""
+    import scipy.sparse as sp
+
+    from oracle.cpppd_oracle import chambolle_pock_ppd_oracle
+
+    rng = np.random.default_rng(21)
+    n, m = 9000, 60
+    a = sp.random(m, n, density=0.002, random_state=5, format="lil")
+    a[7, :] = np.round(rng.standard_normal(n), 2) + 0.005      # 9000 entries: three segments
+    a[:, 11] = (np.round(rng.standard_normal(m), 2) + 0.005)[:, None]
+    a = a.tocsr()
+    a_eq = sp.csr_matrix(np.ones((1, n)))                      # dense equality row
+    xf = rng.random(n)
+    c = np.round(rng.standard_normal(n), 2)
+    lb, ub = np.zeros(n), np.ones(n)
+    args = (c, a_eq, a_eq @ xf, a, None, a @ xf + 0.1, lb, ub)
+    tr_o, tr = [], []
+    with np.errstate(invalid="ignore"):
+        xo, bo = chambolle_pock_ppd_oracle(*args, nb_max_iter=60, nb_iter_plot=20, force_integer=True,
+                                           callback_func=lambda k, xx, e1, e2, el, p, q: tr_o.append((k, e1, e2, p, q)))
+    x, best, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=60, nb_iter_plot=20, force_integer=True,
+                                                  callback_func=lambda k, xx, e1, e2, el, p, q: tr.append((k, e1, e2, p, q)))
+    info = solver.info()
+    solver.close()
+    assert info["long_rows"] == 2 and info["long_cols"] == 0 and info["long_entries"] == 2 * n  # default threshold 2048
+    assert rel_inf(x, xo) <= 1e-9
+    curves_close(np.array(tr), np.array(tr_o))
+    assert (best is None) == (bo is None)
+    # never split: bit-identical again
+    x2, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=60, nb_iter_plot=20, force_integer=True,
+                                                long_row_threshold=-1)
+    assert solver.info()["long_rows"] == 0
+    solver.close()
+    assert np.array_equal(x2, xo)
+    args_g, g = case_args("l1svm")
+    x3, _, solver = emulated_chambolle_pock_ppd(*args_g, nb_max_iter=100, nb_iter_plot=10)
+    assert solver.info()["long_cols"] == 0
+    solver.close()
+    assert np.array_equal(x3, g["x_100"])

@@ -140,3 +140,18 @@ def test_halo_wait_gives_up_instead_of_hanging(transport, monkeypatch):
 
     res = run_ranks(2, body)
     assert res[1] == "idle" and res[0] is not None and res[0] < 30.0
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("transport", ["push_wait_kernels", "nccl", "fused_in_kernels"])
+def test_multi_rank_long_rows(transport):
+    """Long rows / columns with world_size 2: the long column sums gather ghost y entries, so they must run after
+    the halo arrived (the fused transport is switched off for such LPs)."""
+    args, g = case_args("l1svm")
+    y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+    res = solve_on_ranks(args, 2, TRANSPORTS[transport], 100, 10, long_row_threshold=64)
+    assert sum(r["info"]["long_cols"] for r in res) == 9  # the weight columns, wherever they live
+    for r in res:
+        assert np.max(np.abs(r["x"] - g["x_100"])) <= 1e-9 * np.max(np.abs(g["x_100"]))
+        assert np.max(np.abs(r["y"] - y_gold)) <= 1e-9 * np.max(np.abs(y_gold))
+        assert np.allclose(r["trace"], g["trace_10"], rtol=1e-6, atol=1e-9, equal_nan=True)
