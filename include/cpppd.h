@@ -176,6 +176,9 @@ typedef struct {
   float variant_ms[2][CPPPD_KERNEL_VARIANTS];
   int64_t long_rows, long_cols; /* rows / columns handled by the long-row path on this rank */
   int64_t long_entries;         /* their entries */
+  int32_t balanced_split;       /* world_size > 1: the locality buckets left some rank with more than 1.5x its share of
+                                   the row or column entries, so rows / columns were dealt out by prefix sums instead */
+  int32_t reserved;
 } cpppd_info;
 
 typedef enum {

@@ -12,7 +12,14 @@ Definitions (A = [A_eq; A_ineq], m x n, CSR; N ranks; granule G):
   bucket     = key // G,   nb = n // G + 2 buckets
   work[q]    = nnz of the rows in bucket q + nnz of the columns in bucket q
   owner(q)   = min(N-1, (work before bucket q) * N // total work)
-A row / column belongs to the owner of its bucket.  Rank r keeps its rows in the order
+A row / column belongs to the owner of its bucket — unless that leaves some rank with more than 1.5 times
+its share of the row entries or of the column entries (patterns without locality: every row of an L1-SVM LP
+starts at a weight column, so all rows share one bucket; a random pattern gives the first ranks the columns
+and the last ranks the rows).  Then ownership falls back to the BALANCED SPLIT, decided per row and per
+column from the prefix sums in original order:
+  owner(row i)    = min(N-1, indptr[i] * N // nnz)
+  owner(column j) = min(N-1, (entries of the columns before j) * N // nnz)
+Rank r keeps its rows in the order
 (equalities first, then inequalities; inside each, by bucket, then by min(length, 4095), then by
 original index) and its columns in the order (bucket, min(length, 4095), original index) — grouping
 equal lengths inside a bucket is the sigma-sorting of SELL-C-sigma: slices of 32 neighbours get
@@ -70,6 +77,13 @@ def partition(indptr, indices, n, m_eq, world, granule=None, reorder=True):
     else:
         owner_of_bucket = np.zeros(nb, dtype=np.int64)
     row_owner, col_owner = owner_of_bucket[rq], owner_of_bucket[cq]
+    nnz = int(lens.sum())
+    row_share = np.bincount(row_owner, weights=lens, minlength=world).astype(np.int64)
+    col_share = np.bincount(col_owner, weights=col_lens, minlength=world).astype(np.int64)
+    balanced = bool(nnz > 0 and 2 * world * max(int(row_share.max()), int(col_share.max())) > 3 * nnz)
+    if balanced:
+        row_owner = np.minimum(world - 1, indptr[:-1] * world // nnz)
+        col_owner = np.minimum(world - 1, (np.cumsum(col_lens) - col_lens) * world // nnz)
     is_ineq = (np.arange(m) >= m_eq).astype(np.int64)
     row_order = np.lexsort((np.arange(m), np.minimum(lens, 4095), rq, is_ineq, row_owner))
     col_order = np.lexsort((np.arange(n), np.minimum(col_lens, 4095), cq, col_owner))
@@ -77,7 +91,7 @@ def partition(indptr, indices, n, m_eq, world, granule=None, reorder=True):
     col_start = np.concatenate(([0], np.cumsum(np.bincount(col_owner, minlength=world))))
     m_eq_local = np.bincount(row_owner[:m_eq], minlength=world)
     return dict(row_order=row_order, row_start=row_start, col_order=col_order, col_start=col_start,
-                m_eq_local=m_eq_local, row_owner=row_owner, col_owner=col_owner, granule=G)
+                m_eq_local=m_eq_local, row_owner=row_owner, col_owner=col_owner, granule=G, balanced_split=balanced)
 
 
 def ghosts(indptr, indices, part, rank):

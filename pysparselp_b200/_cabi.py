@@ -73,10 +73,11 @@ class Info(C.Structure):
         ("halo_send_bytes_per_iteration", C.c_int64), ("partition_granule", C.c_int64),
         ("dual_variant", C.c_int32), ("autotuned", C.c_int32), ("variant_ms", (C.c_float * KERNEL_VARIANTS) * 2),
         ("long_rows", C.c_int64), ("long_cols", C.c_int64), ("long_entries", C.c_int64),
+        ("balanced_split", C.c_int32), ("reserved", C.c_int32),
     ]
 
     def as_dict(self):
-        out = {name: getattr(self, name) for name, _ in self._fields_ if name != "variant_ms"}
+        out = {name: getattr(self, name) for name, _ in self._fields_ if name not in ("variant_ms", "reserved")}
         out["variant_ms"] = {"k_primal": list(self.variant_ms[0]), "k_dual": list(self.variant_ms[1])}
         return out
 

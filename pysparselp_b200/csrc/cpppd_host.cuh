@@ -536,31 +536,50 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     h->granule = G;
     const int64_t nb = n / G + 2;
     int32_t *row_key = nullptr, *col_key = nullptr, *col_len = nullptr, *owner_dev = nullptr, *counts = nullptr;
-    unsigned long long *work = nullptr;
+    unsigned long long *work = nullptr;  // [0, nb): entries of the rows of a bucket, [nb, 2 nb): of its columns
     if (int rc = tmp.get(&row_key, m)) return rc;
     if (int rc = tmp.get(&col_key, n)) return rc;
     if (int rc = tmp.get(&col_len, n)) return rc;
-    if (int rc = tmp.get(&work, nb)) return rc;
+    if (int rc = tmp.get(&work, 2 * nb)) return rc;
     if (int rc = tmp.get(&owner_dev, nb)) return rc;
     if (int rc = tmp.get(&counts, 3 * (int64_t)N)) return rc;
     if (m) k_row_key<<<grid_for(m), kBlock, 0, st>>>(rowptr, indices, m, (int32_t)n, row_key);
     if (n) k_fill_i32<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)n);
     CK(cudaMemsetAsync(col_len, 0, sizeof(int32_t) * std::max<int64_t>(n, 1), st));
     if (nnz) k_col_key<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_key, col_key, col_len);
-    CK(cudaMemsetAsync(work, 0, sizeof(unsigned long long) * nb, st));
+    CK(cudaMemsetAsync(work, 0, sizeof(unsigned long long) * 2 * nb, st));
     if (m) k_bucket_work<<<grid_for(m), kBlock, 0, st>>>(row_key, rowptr, nullptr, m, (int32_t)G, work);
-    if (n) k_bucket_work<<<grid_for(n), kBlock, 0, st>>>(col_key, nullptr, col_len, n, (int32_t)G, work);
-    std::vector<unsigned long long> work_h(nb);
-    CK(cudaMemcpyAsync(work_h.data(), work, sizeof(unsigned long long) * nb, cudaMemcpyDeviceToHost, st));
+    if (n) k_bucket_work<<<grid_for(n), kBlock, 0, st>>>(col_key, nullptr, col_len, n, (int32_t)G, work + nb);
+    std::vector<unsigned long long> work_h(2 * nb);
+    CK(cudaMemcpyAsync(work_h.data(), work, sizeof(unsigned long long) * 2 * nb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     std::vector<int32_t> owner_h(nb, 0);
     unsigned long long total = 0, before = 0;
     for (auto w : work_h) total += w;
+    std::vector<unsigned long long> row_share(N, 0), col_share(N, 0);
     for (int64_t q = 0; q < nb; ++q) {
       owner_h[q] = total ? (int32_t)std::min<unsigned long long>(N - 1, (unsigned __int128)before * N / total) : 0;
-      before += work_h[q];
+      before += work_h[q] + work_h[nb + q];
+      row_share[owner_h[q]] += work_h[q];
+      col_share[owner_h[q]] += work_h[nb + q];
     }
     CK(cudaMemcpyAsync(owner_dev, owner_h.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    // A pattern without locality leaves some rank with far more than its share of the row entries or of the
+    // column entries (every kernel then waits for that rank): fall back to the balanced split, where the owner
+    // of a row / column follows from the entries in front of it (oracle/partition_oracle.py restates this).
+    unsigned long long worst = 0;
+    for (int r = 0; r < N; ++r) worst = std::max(worst, std::max(row_share[r], col_share[r]));
+    h->balanced_split = nnz > 0 && (unsigned __int128)2 * N * worst > (unsigned __int128)3 * (unsigned long long)nnz;
+    int64_t *col_prefix = nullptr;
+    if (h->balanced_split) {
+      int64_t *col_len64 = nullptr;
+      if (int rc = tmp.get(&col_len64, n + 1)) return rc;
+      if (int rc = tmp.get(&col_prefix, n + 1)) return rc;
+      CK(cudaMemsetAsync(col_len64, 0, sizeof(int64_t) * (n + 1), st));
+      if (n) k_widen_indptr<<<grid_for(n), kBlock, 0, st>>>(col_len, col_len64, n);
+      if (int rc = exclusive_scan(h, col_len64, col_prefix, n + 1)) return rc;
+      tmp.release(col_len64);
+    }
     // ---- local orders: rows by (owner, is_ineq, bucket, id), columns by (owner, bucket, id)
     uint64_t *rk_a = nullptr, *rk_b = nullptr, *ck_a = nullptr, *ck_b = nullptr;
     uint32_t *ro_a = nullptr, *ro_b = nullptr, *co_a = nullptr, *co_b = nullptr;
@@ -573,8 +592,10 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = tmp.get(&co_a, n)) return rc;
     if (int rc = tmp.get(&co_b, n)) return rc;
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * N, st));
-    if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rowptr, nullptr, rk_a, ro_a, counts, counts + N);
-    if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, nullptr, col_len, ck_a, co_a, counts + 2 * N, nullptr);
+    if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rowptr, nullptr,
+                                                       h->balanced_split ? rowptr : nullptr, nnz, N, rk_a, ro_a, counts, counts + N);
+    if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, nullptr, col_len,
+                                                       col_prefix, nnz, N, ck_a, co_a, counts + 2 * N, nullptr);
     const int end_bit = 44 + bits_for((uint64_t)2 * N + 1);
     cub::DoubleBuffer<uint64_t> rk(rk_a, rk_b), ck(ck_a, ck_b);
     cub::DoubleBuffer<uint32_t> rov(ro_a, ro_b), cov(co_a, co_b);
@@ -597,7 +618,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     tmp.release(rk_a); tmp.release(rk_b); tmp.release(ck_a); tmp.release(ck_b);
     if (row_order == ro_a) tmp.release(ro_b); else tmp.release(ro_a);
     if (col_order == co_a) tmp.release(co_b); else tmp.release(co_a);
-    tmp.release(row_key); tmp.release(col_key); tmp.release(col_len); tmp.release(work);
+    tmp.release(row_key); tmp.release(col_key); tmp.release(col_len); tmp.release(work); tmp.release(col_prefix);
     // ---- ghosts of this rank
     int32_t *gcol_flag = nullptr, *grow_flag = nullptr;
     if (int rc = tmp.get(&gcol_flag, n + 1)) return rc;

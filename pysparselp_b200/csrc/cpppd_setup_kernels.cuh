@@ -75,16 +75,20 @@ __global__ void k_bucket_work(const int32_t *__restrict__ key, const int64_t *__
   if (w) atomicAdd(work + key[i] / granule, w);
 }
 
-// sort key of a row / column: (owner, [is_ineq,] bucket); also counts per owner
+// sort key of a row / column: (owner, [is_ineq,] bucket); also counts per owner.
+// The owner is the owner of the bucket, or — balanced split, prefix != nullptr — decided per row / column from
+// the entries in front of it in original order: min(world - 1, prefix[i] * world / total).
 __global__ void k_sort_keys(const int32_t *__restrict__ key, int64_t count, int32_t granule,
                             const int32_t *__restrict__ owner_of_bucket, int64_t m_eq, int is_rows,
                             const int64_t *__restrict__ rowptr, const int32_t *__restrict__ len32,
+                            const int64_t *__restrict__ prefix, int64_t total, int world,
                             uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_id,
                             int32_t *__restrict__ count_per_owner, int32_t *__restrict__ eq_per_owner) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   int32_t q = key[i] / granule;
   int32_t o = owner_of_bucket[q];
+  if (prefix) o = (int32_t)min((int64_t)world - 1, prefix[i] * world / total);
   // inside a bucket, rows / columns of equal length sit together (SELL sigma-sorting: slices of
   // 32 neighbours then have nearly equal widths and little padding)
   int64_t len = rowptr ? rowptr[i + 1] - rowptr[i] : (int64_t)len32[i];

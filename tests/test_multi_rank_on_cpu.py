@@ -155,3 +155,30 @@ def test_multi_rank_long_rows(transport):
         assert np.max(np.abs(r["x"] - g["x_100"])) <= 1e-9 * np.max(np.abs(g["x_100"]))
         assert np.max(np.abs(r["y"] - y_gold)) <= 1e-9 * np.max(np.abs(y_gold))
         assert np.allclose(r["trace"], g["trace_10"], rtol=1e-6, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_balanced_split_for_patterns_without_locality(world):
+    """Every row of the L1-SVM LP starts at a weight column: the locality buckets would give one rank everything.
+    The partition then deals rows and columns out by prefix sums (oracle/partition_oracle.py); iterates stay
+    bit-identical because whole rows and whole columns still live on one rank."""
+    args, g = case_args("l1svm")
+    y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+    c, a_eq, beq, a_in, b_lo, b_up, lb, ub = args
+    a_in1, b_in1 = one_sided_rows(a_in, b_lo, b_up)
+    A, b, m_eq = stack_operator(None, None, a_in1, b_in1, c.size)
+    part = po.partition(A.indptr, A.indices, A.shape[1], m_eq, world, granule=32)
+    assert part["balanced_split"]
+    res = solve_on_ranks(args, world, 0, 100, 10)
+    for rank, r in enumerate(res):
+        assert r["info"]["balanced_split"] == 1
+        assert np.array_equal(r["x"], g["x_100"]) and np.array_equal(r["y"], y_gold)
+        own_c, ghost_c = r["cols"]
+        own_r, ghost_r = r["rows"]
+        assert np.array_equal(own_c, part["col_order"][part["col_start"][rank]: part["col_start"][rank + 1]])
+        assert np.array_equal(own_r, part["row_order"][part["row_start"][rank]: part["row_start"][rank + 1]])
+        gc, gr = po.ghosts(A.indptr, A.indices, part, rank)
+        assert np.array_equal(ghost_c, gc) and np.array_equal(ghost_r, gr)
+        # nobody holds more than 1.5x its share of the entries, rows and columns alike
+        assert r["info"]["nnz_local_rows"] * world * 2 <= 3 * A.nnz and r["info"]["nnz_local_cols"] * world * 2 <= 3 * A.nnz
