@@ -82,7 +82,12 @@ enum {
    * emulation of the library only) */
   CPPPD_FLAG_FUSED_HALO = 1u << 7,
   /* never time the kernel variants at creation: use variant 1 (see cpppd_problem.kernel_variant) */
-  CPPPD_FLAG_NO_AUTOTUNE = 1u << 8
+  CPPPD_FLAG_NO_AUTOTUNE = 1u << 8,
+  /* one GPU, LPs whose operands fit the L1 of one SM (n, m <= 4096 and <= 16384 stored entries in A and A^T
+   * together, e.g. netlib SC105): cpppd_iterate(k) runs all k iterations in ONE launch of one CTA instead of 2k
+   * graph nodes — such LPs are bound by launch latency, not bandwidth.  Same per-row code, same bits.
+   * (Opt-in until it has been measured on hardware.) */
+  CPPPD_FLAG_TINY_PERSISTENT = 1u << 9
 };
 
 typedef struct {
@@ -178,7 +183,7 @@ typedef struct {
   int64_t long_entries;         /* their entries */
   int32_t balanced_split;       /* world_size > 1: the locality buckets left some rank with more than 1.5x its share of
                                    the row or column entries, so rows / columns were dealt out by prefix sums instead */
-  int32_t reserved;
+  int32_t tiny_persistent;      /* iterations run in one persistent CTA (CPPPD_FLAG_TINY_PERSISTENT and a tiny LP) */
 } cpppd_info;
 
 typedef enum {

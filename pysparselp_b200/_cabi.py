@@ -25,6 +25,7 @@ FLAG_NO_P2P = 1 << 5
 FLAG_NO_REORDER = 1 << 6
 FLAG_FUSED_HALO = 1 << 7
 FLAG_NO_AUTOTUNE = 1 << 8
+FLAG_TINY_PERSISTENT = 1 << 9
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 
@@ -73,7 +74,7 @@ class Info(C.Structure):
         ("halo_send_bytes_per_iteration", C.c_int64), ("partition_granule", C.c_int64),
         ("dual_variant", C.c_int32), ("autotuned", C.c_int32), ("variant_ms", (C.c_float * KERNEL_VARIANTS) * 2),
         ("long_rows", C.c_int64), ("long_cols", C.c_int64), ("long_entries", C.c_int64),
-        ("balanced_split", C.c_int32), ("reserved", C.c_int32),
+        ("balanced_split", C.c_int32), ("tiny_persistent", C.c_int32),
     ]
 
     def as_dict(self):

@@ -904,6 +904,9 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   memset(h->stats_host, 0, sizeof(cpppd_stats));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
+  // a single CTA can carry a whole iteration when both operands fit the L1 of one SM (see k_tiny_iterate)
+  h->tiny = (h->flags & CPPPD_FLAG_TINY_PERSISTENT) && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
+            std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
   if (int rc = tune_kernels(h)) return rc;
   if (want_p2p)
     if (int rc = setup_p2p(h)) return rc;
@@ -1046,7 +1049,26 @@ int get_graph(cpppd_solver *h, int64_t k, cudaGraphExec_t *out) {
   return 0;
 }
 
+// tiny LPs with CPPPD_FLAG_TINY_PERSISTENT: all k iterations in one launch of one CTA (k_tiny_iterate)
+int run_tiny(cpppd_solver *h, int64_t k) {
+  const int64_t widest = std::max(h->AT.nslices, h->A.nslices) * kSlice;
+  const int threads = (int)std::min<int64_t>(kTinyBlock, std::max<int64_t>(kSlice, widest));
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  if (h->A.dict)
+    k_tiny_iterate<true><<<1, threads, 0, h->stream>>>(view(h->AT), view(h->A), h->vc, h->vT, h->vlb, h->vub, h->vb, h->vsigma,
+                                                      h->x, h->xbar, h->y, h->n, h->m, h->m_eq, has_eq, has_ineq, h->theta,
+                                                      h->one_plus_theta, k);
+  else
+    k_tiny_iterate<false><<<1, threads, 0, h->stream>>>(view(h->AT), view(h->A), h->vc, h->vT, h->vlb, h->vub, h->vb, h->vsigma,
+                                                       h->x, h->xbar, h->y, h->n, h->m, h->m_eq, has_eq, has_ineq, h->theta,
+                                                       h->one_plus_theta, k);
+  CK(cudaGetLastError());
+  h->niter += k;
+  return 0;
+}
+
 int run_iterations(cpppd_solver *h, int64_t k) {
+  if (h->tiny && k > 0) return run_tiny(h, k);
   const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH) && (h->world == 1 || h->p2p.active || (h->flags & CPPPD_FLAG_GRAPH_COMM));
   while (k > 0) {
     int64_t step = std::min<int64_t>(k, kGraphChunk);

@@ -113,8 +113,25 @@ __device__ __forceinline__ void comm_finish(const FusedComm *cm) {
 // kMinB is the CTAs/SM the variant is compiled for (register cap = 65536 / (256 * kMinB)).
 // cpppd_create() times the variants on the actual operands and keeps the fastest (cpppd_host.cuh).
 
+// How operands are loaded.
+// LoadStream: one pass over operands far larger than the caches — matrix entries and vectors are read once
+// (ld.global.cs, evict-first), gathers go through the read-only path (ld.global.nc): the gathered vector is not
+// written by the kernel that gathers from it.
+// LoadResident: the persistent kernel for tiny LPs (k_tiny_iterate) re-reads the whole LP every iteration from
+// L1 / L2 and WRITES the vectors it gathers from between two barriers: ordinary coherent loads (ld.global.ca).
+struct LoadStream {
+  template <typename T> static __device__ __forceinline__ T entry(const T *p) { return __ldcs(p); }
+  static __device__ __forceinline__ double gather(const double *p) { return __ldg(p); }
+  static __device__ __forceinline__ double vec(const Vec &v, int64_t i) { return v.at(i); }
+};
+struct LoadResident {
+  template <typename T> static __device__ __forceinline__ T entry(const T *p) { return __ldca(p); }
+  static __device__ __forceinline__ double gather(const double *p) { return __ldca(p); }
+  static __device__ __forceinline__ double vec(const Vec &v, int64_t i) { return v.p ? __ldca(v.p + i) : v.c; }
+};
+
 // sum of column j of A times y, equality and inequality rows apart (:206, :216)
-template <bool kDict, int kChunk>
+template <bool kDict, int kChunk, typename L = LoadStream>
 __device__ __forceinline__ void primal_sums(const SellView &AT, const double *__restrict__ y, const double *sdict,
                                             int64_t p0, int64_t p1, int lane, double &s_eq, double &s_in) {
   const int32_t *ip = AT.idx + p0 + lane;
@@ -124,11 +141,11 @@ __device__ __forceinline__ void primal_sums(const SellView &AT, const double *__
   if (kChunk == 0) {
 #pragma unroll 4
     for (int k = 0; k < width; ++k) {
-      const int32_t r = __ldcs(ip + k * kSlice);
+      const int32_t r = L::entry(ip + k * kSlice);
       double a;
-      if (kDict) a = sdict[(r >> AT.idx_bits) & AT.code_mask]; else a = __ldcs(vp + k * kSlice);
+      if (kDict) a = sdict[(r >> AT.idx_bits) & AT.code_mask]; else a = L::entry(vp + k * kSlice);
       if (r >= 0) {
-        const double t = __dmul_rn(a, __ldg(y + (r & mask)));
+        const double t = __dmul_rn(a, L::gather(y + (r & mask)));
         if (r & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
       }
     }
@@ -141,11 +158,11 @@ __device__ __forceinline__ void primal_sums(const SellView &AT, const double *__
 #pragma unroll
       for (int u = 0; u < kC; ++u) {
         const bool ok = k0 + u < width;
-        r[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
-        a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
+        r[u] = ok ? L::entry(ip + (k0 + u) * kSlice) : kPad;
+        a[u] = (!kDict && ok) ? L::entry(vp + (k0 + u) * kSlice) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < kC; ++u) g[u] = r[u] >= 0 ? __ldg(y + (r[u] & mask)) : 0.0;
+      for (int u = 0; u < kC; ++u) g[u] = r[u] >= 0 ? L::gather(y + (r[u] & mask)) : 0.0;
 #pragma unroll
       for (int u = 0; u < kC; ++u) {
         if (r[u] >= 0) {
@@ -159,7 +176,7 @@ __device__ __forceinline__ void primal_sums(const SellView &AT, const double *__
 }
 
 // row i of A times xbar (:235, :240)
-template <bool kDict, int kChunk>
+template <bool kDict, int kChunk, typename L = LoadStream>
 __device__ __forceinline__ double dual_sum(const SellView &A, const double *__restrict__ xbar, const double *sdict,
                                            int64_t p0, int64_t p1, int lane) {
   const int32_t *ip = A.idx + p0 + lane;
@@ -170,10 +187,10 @@ __device__ __forceinline__ double dual_sum(const SellView &A, const double *__re
   if (kChunk == 0) {
 #pragma unroll 4
     for (int k = 0; k < width; ++k) {
-      const int32_t jc = __ldcs(ip + k * kSlice);
+      const int32_t jc = L::entry(ip + k * kSlice);
       double a;
-      if (kDict) a = sdict[(jc >> A.idx_bits) & A.code_mask]; else a = __ldcs(vp + k * kSlice);
-      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, __ldg(xbar + (jc & mask))));
+      if (kDict) a = sdict[(jc >> A.idx_bits) & A.code_mask]; else a = L::entry(vp + k * kSlice);
+      if (jc >= 0) acc = __dadd_rn(acc, __dmul_rn(a, L::gather(xbar + (jc & mask))));
     }
   } else {
     constexpr int kC = kChunk > 0 ? kChunk : 1;
@@ -184,11 +201,11 @@ __device__ __forceinline__ double dual_sum(const SellView &A, const double *__re
 #pragma unroll
       for (int u = 0; u < kC; ++u) {
         const bool ok = k0 + u < width;
-        jc[u] = ok ? __ldcs(ip + (k0 + u) * kSlice) : kPad;
-        a[u] = (!kDict && ok) ? __ldcs(vp + (k0 + u) * kSlice) : 0.0;
+        jc[u] = ok ? L::entry(ip + (k0 + u) * kSlice) : kPad;
+        a[u] = (!kDict && ok) ? L::entry(vp + (k0 + u) * kSlice) : 0.0;
       }
 #pragma unroll
-      for (int u = 0; u < kC; ++u) g[u] = jc[u] >= 0 ? __ldg(xbar + (jc[u] & mask)) : 0.0;
+      for (int u = 0; u < kC; ++u) g[u] = jc[u] >= 0 ? L::gather(xbar + (jc[u] & mask)) : 0.0;
 #pragma unroll
       for (int u = 0; u < kC; ++u) {
         if (jc[u] >= 0) {
@@ -202,7 +219,7 @@ __device__ __forceinline__ double dual_sum(const SellView &A, const double *__re
 }
 
 // body of k_primal for one thread (column j of slice s)
-template <bool kWriteD, bool kDict, int kChunk, bool kEarlyBounds, bool kComm>
+template <bool kWriteD, bool kDict, int kChunk, bool kEarlyBounds, bool kComm, typename L = LoadStream>
 __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__restrict__ y, const Vec &c, const Vec &T,
                                             const Vec &lb, const Vec &ub, double *__restrict__ x,
                                             double *__restrict__ xbar, double *__restrict__ d_out, int64_t n,
@@ -220,23 +237,23 @@ __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__
   // loads that do not depend on the matrix are issued first: they are in flight together with the entries
   double cj = 0.0, tj = 0.0, xo = 0.0, l = 0.0, u = 0.0;
   if (live) {
-    cj = c.at(j);
-    tj = T.at(j);
-    xo = __ldcs(x + j);
+    cj = L::vec(c, j);
+    tj = L::vec(T, j);
+    xo = L::entry(x + j);
     if (kEarlyBounds) {
-      l = lb.at(j);
-      u = ub.at(j);
+      l = L::vec(lb, j);
+      u = L::vec(ub, j);
     }
   }
   double s_eq = 0.0, s_in = 0.0;
-  primal_sums<kDict, kChunk>(AT, y, sdict, p0, p1, lane, s_eq, s_in);
+  primal_sums<kDict, kChunk, L>(AT, y, sdict, p0, p1, lane, s_eq, s_in);
   if (!live) return;
   double d = cj;
   if (has_eq) d = __dadd_rn(d, s_eq);
   if (has_ineq) d = __dadd_rn(d, s_in);
   if (!kEarlyBounds) {
-    l = lb.at(j);
-    u = ub.at(j);
+    l = L::vec(lb, j);
+    u = L::vec(ub, j);
   }
   double x2 = __dsub_rn(xo, __dmul_rn(tj, d));
   x2 = (l > x2) ? l : x2;  // np.maximum(x2, lb)  (NaN in x2 propagates)
@@ -272,7 +289,7 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
 }
 
 // body of k_dual for one thread (row i of slice s)
-template <bool kDict, int kChunk, bool kComm>
+template <bool kDict, int kChunk, bool kComm, typename L = LoadStream>
 __device__ __forceinline__ void dual_rows(const SellView &A, const double *__restrict__ xbar, const Vec &b,
                                           const Vec &sigma, double *__restrict__ y, int64_t m, int64_t m_eq,
                                           const FusedComm *__restrict__ cm, const double *sdict, int64_t i, int64_t s) {
@@ -287,11 +304,11 @@ __device__ __forceinline__ void dual_rows(const SellView &A, const double *__res
   const bool live = i < m;
   double bi = 0.0, si = 0.0, yi = 0.0;
   if (live) {
-    bi = b.at(i);
-    si = sigma.at(i);
-    yi = __ldcs(y + i);
+    bi = L::vec(b, i);
+    si = L::vec(sigma, i);
+    yi = L::entry(y + i);
   }
-  const double acc = dual_sum<kDict, kChunk>(A, xbar, sdict, p0, p1, lane);
+  const double acc = dual_sum<kDict, kChunk, L>(A, xbar, sdict, p0, p1, lane);
   if (!live) return;
   const double r = __dsub_rn(acc, bi);
   double yn = __dadd_rn(yi, __dmul_rn(si, r));
@@ -314,6 +331,34 @@ k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__
   const int64_t s = i >> 5;
   if (s < A.nslices) dual_rows<kDict, kChunk, kComm>(A, xbar, b, sigma, y, m, m_eq, cm, sdict, i, s);
   if (kComm) comm_finish(cm);
+}
+
+// Tiny LPs (SC105: 103 x 105; everything fits the L1 of one SM): a whole iteration is two kernels of a few
+// microseconds of launch latency and a few hundred nanoseconds of work.  k_tiny_iterate runs `iters` complete
+// iterations in ONE CTA — primal half, barrier, dual half, barrier — with the threads striding over the slices.
+// Same per-row code as k_primal / k_dual (variant 1), so the iterates are the same bits; loads are ordinary
+// coherent ones (LoadResident) because y and xbar are rewritten between the barriers.
+constexpr int kTinyBlock = 1024;
+template <bool kDict>
+__global__ void __launch_bounds__(kTinyBlock, 1)
+k_tiny_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, Vec sigma, double *x, double *xbar, double *y,
+               int64_t n, int64_t m, int64_t m_eq, int has_eq, int has_ineq, double theta, double one_plus_theta,
+               int64_t iters) {
+  __shared__ double sdict[kDict ? 256 : 1];
+  if (kDict) {
+    if ((int)threadIdx.x < AT.ndict) sdict[threadIdx.x] = AT.dict[threadIdx.x];
+    __syncthreads();
+  }
+  const int64_t cols = AT.nslices * kSlice, rows = A.nslices * kSlice;
+  for (int64_t it = 0; it < iters; ++it) {
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x)  // blockDim.x is a multiple of 32: lane == j % 32
+      primal_rows<false, kDict, 0, false, false, LoadResident>(AT, y, c, T, lb, ub, x, xbar, nullptr, n, has_eq, has_ineq,
+                                                               theta, one_plus_theta, nullptr, sdict, j, j >> 5);
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < rows; i += blockDim.x)
+      dual_rows<kDict, 0, false, LoadResident>(A, xbar, b, sigma, y, m, m_eq, nullptr, sdict, i, i >> 5);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -136,6 +136,7 @@ struct cpppd_solver {
   int64_t n = 0, m = 0, m_eq = 0, nnz_rows = 0, nnz_cols = 0;
   int rank = 0, world = 1;
   bool identity_layout = true;  // local index == original index (one GPU, no reordering)
+  bool tiny = false;            // iterations run in k_tiny_iterate (one persistent CTA)
   bool balanced_split = false;  // ownership by prefix sums instead of locality buckets (see setup())
   int32_t *col_old = nullptr;   // n + ghosts : original column id of a local column
   int32_t *row_old = nullptr;   // m + ghosts : original row id of a local row

@@ -329,3 +329,32 @@ def test_emulated_long_rows_with_segments_and_force_integer():
     assert solver.info()["long_cols"] == 0
     solver.close()
     assert np.array_equal(x3, g["x_100"])
+
+
+@pytest.mark.parametrize("name", ["sc105", "random_small", "random_small_alpha"])
+@pytest.mark.parametrize("flags", [_cabi.FLAG_TINY_PERSISTENT,
+                                   _cabi.FLAG_TINY_PERSISTENT | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS | _cabi.FLAG_REORDER])
+def test_emulated_tiny_persistent_kernel(name, flags):
+    """CPPPD_FLAG_TINY_PERSISTENT: the iterations between two stats blocks run in one launch of one CTA."""
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    trace = []
+    x, best, solver = emulated_chambolle_pock_ppd(
+        *args, nb_max_iter=100, nb_iter_plot=10, flags=flags,
+        callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)), **kw)
+    try:
+        assert solver.info()["tiny_persistent"] == 1 and solver.niter == 100
+        y = solver.get_y()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        if "alpha" not in kw:
+            assert np.array_equal(x, g["x_100"]) and np.array_equal(y, y_gold)
+        else:
+            assert rel_inf(x, g["x_100"]) <= 1e-9 and rel_inf(y, y_gold) <= 1e-9
+        curves_close(np.array(trace), g["trace_10"])
+    finally:
+        solver.close()
+    # too large for one CTA: the flag is ignored
+    args, g = case_args("potts50")
+    x, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=20, nb_iter_plot=10, flags=_cabi.FLAG_TINY_PERSISTENT)
+    assert solver.info()["tiny_persistent"] == 0
+    solver.close()
