@@ -957,12 +957,30 @@ int launch_dual(cpppd_solver *h, int variant = -1) {
   return pp.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
 }
 
+// Process-wide memory of tune_kernels(): the timings depend on the device and on the shape of the two SELL
+// operands (slices, stored entries, uniform widths, long rows, storage variant, numbering), not on the values.
+using TuneKey = std::array<int64_t, 15>;
+struct TuneChoice {
+  int primal = 0, dual = 0;
+  float ms[2][CPPPD_KERNEL_VARIANTS] = {};
+};
+std::map<TuneKey, TuneChoice> g_tune_cache;
+std::mutex g_tune_mutex;
+
+TuneKey tune_key(const cpppd_solver *h) {
+  return TuneKey{h->device,          h->n,          h->m,           h->A.nslices,        h->A.padded,
+                 h->A.uniform_width, h->AT.nslices, h->AT.padded,   h->AT.uniform_width, h->longA.nnz,
+                 h->longAT.nnz,      h->A.dict ? h->ndict : 0, h->const_mask, h->hx.ghost + h->hy.ghost,
+                 h->identity_layout ? 0 : 1 + h->granule};
+}
+
 // Choose the kernel variants (called at the end of setup(), before any neighbour may write into this
 // rank's vectors).  Forced by cpppd_problem.kernel_variant / CPPPD_KERNEL_VARIANT, or — for LPs large
 // enough for the choice to matter — measured: every variant runs on the real operands (one untimed launch
 // each, then two passes of two timed launches, CUDA events), the fastest wins, and variant 0 is only given
 // up for a gain above 2 %.
-// The iterates do not depend on the choice; the state (x, xbar, y) is put back afterwards.
+// The iterates do not depend on the choice; the state (x, xbar, y) is put back afterwards.  A measured choice is
+// remembered per process and operand shape (g_tune_cache; CPPPD_AUTOTUNE_CACHE=0 measures every time).
 int tune_kernels(cpppd_solver *h) {
   int request = h->variant_request;
   if (request == 0)
@@ -978,6 +996,22 @@ int tune_kernels(cpppd_solver *h) {
   int64_t min_nnz = (int64_t)1 << 22;
   if (const char *env = getenv("CPPPD_AUTOTUNE_MIN_NNZ")) min_nnz = atoll(env);
   if ((h->flags & CPPPD_FLAG_NO_AUTOTUNE) || std::max(h->nnz_rows, h->nnz_cols) < min_nnz) return 0;
+  // operands of the same shape were timed before in this process (a second solve of the same LP family):
+  // reuse that choice instead of spending another ~50 launches
+  const TuneKey key = tune_key(h);
+  bool use_cache = true;
+  if (const char *env = getenv("CPPPD_AUTOTUNE_CACHE")) use_cache = atoi(env) != 0;
+  if (use_cache) {
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    auto hit = g_tune_cache.find(key);
+    if (hit != g_tune_cache.end()) {
+      h->primal_variant = hit->second.primal;
+      h->dual_variant = hit->second.dual;
+      memcpy(h->variant_ms, hit->second.ms, sizeof h->variant_ms);
+      h->autotuned = true;
+      return 0;
+    }
+  }
   cudaStream_t st = h->stream;
   Scratch tmp(h);
   const int64_t nx = h->x_len, ny = h->y_len;
@@ -1016,6 +1050,14 @@ int tune_kernels(cpppd_solver *h) {
   cudaEventDestroy(e1);
   if (rc) return rc;
   h->autotuned = true;
+  if (use_cache) {
+    TuneChoice choice;
+    choice.primal = h->primal_variant;
+    choice.dual = h->dual_variant;
+    memcpy(choice.ms, h->variant_ms, sizeof choice.ms);
+    std::lock_guard<std::mutex> lock(g_tune_mutex);
+    g_tune_cache[key] = choice;
+  }
   // back to the initial state: x = x0, xbar = x (:190), y = 0 (:166,:177)
   CK(cudaMemcpyAsync(h->x, x_saved, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(h->xbar, x_saved, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));

@@ -11,6 +11,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <climits>
 #include <cstdarg>
@@ -19,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 

@@ -257,6 +257,30 @@ def test_emulated_autotune_leaves_the_initial_state_untouched(monkeypatch):
     assert np.array_equal(x, xo) and info["autotuned"] == 0 and info["primal_variant"] == 1
 
 
+def test_emulated_autotune_choice_is_remembered_per_operand_shape(monkeypatch):
+    """A second solve on operands of the same shape reuses the measured choice (same timings reported, to the
+    bit); CPPPD_AUTOTUNE_CACHE=0 measures again; another shape is measured on its own."""
+    monkeypatch.setenv("CPPPD_AUTOTUNE_MIN_NNZ", "0")
+    args, g = case_args("sc105")
+
+    def tuned_info(a, **kw):
+        x, _, solver = emulated_chambolle_pock_ppd(*a, nb_max_iter=100, nb_iter_plot=10, **kw)
+        info = solver.info()
+        solver.close()
+        assert np.array_equal(x, g["x_100"]) and info["autotuned"] == 1
+        return info
+
+    first, second = tuned_info(args), tuned_info(args)
+    assert second["variant_ms"] == first["variant_ms"]
+    assert (second["primal_variant"], second["dual_variant"]) == (first["primal_variant"], first["dual_variant"])
+    # SC105 pads by more than 15 % and is renumbered automatically; the caller's numbering gives other operands
+    other_shape = tuned_info(args, flags=_cabi.FLAG_NO_REORDER)
+    assert other_shape["variant_ms"] != first["variant_ms"]
+    monkeypatch.setenv("CPPPD_AUTOTUNE_CACHE", "0")
+    again = tuned_info(args)
+    assert again["variant_ms"] != first["variant_ms"]  # wall-clock timings of a new measurement
+
+
 # thresholds that make a handful of rows / columns long (the emulator runs one CTA of fibers per segment: slow)
 LONG_THRESHOLD = {"l1svm": 64, "sc105": 3, "random_small": 13}
 
