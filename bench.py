@@ -208,6 +208,22 @@ def run_reference(a):
     dt = time.perf_counter() - t0
     its = a.steps * a.ref_iters_per_step / dt * scale
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    del co
+    # beside it: the reference's own arithmetic (scipy csr_matvec / csc_matvec + numpy ufuncs, one thread by
+    # construction) on the same sample — what a PySparseLP user runs today
+    numpy_its = None
+    if a.ref_numpy_iters > 0:
+        from oracle.cpppd_oracle import CpPpdOracle
+
+        o = CpPpdOracle(*generators.lp_args(lp))
+        o.primal_step()
+        o.dual_step()
+        t0 = time.perf_counter()
+        for _ in range(a.ref_numpy_iters):
+            o.primal_step()
+            o.dual_step()
+        numpy_its = a.ref_numpy_iters / (time.perf_counter() - t0) * scale
+        del o
     sample = ("each step = %d iteration(s) of the %dx%d Potts LP (nnz %d) on the CPU, value scaled by nnz ratio %.4f "
               "to the %dx%d workload; plain-C OpenMP oracle port of pysparselp/ChambollePockPPD.py:195-343"
               % (a.ref_iters_per_step, size, size, nnz, scale, a.size, a.size))
@@ -216,7 +232,8 @@ def run_reference(a):
         "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(a),
-        "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": its, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "numpy_scipy_single_thread_value": numpy_its},
         "e2e": {"value": its, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -428,6 +445,8 @@ def main():
     ap.add_argument("--size", type=int, default=4096, help="Potts image side (4096 = BASELINE configs[4])")
     ap.add_argument("--iters-per-step", type=int, default=50)
     ap.add_argument("--ref-iters-per-step", type=int, default=1)
+    ap.add_argument("--ref-numpy-iters", type=int, default=2,
+                    help="--impl reference: iterations of the numpy/scipy restatement timed beside the C port (0: skip)")
     ap.add_argument("--e2e-iters", type=int, default=500)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

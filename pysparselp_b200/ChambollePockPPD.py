@@ -344,9 +344,12 @@ class CpPpdSolver(SolverHandle):
             try:
                 import nvidia.nccl
 
-                cand = os.path.join(os.path.dirname(nvidia.nccl.__file__), "lib", "libnccl.so.2")
-                if os.path.isfile(cand):
-                    os.environ["CPPPD_NCCL_LIB"] = cand
+                # (a namespace package: no __file__, the directories are in __path__)
+                for base in list(getattr(nvidia.nccl, "__path__", [])):
+                    cand = os.path.join(base, "lib", "libnccl.so.2")
+                    if os.path.isfile(cand):
+                        os.environ["CPPPD_NCCL_LIB"] = cand
+                        break
             except Exception:
                 pass
         ident = np.zeros(128, dtype=np.uint8)

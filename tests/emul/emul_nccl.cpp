@@ -11,6 +11,39 @@
 #include "shim/cuda_runtime.h"
 #include "shim/nccl.h"
 
+#ifdef CPPPD_EMUL_FAST_SWITCH
+// Fiber switch of the CUDA emulator (declared in shim/cuda_runtime.h; defined once, here): push the callee-saved
+// registers and the floating point control words, swap the stack pointer, pop them again.  System V x86-64.
+asm(R"(
+.text
+.globl emul_switch
+.type emul_switch,@function
+emul_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    subq $8, %rsp
+    stmxcsr (%rsp)
+    fnstcw 4(%rsp)
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    ldmxcsr (%rsp)
+    fldcw 4(%rsp)
+    addq $8, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emul_switch,.-emul_switch
+)");
+#endif
+
 namespace {
 
 struct Barrier {

@@ -3,9 +3,11 @@
 // tests/emul/make_emul.py rewrites the `kernel<<<grid, block, smem, stream>>>(args)` launches into
 // emul::launch(grid, block, [=] { kernel(args); }) and compiles the result against this header.
 //
-// Execution model: blocks run one after the other; the threads of a block are fibers (ucontext) that are
-// resumed round-robin, so __syncthreads() and the warp shuffles are real rendezvous between the 256
-// "threads" of a CTA.  Streams are synchronous, events are wall-clock, a captured graph is the recorded
+// Execution model: blocks run one after the other; the threads of a block are fibers that are resumed
+// round-robin, so __syncthreads() and the warp shuffles are real rendezvous between the 256 "threads" of a
+// CTA.  On x86-64 a fiber switch is a dozen instructions (emul_switch in emul_nccl.cpp: callee-saved
+// registers and the stack pointer; glibc's swapcontext costs a sigprocmask system call per switch, which
+// dominated the run time of the emulated tests); elsewhere it falls back to ucontext.  Streams are synchronous, events are wall-clock, a captured graph is the recorded
 // list of launches.  All emulator state is thread_local: one OS thread plays one rank ("GPU"), peer memory
 // is the shared address space, and tests/emul/emul_nccl.cpp supplies an in-process NCCL.
 //
@@ -48,8 +50,42 @@ namespace emul {
 constexpr int kMaxThreads = 1024;
 constexpr size_t kStackBytes = 64 * 1024;
 
+#if defined(__x86_64__) && !defined(CPPPD_EMUL_UCONTEXT)
+#define CPPPD_EMUL_FAST_SWITCH 1
+// saves the callee-saved state on the current stack, stores the stack pointer in *save_sp, continues on load_sp
+extern "C" void emul_switch(void **save_sp, void *load_sp);
+struct Context {
+  void *sp = nullptr;
+};
+inline void switch_context(Context &from, Context &to) { emul_switch(&from.sp, to.sp); }
+// a context that starts in `entry` (which never returns) on the given stack
+inline void make_context(Context &c, char *stack, size_t bytes, void (*entry)()) {
+  uintptr_t top = (reinterpret_cast<uintptr_t>(stack) + bytes) & ~(uintptr_t)15;
+  void **sp = reinterpret_cast<void **>(top - 72);  // [mxcsr|fpcw] r15 r14 r13 r12 rbx rbp <return address> <pad>
+  memset(sp, 0, 72);
+  const uint32_t mxcsr = 0x1F80;
+  const uint16_t fpcw = 0x037F;
+  memcpy(reinterpret_cast<char *>(sp), &mxcsr, 4);
+  memcpy(reinterpret_cast<char *>(sp) + 4, &fpcw, 2);
+  sp[7] = reinterpret_cast<void *>(entry);  // `ret` of emul_switch jumps here with rsp = top - 8 (as after a call)
+  c.sp = sp;
+}
+#else
+struct Context {
+  ucontext_t uc;
+};
+inline void switch_context(Context &from, Context &to) { swapcontext(&from.uc, &to.uc); }
+inline void make_context(Context &c, char *stack, size_t bytes, void (*entry)()) {
+  getcontext(&c.uc);
+  c.uc.uc_stack.ss_sp = stack;
+  c.uc.uc_stack.ss_size = bytes;
+  c.uc.uc_link = nullptr;
+  makecontext(&c.uc, entry, 0);
+}
+#endif
+
 struct Fiber {
-  ucontext_t ctx;
+  Context ctx;
   bool done = true;
 };
 
@@ -64,7 +100,7 @@ struct BlockState {
   Rendezvous bar, warp_bar[kMaxThreads / 32];
   unsigned char slot[kMaxThreads][8];
   Fiber fibers[kMaxThreads];
-  ucontext_t main_ctx;
+  Context main_ctx;
   const std::function<void()> *body = nullptr;
   int current = -1;
   char *stacks = nullptr;
@@ -72,7 +108,7 @@ struct BlockState {
 };
 inline thread_local BlockState g_block;
 
-inline void yield() { swapcontext(&g_block.fibers[g_block.current].ctx, &g_block.main_ctx); }
+inline void yield() { switch_context(g_block.fibers[g_block.current].ctx, g_block.main_ctx); }
 
 inline void release_if_complete(Rendezvous &r, int live) {
   if (live > 0 && r.arrived >= live) {
@@ -99,7 +135,8 @@ inline void fiber_entry() {
   b.progress = true;
   release_if_complete(b.bar, b.live);  // threads that exited do not take part in later barriers
   release_if_complete(b.warp_bar[t >> 5], b.warp_live[t >> 5]);
-  swapcontext(&b.fibers[t].ctx, &b.main_ctx);
+  switch_context(b.fibers[t].ctx, b.main_ctx);
+  abort();  // a finished fiber is never resumed
 }
 
 inline void run_block(int nthreads, const std::function<void()> &body) {
@@ -116,11 +153,7 @@ inline void run_block(int nthreads, const std::function<void()> &body) {
     b.warp_live[t >> 5]++;
     Fiber &f = b.fibers[t];
     f.done = false;
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = b.stacks + kStackBytes * t;
-    f.ctx.uc_stack.ss_size = kStackBytes;
-    f.ctx.uc_link = nullptr;
-    makecontext(&f.ctx, fiber_entry, 0);
+    make_context(f.ctx, b.stacks + kStackBytes * t, kStackBytes, fiber_entry);
   }
   while (b.live > 0) {
     b.progress = false;
@@ -128,7 +161,7 @@ inline void run_block(int nthreads, const std::function<void()> &body) {
       if (b.fibers[t].done) continue;
       b.current = t;
       g_threadIdx.x = (unsigned)t;
-      swapcontext(&b.main_ctx, &b.fibers[t].ctx);
+      switch_context(b.main_ctx, b.fibers[t].ctx);
     }
     if (!b.progress && b.live > 0) {
       fprintf(stderr, "emul: dead-lock inside a block (%d threads waiting)\n", b.live);

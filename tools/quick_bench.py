@@ -11,6 +11,7 @@ ap.add_argument("--kind", default="potts")
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--flags", type=int, default=0)
+ap.add_argument("--variant", type=int, default=0, help="kernel_variant (0: autotune); primal | dual << 8")
 a = ap.parse_args()
 t0 = time.time()
 if a.kind == "potts":
@@ -20,13 +21,14 @@ elif a.kind == "random":
 t1 = time.time()
 a_in, b_in = one_sided_rows(lp.a_ineq, lp.b_lower, lp.b_upper)
 A, b, m_eq = stack_operator(lp.a_eq, lp.b_eq, a_in, b_in, lp.c.size)
-s = CpPpdSolver(lp.c, A, m_eq, b, lp.lb, lp.ub, flags=a.flags)
+s = CpPpdSolver(lp.c, A, m_eq, b, lp.lb, lp.ub, flags=a.flags, kernel_variant=a.variant)
 t2 = time.time()
 info = s.info()
 s.iterate(20); s.sync()
 times = [s.time_iterations(a.iters) / a.iters for _ in range(a.reps)]
 ms = float(np.median(times))
-out = dict(kind=a.kind, size=a.size, n=info["n"], m=info["m_eq"] + info["m_ineq"], nnz=info["nnz"],
+kp, kd = [v / 16 for v in s.time_kernels(16)]
+out = dict(kind=a.kind, size=a.size, variant=a.variant, chosen=(info["primal_variant"], info["dual_variant"]), primal_ms=kp, dual_ms=kd, n=info["n"], m=info["m_eq"] + info["m_ineq"], nnz=info["nnz"],
            build_s=round(t1 - t0, 2), setup_s=round(t2 - t1, 2), ms_per_iter=ms, it_per_s=1e3 / ms,
            algo_GBs=info["bytes_per_iteration_algorithmic"] / ms / 1e6,
            actual_GBs=info["bytes_per_iteration_actual"] / ms / 1e6, times=times,
