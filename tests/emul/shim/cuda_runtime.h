@@ -262,7 +262,18 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 4; return cudaSuccess; }  // 4 "SMs"
-inline cudaError_t cudaMalloc(void **p, size_t bytes) { *p = malloc(bytes ? bytes : 1); return *p ? cudaSuccess : cudaErrorEmul; }
+// Device memory is NOT zero-initialised on a GPU (and torch's caching allocator hands out recycled blocks), while
+// a fresh malloc usually is: every allocation is filled with a poison byte so that a kernel relying on zeros fails
+// here too (0x5A: doubles become 5.6e129, int32 indices 1.5e9).  CPPPD_EMUL_POISON=<byte> changes it, -1 disables.
+inline int poison_byte() {
+  static const int v = [] { const char *e = getenv("CPPPD_EMUL_POISON"); return e ? atoi(e) : 0x5A; }();
+  return v;
+}
+inline cudaError_t cudaMalloc(void **p, size_t bytes) {
+  *p = malloc(bytes ? bytes : 1);
+  if (*p && poison_byte() >= 0) memset(*p, poison_byte(), bytes ? bytes : 1);
+  return *p ? cudaSuccess : cudaErrorEmul;
+}
 template <typename T> inline cudaError_t cudaMalloc(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
 inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 template <typename T> inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc((void **)p, bytes); }
