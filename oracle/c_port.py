@@ -80,3 +80,14 @@ class COracle:
                               _p(self.rowidx), _p(self.cval), _p(self.c), _p(self.b), _p(self.lb), _p(self.ub),
                               _p(self.T), _p(self.sigma), C.c_double(self.theta), C.c_double(self.opt),
                               _p(self.x), _p(self.xbar), _p(self.y))
+
+    def primal_step(self):
+        """Primal half of one iteration (reference :198-228): what a callback of that iteration sees in x."""
+        lib().cpppd_c_primal(C.c_int64(self.n), C.c_int64(self.m_eq), self.has_eq, self.has_ineq, _p(self.colptr),
+                             _p(self.rowidx), _p(self.cval), _p(self.y), _p(self.c), _p(self.T), _p(self.lb),
+                             _p(self.ub), C.c_double(self.theta), C.c_double(self.opt), _p(self.x), _p(self.xbar))
+
+    def dual_step(self):
+        """Dual half (reference :231-240, :333-341)."""
+        lib().cpppd_c_dual(C.c_int64(self.m), C.c_int64(self.m_eq), _p(self.rowptr), _p(self.colidx), _p(self.val),
+                           _p(self.xbar), _p(self.b), _p(self.sigma), _p(self.y))

@@ -92,3 +92,26 @@ def test_c_port_bit_exact_vs_reference_golden(name):
     else:
         assert np.array_equal(o.x, g["x_100"]) and np.array_equal(o.y, y_gold)
         assert np.array_equal(o.T, g["diag_t"])
+
+
+@pytest.mark.parametrize("case", ["SC105", "potts50"])
+def test_c_port_reproduces_every_point_of_the_reference_curves(case):
+    """All 83 (SC105, 41 500 iterations) / 55 (Potts 50x50, 27 500 iterations) points of the reference's own golden
+    curves for this path (tests/netlib_curves_SC105.json, tests/test_pott_segmentation_curves.json), through the
+    plain-C port: the callback of a stats iteration k sees x after the primal half of iteration k (:242-329)."""
+    from oracle.c_port import COracle
+
+    with open(os.path.join(GOLDEN, "reference_curves.json")) as f:
+        ref = np.array(json.load(f)[case])
+    args, g = case_args("sc105" if case == "SC105" else "potts50")
+    gt = g["ground_truth"]
+    idx = np.arange(gt.size) if case == "SC105" else np.arange(2500).reshape(50, 50, 1)
+    o = COracle(*args)
+    curve = []
+    for _ in range(len(ref)):
+        o.primal_step()
+        curve.append(float(np.mean(np.abs(gt - o.x[idx]))))
+        o.dual_step()
+        o.iterate(499)
+    np.testing.assert_almost_equal(curve, ref)  # the reference's own tolerance (7 decimals)
+    assert np.max(np.abs(np.array(curve) - ref)) == 0.0
