@@ -124,6 +124,16 @@ struct LoadStream {
   static __device__ __forceinline__ double gather(const double *p) { return __ldg(p); }
   static __device__ __forceinline__ double vec(const Vec &v, int64_t i) { return v.at(i); }
 };
+// LoadPeer: the kernels that carry the halo exchange themselves (kComm) gather ghost entries that a neighbour GPU
+// stores over NVLink WHILE this kernel runs.  L1 is not coherent with those stores: a warp that needs no ghost (and
+// therefore does not wait) may pull the 32-byte sector that holds the last owned entries AND the first ghosts into
+// L1 before the neighbour's store lands, and a later ld.global.nc / .ca of the ghost on the same SM would hit that
+// stale sector.  Gathers therefore go to L2, the point of coherence for peer stores (ld.global.cg).
+struct LoadPeer {
+  template <typename T> static __device__ __forceinline__ T entry(const T *p) { return __ldcs(p); }
+  static __device__ __forceinline__ double gather(const double *p) { return __ldcg(p); }
+  static __device__ __forceinline__ double vec(const Vec &v, int64_t i) { return v.at(i); }
+};
 struct LoadResident {
   template <typename T> static __device__ __forceinline__ T entry(const T *p) { return __ldca(p); }
   static __device__ __forceinline__ double gather(const double *p) { return __ldca(p); }
@@ -283,8 +293,8 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
   const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = j >> 5;
   if (s < AT.nslices)
-    primal_rows<kWriteD, kDict, kChunk, (kChunk > 0 && kMinB <= 6), kComm>(AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq,
-                                                                          has_ineq, theta, one_plus_theta, cm, sdict, j, s);
+    primal_rows<kWriteD, kDict, kChunk, (kChunk > 0 && kMinB <= 6), kComm, typename std::conditional<kComm, LoadPeer, LoadStream>::type>(
+        AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta, one_plus_theta, cm, sdict, j, s);
   if (kComm) comm_finish(cm);  // every thread of the CTA gets here (no early return above)
 }
 
@@ -329,7 +339,9 @@ k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__
   }
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = i >> 5;
-  if (s < A.nslices) dual_rows<kDict, kChunk, kComm>(A, xbar, b, sigma, y, m, m_eq, cm, sdict, i, s);
+  if (s < A.nslices)
+    dual_rows<kDict, kChunk, kComm, typename std::conditional<kComm, LoadPeer, LoadStream>::type>(A, xbar, b, sigma, y, m, m_eq, cm,
+                                                                                               sdict, i, s);
   if (kComm) comm_finish(cm);
 }
 

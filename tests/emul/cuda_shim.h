@@ -31,6 +31,7 @@ inline void __syncthreads() { if (g_emul_stop_at_barrier) throw EmulBarrier(); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldca(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
