@@ -20,6 +20,13 @@
  *     unless the function says it synchronises;
  *   - there is NO CPU fallback: without a CUDA device cpppd_create() fails.
  *
+ * Environment variables read by the library (all optional)
+ *   CPPPD_NCCL_LIB          path of the libnccl.so.2 to dlopen (world_size > 1 only)
+ *   CPPPD_HALO_TIMEOUT_S    seconds a peer-memory halo wait may spin before CPPPD_ERR_COMM (default 60, 0: for ever)
+ *   CPPPD_KERNEL_VARIANT    like cpppd_problem.kernel_variant when that field is 0
+ *   CPPPD_AUTOTUNE_MIN_NNZ  smallest operand (entries) whose kernel variants are timed at creation (default 2^22)
+ *   CPPPD_AUTOTUNE_CACHE    0: time the variants at every creation instead of once per operand shape and process
+ *
  * Problem statement (reference ChambollePockPPD.py:55-65 after the one-sided
  * conversion of :74-88, which stays in Python):
  *     min c.x   s.t.  A[0:m_eq] x = b[0:m_eq],   A[m_eq:m] x <= b[m_eq:m],   lb <= x <= ub
@@ -64,7 +71,7 @@ enum {
   /* compress matrix values through a dictionary when they take few distinct values
    * (bit-exact: the dictionary holds the original doubles) */
   CPPPD_FLAG_VALUE_DICT = 1u << 0,
-  /* replace constant vectors (b, sigma, lb, ub) by scalars inside the kernels */
+  /* replace constant vectors (b, sigma, lb, ub, c, T) by scalars inside the kernels */
   CPPPD_FLAG_CONST_VECTORS = 1u << 1,
   /* do not capture the inner iterations into CUDA graphs */
   CPPPD_FLAG_NO_GRAPH = 1u << 2,
@@ -98,10 +105,10 @@ typedef struct {
   int64_t m_ineq;       /* inequality rows: rows [m_eq, m_eq + m_ineq) */
   int64_t nnz;          /* stored entries (explicit zeros count, as in scipy) */
   const void *indptr;   /* m+1 row pointers, int32 or int64 */
-  const void *indices;  /* nnz column indices, int32 or int64 */
+  const void *indices;  /* nnz column indices, int32 (wider indices are narrowed by the host front) */
   const double *values; /* nnz values */
   int32_t indptr_bits;  /* 32 or 64 */
-  int32_t index_bits;   /* 32 or 64 */
+  int32_t index_bits;   /* must be 32 */
   const double *c;      /* n   costs                           (ChambollePockPPD.py:198)   */
   const double *b;      /* m   right-hand sides [b_eq; b_ineq] (:235,:240)                 */
   const double *lb;     /* n   lower bounds, -inf allowed      (:221)                      */
@@ -164,8 +171,8 @@ typedef struct {
   int64_t device_bytes;      /* resident device memory of the solver state */
   int64_t bytes_per_iteration_algorithmic; /* 2*nnz*12 + P(m+1) + P(n+1) + 8(8n+5m) */
   int64_t bytes_per_iteration_actual;      /* what the kernels of this handle really stream    */
-  int32_t value_bytes;       /* bytes per stored matrix value (8, or 1/2 with a dictionary)    */
-  int32_t const_vector_mask; /* bit0 b, bit1 sigma, bit2 lb, bit3 ub folded to scalars         */
+  int32_t value_bytes;       /* bytes per stored matrix value: 8, or 0 with a dictionary (the code lives in the index word) */
+  int32_t const_vector_mask; /* bit0 b, bit1 sigma, bit2 lb, bit3 ub, bit4 c, bit5 T folded to scalars */
   int32_t sm_count;
   int32_t world_size;
   int32_t rank;
@@ -176,7 +183,8 @@ typedef struct {
   int64_t halo_send_bytes_per_iteration; /* bytes this rank sends per iteration (xbar + y halos)    */
   int64_t partition_granule;
   int32_t dual_variant;      /* kernel variant in use for k_dual (1-based) */
-  int32_t autotuned;         /* 1 when the variants were timed at creation */
+  int32_t autotuned;         /* 1 when the variants were chosen by timing (at this creation, or at an earlier one
+                                of operands of the same shape in this process) */
   /* milliseconds per launch measured at creation for k_primal ([0][v-1]) and k_dual ([1][v-1]); 0 = not timed */
   float variant_ms[2][CPPPD_KERNEL_VARIANTS];
   int64_t long_rows, long_cols; /* rows / columns handled by the long-row path on this rank */
