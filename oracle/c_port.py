@@ -16,12 +16,31 @@ LIB = os.path.join(_HERE, "_build", "libcpppd_oracle.so")
 _lib = None
 
 
+def _cpu_signature():
+    """The library is built with -march=native and travels with the repo snapshot (built files are not
+    git-tracked but are shipped to the GPU box): rebuild when the host CPU is not the one it was built on."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " ".join(sorted(line.split(":", 1)[1].split()))
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force=False):
-    if not force and os.path.isfile(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+    stamp = LIB + ".cpu"
+    sig = _cpu_signature()
+    fresh = os.path.isfile(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC)
+    same_cpu = os.path.isfile(stamp) and open(stamp).read() == sig
+    if not force and fresh and same_cpu:
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = ["gcc", "-O3", "-march=native", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", LIB, SRC, "-lm"]
     subprocess.run(cmd, check=True, capture_output=True)
+    with open(stamp, "w") as f:
+        f.write(sig)
     return LIB
 
 
