@@ -156,10 +156,14 @@ def pack_lp(args):
     return d
 
 
-def main():
+def main(only=()):
+    """Mint every golden, or only the named cases (``python -m oracle.make_golden kb2 sc50a``)."""
     os.makedirs(GOLDEN, exist_ok=True)
     ref_loader.load_reference()
     import importlib
+
+    def want(name):
+        return not only or name in only
 
     from pysparselp_b200 import generators
     from pysparselp_b200.examples import example_l1_svm as my_svm
@@ -180,14 +184,15 @@ def main():
     g = generators.potts_lp(50)
     assert_same_args(args, (g.c, sp.csr_matrix((0, g.c.size)), np.empty(0), g.a_ineq,
                             np.full(g.b_upper.size, -np.inf), g.b_upper, g.lb, g.ub))
-    mint("potts50", args, extra=dict(ground_truth=gt_ref))
+    if want("potts50"):
+        mint("potts50", args, extra=dict(ground_truth=gt_ref))
 
     # ---- C2: netlib SC105 (reference tests/test_netlib.py:19-48)
     ref_netlib = importlib.import_module("pysparselp.netlib")
     ref_slp = ref_loader.reference_sparse_lp()
 
-    def sc105(get_problem, cls):
-        d = get_problem("SC105")
+    def netlib_lp(get_problem, cls, problem):
+        d = get_problem(problem)
         gt = d["solution"]
         lp = cls()
         lp.add_variables_array(len(d["cost_vector"]), lower_bounds=d["lower_bounds"],
@@ -198,13 +203,18 @@ def main():
         lp.convert_to_one_sided_inequality_system()
         return lp, gt
 
-    with quiet:
-        lp_ref, gt_ref = sc105(ref_netlib.get_problem, ref_slp.SparseLP)
-    lp_my, gt_my = sc105(my_get_problem, MySparseLP)
-    args = solver_args_from_lp(lp_ref)
-    assert_same_args(args, solver_args_from_lp(lp_my))
-    assert np.array_equal(gt_ref, gt_my)
-    mint("sc105", args, extra=dict(ground_truth=gt_ref, **pack_lp(args)))
+    # SC105 is the case the reference tests; the other problems it vendors (AFIRO, KB2 — the one with a BOUNDS
+    # section —, SC50A, SC50B) go through the same preparation: MPS parser -> modeling layer -> solver
+    for problem in ("SC105", "AFIRO", "KB2", "SC50A", "SC50B"):
+        if not want(problem.lower()):
+            continue
+        with quiet:
+            lp_ref, gt_ref = netlib_lp(ref_netlib.get_problem, ref_slp.SparseLP, problem)
+        lp_my, gt_my = netlib_lp(my_get_problem, MySparseLP, problem)
+        args = solver_args_from_lp(lp_ref)
+        assert_same_args(args, solver_args_from_lp(lp_my))
+        assert np.array_equal(gt_ref, gt_my)
+        mint(problem.lower(), args, extra=dict(ground_truth=gt_ref, **pack_lp(args)))
 
     # ---- L1-SVM 1000 x 2 (reference example_l1_svm.py:91-113)
     ref_svm = importlib.import_module("pysparselp.examples.example_l1_svm")
@@ -218,7 +228,8 @@ def main():
     g, _ = generators.l1svm_lp(1000, 2)
     assert_same_args(args, (g.c, sp.csr_matrix((0, g.c.size)), np.empty(0), g.a_ineq, g.b_lower, g.b_upper,
                             g.lb, g.ub))
-    mint("l1svm", args)
+    if want("l1svm"):
+        mint("l1svm", args)
 
     # ---- small random LP with equalities, two-sided rows, infinite bounds and an x0-free start
     rng = np.random.default_rng(7)
@@ -241,10 +252,14 @@ def main():
     ub[rng.random(n) < 0.1] = np.inf
     c = np.round(rng.standard_normal(n), 2)
     args = (c, a_eq, beq, a_in, b_lo, b_up, lb, ub)
-    mint("random_small", args, extra=pack_lp(args))
-    mint("random_small_alpha", args, extra=pack_lp(args), alpha=1.5, theta=0.7)
+    if want("random_small"):
+        mint("random_small", args, extra=pack_lp(args))
+    if want("random_small_alpha"):
+        mint("random_small_alpha", args, extra=pack_lp(args), alpha=1.5, theta=0.7)
 
     # ---- the reference's own goldens for the path
+    if not want("reference_curves"):
+        return
     curves = {}
     for key, fname in (("SC105", "netlib_curves_SC105.json"), ("potts50", "test_pott_segmentation_curves.json"),
                        ("l1svm", "test_l1_svm_results.json")):
@@ -256,4 +271,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(only=set(sys.argv[1:]))

@@ -81,5 +81,7 @@ def case_args(name):
     return args, g
 
 
-GOLDEN_CASES = ["potts50", "sc105", "l1svm", "random_small", "random_small_alpha"]
+# potts50 / sc105 / l1svm: the LPs of the reference's own regression tests; afiro, kb2 (the one with a BOUNDS section),
+# sc50a, sc50b: the other netlib problems the reference vendors, through MPS parser -> modeling layer -> solver
+GOLDEN_CASES = ["potts50", "sc105", "l1svm", "random_small", "random_small_alpha", "afiro", "kb2", "sc50a", "sc50b"]
 CASE_PARAMS = {"random_small_alpha": dict(alpha=1.5, theta=0.7)}

@@ -190,6 +190,30 @@ def test_netlib_sc105_shapes_and_solution():
         get_problem("NOPE")
 
 
+@pytest.mark.parametrize("problem", ["SC105", "AFIRO", "KB2", "SC50A", "SC50B"])
+def test_netlib_problems_reach_the_solver_as_the_reference_builds_them(problem):
+    """MPS parser -> modeling layer -> one-sided conversion -> remove_fixed_variables, as reference
+    tests/test_netlib.py:19-48 prepares a netlib LP: the solver inputs must hash to the digest recorded when the
+    golden was minted from the unmodified reference (oracle/make_golden.py asserted array equality then)."""
+    from conftest import load_golden, solver_args_from_lp
+    from oracle.make_golden import lp_digest
+    from pysparselp_b200.netlib import get_problem
+    from pysparselp_b200.SparseLP import SparseLP
+
+    d = get_problem(problem)
+    gt = d["solution"]
+    lp = SparseLP()
+    lp.add_variables_array(len(d["cost_vector"]), lower_bounds=d["lower_bounds"],
+                           upper_bounds=np.minimum(d["upper_bounds"], np.max(gt) * 2), costs=d["cost_vector"])
+    lp.add_equality_constraints_sparse(d["a_eq"], d["b_eq"])
+    lp.add_inequality_constraints_sparse(d["a_ineq"], d["b_lower"], d["b_upper"])
+    lp.convert_to_one_sided_inequality_system()
+    assert lp.check_solution(gt)
+    g = load_golden(problem.lower())
+    assert lp_digest(solver_args_from_lp(lp)) == bytes(g["digest"]).decode()
+    assert np.array_equal(gt, g["ground_truth"])
+
+
 @pytest.mark.parametrize("size", [7, 50])
 def test_potts_generator_matches_modeling_layer(size):
     from pysparselp_b200 import generators
