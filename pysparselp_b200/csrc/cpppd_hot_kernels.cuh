@@ -357,8 +357,8 @@ k_tiny_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, Vec
                int64_t n, int64_t m, int64_t m_eq, int has_eq, int has_ineq, double theta, double one_plus_theta,
                int64_t iters) {
   __shared__ double sdict[kDict ? 256 : 1];
-  if (kDict) {
-    if ((int)threadIdx.x < AT.ndict) sdict[threadIdx.x] = AT.dict[threadIdx.x];
+  if (kDict) {  // (the CTA may have fewer threads than the dictionary has entries)
+    for (int t = threadIdx.x; t < AT.ndict; t += blockDim.x) sdict[t] = AT.dict[t];
     __syncthreads();
   }
   const int64_t cols = AT.nslices * kSlice, rows = A.nslices * kSlice;

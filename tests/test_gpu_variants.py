@@ -89,7 +89,8 @@ def test_autotune_is_on_by_default_for_large_operands():
         solver.close()
 
 
-@pytest.mark.parametrize("name", ["sc105", "random_small", "random_small_alpha"])
+# (kb2: 146 distinct values but a CTA of 64 threads — the dictionary is staged in a loop)
+@pytest.mark.parametrize("name", ["sc105", "random_small", "random_small_alpha", "kb2", "afiro"])
 def test_tiny_persistent_kernel_gives_the_same_bits(name):
     """CPPPD_FLAG_TINY_PERSISTENT: all iterations between two stats blocks in one launch of one CTA."""
     from pysparselp_b200 import _cabi

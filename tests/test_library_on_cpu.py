@@ -355,7 +355,8 @@ def test_emulated_long_rows_with_segments_and_force_integer():
     assert np.array_equal(x3, g["x_100"])
 
 
-@pytest.mark.parametrize("name", ["sc105", "random_small", "random_small_alpha"])
+# (kb2: 146 distinct values but a CTA of 64 threads — the dictionary is staged in a loop)
+@pytest.mark.parametrize("name", ["sc105", "random_small", "random_small_alpha", "kb2", "afiro"])
 @pytest.mark.parametrize("flags", [_cabi.FLAG_TINY_PERSISTENT,
                                    _cabi.FLAG_TINY_PERSISTENT | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS | _cabi.FLAG_REORDER])
 def test_emulated_tiny_persistent_kernel(name, flags):
