@@ -32,7 +32,7 @@ def solve_on_ranks(args, world, flags, nb_max_iter, nb_iter_plot, force_integer=
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("transport", list(TRANSPORTS))
 @pytest.mark.parametrize("world", [2, 3])
-@pytest.mark.parametrize("name", ["potts50", "sc105", "random_small"])
+@pytest.mark.parametrize("name", ["potts50", "sc105", "random_small", "afiro", "kb2"])
 def test_multi_rank_iterates_bit_identical(name, world, transport):
     args, g = case_args(name)
     kw = CASE_PARAMS.get(name, {})
