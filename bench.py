@@ -421,7 +421,8 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
-VARIANT_NAMES = ("loop-unroll4/8cta", "chunk2/8cta", "chunk4/6cta", "chunk4/4cta", "chunk8/4cta")
+VARIANT_NAMES = ("loop-unroll4/8cta", "chunk2/8cta", "chunk4/6cta", "chunk4/4cta", "chunk8/4cta", "rows2-chunk4/3cta",
+                 "rows2-chunk2/4cta")
 
 
 def kernel_variants(info):

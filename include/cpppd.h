@@ -43,9 +43,9 @@
 extern "C" {
 #endif
 
-#define CPPPD_ABI_VERSION 5
+#define CPPPD_ABI_VERSION 6
 
-#define CPPPD_KERNEL_VARIANTS 5
+#define CPPPD_KERNEL_VARIANTS 7
 
 typedef struct cpppd_solver *cpppd_handle;
 
@@ -123,7 +123,7 @@ typedef struct {
                              their own operands during cpppd_create and keep the fastest, smaller ones use
                              variant 1.  Otherwise bits 0-7 force the variant of k_primal and bits 8-15 that of
                              k_dual (1 .. CPPPD_KERNEL_VARIANTS; bits 8-15 zero: same as k_primal).  All
-                             variants produce bit-identical iterates; they differ in loads kept in flight. */
+                             variants produce bit-identical iterates; they differ in loads kept in flight (variants 6 and 7 walk two rows per lane). */
   cpppd_alloc_fn alloc; /* may be NULL */
   cpppd_free_fn free;   /* may be NULL */
   void *alloc_user;

@@ -10,8 +10,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
-ABI_VERSION = 5
-KERNEL_VARIANTS = 5
+ABI_VERSION = 6
+KERNEL_VARIANTS = 7
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)

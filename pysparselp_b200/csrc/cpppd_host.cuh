@@ -936,8 +936,10 @@ int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
   if (h->AT.nslices) {
     const bool dict = h->AT.dict != nullptr;
     const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-    PrimalFn fn = cm ? primal_kernel_fused(write_d, dict) : primal_kernel(write_d, dict, variant >= 0 ? variant : h->primal_variant);
-    fn<<<grid_for(h->AT.nslices * 32), kBlock, 0, h->stream>>>(view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar,
+    const int v = cm ? 0 : (variant >= 0 ? variant : h->primal_variant);
+    PrimalFn fn = cm ? primal_kernel_fused(write_d, dict) : primal_kernel(write_d, dict, v);
+    const int64_t warps = (h->AT.nslices + kVariants[v].rows - 1) / kVariants[v].rows;  // a warp walks `rows` slices
+    fn<<<grid_for(warps * 32), kBlock, 0, h->stream>>>(view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar,
                                                               h->dbuf, h->n, has_eq, has_ineq, h->theta, h->one_plus_theta, cm);
   }
   if (cm || variant >= 0) return 0;
@@ -950,8 +952,10 @@ int launch_dual(cpppd_solver *h, int variant = -1) {
   if (int rc = long_pass(h, h->longA, h->xbar, h->xbar)) return rc;  // long rows: their A xbar into the tail of xbar
   if (h->A.nslices) {
     const bool dict = h->A.dict != nullptr;
-    DualFn fn = cm ? dual_kernel_fused(dict) : dual_kernel(dict, variant >= 0 ? variant : h->dual_variant);
-    fn<<<grid_for(h->A.nslices * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
+    const int v = cm ? 0 : (variant >= 0 ? variant : h->dual_variant);
+    DualFn fn = cm ? dual_kernel_fused(dict) : dual_kernel(dict, v);
+    const int64_t warps = (h->A.nslices + kVariants[v].rows - 1) / kVariants[v].rows;
+    fn<<<grid_for(warps * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
   }
   if (cm || variant >= 0) return 0;
   return pp.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);

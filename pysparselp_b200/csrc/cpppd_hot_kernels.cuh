@@ -228,6 +228,162 @@ __device__ __forceinline__ double dual_sum(const SellView &A, const double *__re
   return acc;
 }
 
+// ---- two rows per thread -------------------------------------------------------------------------------------
+// A warp takes TWO consecutive slices (rows 64w + lane and 64w + 32 + lane) and walks them in lock step, kChunk
+// entries of each at a time: twice the independent loads in flight per thread for the short rows of the Potts LP
+// (3 entries per row, 2 per edge column), where one row per thread leaves a lane with a single short dependent
+// chain.  Each row is still summed alone, sequentially, in stored order — same bits as every other variant.
+template <bool kDict, int kChunk, typename L = LoadStream>
+__device__ __forceinline__ void primal_sums2(const SellView &AT, const double *__restrict__ y, const double *sdict,
+                                             int64_t pa0, int64_t pa1, int64_t pb0, int64_t pb1, int lane,
+                                             double (&s_eq)[2], double (&s_in)[2]) {
+  const int32_t *ip[2] = {AT.idx + pa0 + lane, AT.idx + pb0 + lane};
+  const double *vp[2] = {AT.val + pa0 + lane, AT.val + pb0 + lane};
+  const int width[2] = {(int)((pa1 - pa0) >> 5), (int)((pb1 - pb0) >> 5)};
+  const int widest = width[0] > width[1] ? width[0] : width[1];
+  const int32_t mask = AT.idx_mask;
+  constexpr int kC = kChunk > 0 ? kChunk : 1;
+#pragma unroll 1
+  for (int k0 = 0; k0 < widest; k0 += kC) {
+    int32_t r[2][kC];
+    double a[2][kC], g[2][kC];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const bool ok = k0 + u < width[q];
+        r[q][u] = ok ? L::entry(ip[q] + (k0 + u) * kSlice) : kPad;
+        a[q][u] = (!kDict && ok) ? L::entry(vp[q] + (k0 + u) * kSlice) : 0.0;
+      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < kC; ++u) g[q][u] = r[q][u] >= 0 ? L::gather(y + (r[q][u] & mask)) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        if (r[q][u] >= 0) {
+          const double av = kDict ? sdict[(r[q][u] >> AT.idx_bits) & AT.code_mask] : a[q][u];
+          const double t = __dmul_rn(av, g[q][u]);
+          if (r[q][u] & kEqBit) s_eq[q] = __dadd_rn(s_eq[q], t); else s_in[q] = __dadd_rn(s_in[q], t);
+        }
+      }
+  }
+}
+
+template <bool kDict, int kChunk, typename L = LoadStream>
+__device__ __forceinline__ void dual_sum2(const SellView &A, const double *__restrict__ xbar, const double *sdict,
+                                          int64_t pa0, int64_t pa1, int64_t pb0, int64_t pb1, int lane,
+                                          double (&acc)[2]) {
+  const int32_t *ip[2] = {A.idx + pa0 + lane, A.idx + pb0 + lane};
+  const double *vp[2] = {A.val + pa0 + lane, A.val + pb0 + lane};
+  const int width[2] = {(int)((pa1 - pa0) >> 5), (int)((pb1 - pb0) >> 5)};
+  const int widest = width[0] > width[1] ? width[0] : width[1];
+  const int32_t mask = A.idx_mask;
+  constexpr int kC = kChunk > 0 ? kChunk : 1;
+#pragma unroll 1
+  for (int k0 = 0; k0 < widest; k0 += kC) {
+    int32_t jc[2][kC];
+    double a[2][kC], g[2][kC];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        const bool ok = k0 + u < width[q];
+        jc[q][u] = ok ? L::entry(ip[q] + (k0 + u) * kSlice) : kPad;
+        a[q][u] = (!kDict && ok) ? L::entry(vp[q] + (k0 + u) * kSlice) : 0.0;
+      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < kC; ++u) g[q][u] = jc[q][u] >= 0 ? L::gather(xbar + (jc[q][u] & mask)) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int u = 0; u < kC; ++u) {
+        if (jc[q][u] >= 0) {
+          const double av = kDict ? sdict[(jc[q][u] >> A.idx_bits) & A.code_mask] : a[q][u];
+          acc[q] = __dadd_rn(acc[q], __dmul_rn(av, g[q][u]));
+        }
+      }
+  }
+}
+
+// k_primal for the two columns 64w + lane and 64w + 32 + lane of warp w
+template <bool kWriteD, bool kDict, int kChunk, typename L = LoadStream>
+__device__ __forceinline__ void primal_rows2(const SellView &AT, const double *__restrict__ y, const Vec &c, const Vec &T,
+                                             const Vec &lb, const Vec &ub, double *__restrict__ x,
+                                             double *__restrict__ xbar, double *__restrict__ d_out, int64_t n,
+                                             int has_eq, int has_ineq, double theta, double one_plus_theta,
+                                             const double *sdict, int64_t w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t sa = 2 * w, sb = sa + 1;
+  if (sa >= AT.nslices) return;
+  int64_t p0[2] = {0, 0}, p1[2] = {0, 0};
+  slice_range(AT, sa, p0[0], p1[0]);
+  if (sb < AT.nslices) slice_range(AT, sb, p0[1], p1[1]);
+  const int64_t j[2] = {sa * kSlice + lane, sb * kSlice + lane};
+  const bool live[2] = {j[0] < n, j[1] < n};  // (a missing second slice starts at or behind n)
+  double cj[2] = {0.0, 0.0}, tj[2] = {0.0, 0.0}, xo[2] = {0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    if (live[q]) {
+      cj[q] = L::vec(c, j[q]);
+      tj[q] = L::vec(T, j[q]);
+      xo[q] = L::entry(x + j[q]);
+    }
+  double s_eq[2] = {0.0, 0.0}, s_in[2] = {0.0, 0.0};
+  primal_sums2<kDict, kChunk, L>(AT, y, sdict, p0[0], p1[0], p0[1], p1[1], lane, s_eq, s_in);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (!live[q]) continue;
+    double d = cj[q];
+    if (has_eq) d = __dadd_rn(d, s_eq[q]);
+    if (has_ineq) d = __dadd_rn(d, s_in[q]);
+    const double l = L::vec(lb, j[q]), u = L::vec(ub, j[q]);
+    double x2 = __dsub_rn(xo[q], __dmul_rn(tj[q], d));
+    x2 = (l > x2) ? l : x2;
+    x2 = (u < x2) ? u : x2;
+    xbar[j[q]] = __dsub_rn(__dmul_rn(one_plus_theta, x2), __dmul_rn(theta, xo[q]));
+    x[j[q]] = x2;
+    if (kWriteD) d_out[j[q]] = d;
+  }
+}
+
+// k_dual for the two rows 64w + lane and 64w + 32 + lane of warp w
+template <bool kDict, int kChunk, typename L = LoadStream>
+__device__ __forceinline__ void dual_rows2(const SellView &A, const double *__restrict__ xbar, const Vec &b,
+                                           const Vec &sigma, double *__restrict__ y, int64_t m, int64_t m_eq,
+                                           const double *sdict, int64_t w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t sa = 2 * w, sb = sa + 1;
+  if (sa >= A.nslices) return;
+  int64_t p0[2] = {0, 0}, p1[2] = {0, 0};
+  slice_range(A, sa, p0[0], p1[0]);
+  if (sb < A.nslices) slice_range(A, sb, p0[1], p1[1]);
+  const int64_t i[2] = {sa * kSlice + lane, sb * kSlice + lane};
+  const bool live[2] = {i[0] < m, i[1] < m};
+  double bi[2] = {0.0, 0.0}, si[2] = {0.0, 0.0}, yi[2] = {0.0, 0.0};
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    if (live[q]) {
+      bi[q] = L::vec(b, i[q]);
+      si[q] = L::vec(sigma, i[q]);
+      yi[q] = L::entry(y + i[q]);
+    }
+  double acc[2] = {0.0, 0.0};
+  dual_sum2<kDict, kChunk, L>(A, xbar, sdict, p0[0], p1[0], p0[1], p1[1], lane, acc);
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (!live[q]) continue;
+    const double r = __dsub_rn(acc[q], bi[q]);
+    double yn = __dadd_rn(yi[q], __dmul_rn(si[q], r));
+    if (i[q] >= m_eq) yn = (yn < 0.0) ? 0.0 : yn;
+    y[i[q]] = yn;
+  }
+}
+
 // body of k_primal for one thread (column j of slice s)
 template <bool kWriteD, bool kDict, int kChunk, bool kEarlyBounds, bool kComm, typename L = LoadStream>
 __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__restrict__ y, const Vec &c, const Vec &T,
@@ -280,7 +436,7 @@ __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__
 // kDict: entries are single 32-bit words [pad][eq][code][index]; values come from a <= 256 entry
 // dictionary staged in shared memory.
 // kComm: the halo exchange is done by the kernel itself (see FusedComm); cm is not touched otherwise.
-template <bool kWriteD, bool kDict, int kChunk, int kMinB, bool kComm>
+template <bool kWriteD, bool kDict, int kChunk, int kMinB, bool kComm, int kRows = 1>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
          double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int has_eq, int has_ineq,
@@ -292,7 +448,10 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
   }
   const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = j >> 5;
-  if (s < AT.nslices)
+  if constexpr (kRows == 2) {  // warp s takes slices 2s and 2s + 1 (the grid covers half as many warps)
+    primal_rows2<kWriteD, kDict, kChunk>(AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta, one_plus_theta,
+                                         sdict, s);
+  } else if (s < AT.nslices)
     primal_rows<kWriteD, kDict, kChunk, (kChunk > 0 && kMinB <= 6), kComm, typename std::conditional<kComm, LoadPeer, LoadStream>::type>(
         AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta, one_plus_theta, cm, sdict, j, s);
   if (kComm) comm_finish(cm);  // every thread of the CTA gets here (no early return above)
@@ -328,7 +487,7 @@ __device__ __forceinline__ void dual_rows(const SellView &A, const double *__res
 }
 
 // Dual half-iteration (:231-240, :333-341).  Thread i owns row i of A.
-template <bool kDict, int kChunk, int kMinB, bool kComm>
+template <bool kDict, int kChunk, int kMinB, bool kComm, int kRows = 1>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__restrict__ y, int64_t m,
        int64_t m_eq, const FusedComm *__restrict__ cm) {
@@ -339,7 +498,9 @@ k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__
   }
   const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t s = i >> 5;
-  if (s < A.nslices)
+  if constexpr (kRows == 2) {
+    dual_rows2<kDict, kChunk>(A, xbar, b, sigma, y, m, m_eq, sdict, s);
+  } else if (s < A.nslices)
     dual_rows<kDict, kChunk, kComm, typename std::conditional<kComm, LoadPeer, LoadStream>::type>(A, xbar, b, sigma, y, m, m_eq, cm,
                                                                                                sdict, i, s);
   if (kComm) comm_finish(cm);
@@ -377,13 +538,14 @@ k_tiny_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, Vec
 // variant table
 // ------------------------------------------------------------------------------------------
 struct HotVariant {
-  int chunk, min_blocks;
+  int chunk, min_blocks, rows;  // rows: slices (rows per lane) a warp walks in lock step; the grid shrinks accordingly
   const char *name;
 };
 // index 0 is the variant every other one is measured against (and the one used without tuning)
-constexpr int kNumVariants = 5;
+constexpr int kNumVariants = 7;
 constexpr HotVariant kVariants[kNumVariants] = {
-    {0, 8, "loop-unroll4/8cta"}, {2, 8, "chunk2/8cta"}, {4, 6, "chunk4/6cta"}, {4, 4, "chunk4/4cta"}, {8, 4, "chunk8/4cta"}};
+    {0, 8, 1, "loop-unroll4/8cta"}, {2, 8, 1, "chunk2/8cta"},        {4, 6, 1, "chunk4/6cta"},       {4, 4, 1, "chunk4/4cta"},
+    {8, 4, 1, "chunk8/4cta"},       {4, 3, 2, "rows2-chunk4/3cta"}, {2, 4, 2, "rows2-chunk2/4cta"}};
 
 using PrimalFn = void (*)(SellView, const double *, Vec, Vec, Vec, Vec, double *, double *, double *, int64_t, int, int,
                           double, double, const FusedComm *);
@@ -396,6 +558,8 @@ PrimalFn primal_variant(int v) {
     case 2: return k_primal<kWriteD, kDict, 4, 6, false>;
     case 3: return k_primal<kWriteD, kDict, 4, 4, false>;
     case 4: return k_primal<kWriteD, kDict, 8, 4, false>;
+    case 5: return k_primal<kWriteD, kDict, 4, 3, false, 2>;
+    case 6: return k_primal<kWriteD, kDict, 2, 4, false, 2>;
     default: return k_primal<kWriteD, kDict, 0, 8, false>;
   }
 }
@@ -406,6 +570,8 @@ DualFn dual_variant(int v) {
     case 2: return k_dual<kDict, 4, 6, false>;
     case 3: return k_dual<kDict, 4, 4, false>;
     case 4: return k_dual<kDict, 8, 4, false>;
+    case 5: return k_dual<kDict, 4, 3, false, 2>;
+    case 6: return k_dual<kDict, 2, 4, false, 2>;
     default: return k_dual<kDict, 0, 8, false>;
   }
 }

@@ -31,7 +31,7 @@ def test_struct_layout_matches_header():
 
     # spot checks of the C layout (x86-64 SysV): sizes computed by hand from include/cpppd.h
     assert C.sizeof(_cabi.Stats) == 8 + 11 * 8 + 4 * 4
-    assert C.sizeof(_cabi.Info) == 9 * 8 + 6 * 4 + 9 * 8 + 2 * 4 + 2 * 5 * 4 + 3 * 8 + 2 * 4
+    assert C.sizeof(_cabi.Info) == 9 * 8 + 6 * 4 + 9 * 8 + 2 * 4 + 2 * _cabi.KERNEL_VARIANTS * 4 + 3 * 8 + 2 * 4
     assert _cabi.Problem.indptr.offset == 40 and _cabi.Problem.alpha.offset == 112
     assert _cabi.Problem.rank.offset == 176 and C.sizeof(_cabi.Problem) == 216
 

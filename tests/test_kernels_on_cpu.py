@@ -4,6 +4,8 @@ like the GPU parity tests — this is the kernel logic, run without a GPU."""
 import numpy as np
 import pytest
 
+from pysparselp_b200 import _cabi
+
 from conftest import CASE_PARAMS, GOLDEN_CASES, case_args
 from emul.harness import EmulSolver, lib
 
@@ -19,7 +21,7 @@ def test_emulator_sees_every_kernel_variant():
     assert lib().emul_num_variants() == _cabi.KERNEL_VARIANTS
 
 
-@pytest.mark.parametrize("variant", range(5))
+@pytest.mark.parametrize("variant", range(_cabi.KERNEL_VARIANTS))
 @pytest.mark.parametrize("compressed", [False, True])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_hot_kernels_bit_exact_on_cpu(name, compressed, variant):
@@ -58,7 +60,7 @@ def test_hot_kernels_with_x0_and_ragged_sizes():
     args = (c, sp.csr_matrix((0, n)), np.empty(0), a, None, b_up, lb, ub)
     st = {}
     xo, _ = chambolle_pock_ppd_oracle(*args, x0=x0, nb_max_iter=60, nb_iter_plot=10**6, state_out=st)
-    for variant in range(5):
+    for variant in range(_cabi.KERNEL_VARIANTS):
         s = EmulSolver(*args, x0=x0, variant=variant)
         s.iterate(60)
         assert np.array_equal(s.x, xo) and np.array_equal(s.y, st["y_ineq"]) and np.array_equal(s.xbar, st["xbar"])

@@ -206,7 +206,7 @@ def test_solve_curves_on_device_equal_host_curves(case, monkeypatch):
     np.testing.assert_almost_equal(cd["distance_to_ground_truth"], golden[: len(cd["distance_to_ground_truth"])])
 
 
-@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 3 | (5 << 8)])
+@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 6, 7, 3 | (5 << 8), 7 | (6 << 8)])
 @pytest.mark.parametrize("flags", [0, _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS])
 def test_emulated_every_kernel_variant_gives_the_same_bits(kernel_variant, flags):
     """cpppd_problem.kernel_variant forces one of the compiled variants of k_primal / k_dual; the arithmetic of
@@ -248,7 +248,7 @@ def test_emulated_autotune_leaves_the_initial_state_untouched(monkeypatch):
     info = solver.info()
     solver.close()
     assert np.array_equal(x, xo)
-    assert info["autotuned"] == 1 and 1 <= info["primal_variant"] <= 5 and 1 <= info["dual_variant"] <= 5
+    assert info["autotuned"] == 1 and 1 <= info["primal_variant"] <= 7 and 1 <= info["dual_variant"] <= 7
     assert all(v > 0 for v in info["variant_ms"]["k_primal"]) and all(v > 0 for v in info["variant_ms"]["k_dual"])
     # not timed when asked not to
     x, _, solver = emulated_chambolle_pock_ppd(*args, x0=x0, nb_max_iter=64, nb_iter_plot=1000, flags=_cabi.FLAG_NO_AUTOTUNE)
