@@ -21,11 +21,11 @@ timeout 600 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_n1.json 2>
 echo "bench exit $?" | tee -a $out/${tag}_session.log
 
 echo "== 3. every kernel variant on the bench workload (CUDA events)" | tee -a $out/${tag}_session.log
-for v in 1 2 3 4 5; do
+for v in 1 2 3 4 5 6 7; do
   timeout 300 python tools/quick_bench.py --size 4096 --iters 100 --reps 3 --variant $v >> $out/${tag}_variants.jsonl 2>> $out/${tag}_variants.err
 done
 for f in 3 11; do  # compressed storage: every variant as well
-  for v in 1 3 5; do
+  for v in 1 3 5 6 7; do
     timeout 300 python tools/quick_bench.py --size 4096 --iters 100 --reps 3 --variant $v --flags $f >> $out/${tag}_variants.jsonl 2>> $out/${tag}_variants.err
   done
 done
