@@ -6,7 +6,8 @@ attributes, so code written against ``pysparselp.SparseLP`` runs unchanged:
 
 * variables / constraints builders  (reference ``pysparselp/SparseLP.py:421-613``)
 * ``remove_fixed_variables``         (``:632-674``)
-* ``convert_to_one_sided_inequality_system`` (``:835-879``)
+* ``convert_to_one_sided_inequality_system`` (``:835-879``), ``convert_to_all_equalities`` (``:819-833``),
+  ``convert_to_all_inequalities[_without_bounds]`` (``:881-928``)
 * ``max_constraint_violation`` / ``check_solution`` (``:186-226``)
 * ``solve(method='chambolle_pock_ppd', ...)`` (``:990-1002, :1243-1288, :1378-1383``)
 
@@ -376,6 +377,54 @@ class SparseLP:
         self.a_inequalities = a
         self.b_upper = np.concatenate((self.b_upper[up], -self.b_lower[lo]))
         self.b_lower = None
+
+    def convert_to_all_equalities(self):
+        """``A_ineq x - s = 0`` with one slack ``b_lower <= s <= b_upper`` per inequality row (reference :819-833);
+        the solution of the original LP is the leading part of x."""
+        m = self.nb_inequality_constraints()
+        if m == 0:
+            return
+        a = self.a_inequalities
+        lower = self.b_lower if self.b_lower is not None else np.full(m, -np.inf)
+        self.add_variables_array(m, lower, self.b_upper)
+        self._ineq.replace(None)
+        self.add_inequality_constraints_sparse(sp.hstack((a, -sp.eye(m))).tocsr(), 0, 0)  # equal scalars: equalities
+        self.b_lower = np.empty(0, dtype=np.float64)
+        self.b_upper = np.empty(0, dtype=np.float64)
+        self.inequalityConstraintNames = []
+
+    def convert_to_all_inequalities(self):
+        """Equality rows become two-sided inequality rows ``b <= A_eq x <= b``, in front of the existing ones
+        (reference :881-911)."""
+        m_eq = self.nb_equality_constraints()
+        if m_eq == 0:
+            return
+        m_in = self.nb_inequality_constraints()
+        lower = self.b_lower if self.b_lower is not None else np.full(m_in, -np.inf)
+        upper = self.b_upper if self.b_upper is not None else np.full(m_in, np.inf)
+        self.inequalityConstraintNames = list(self.equalityConstraintNames) + [
+            {"name": d["name"], "start": m_eq + d["start"], "end": m_eq + d["end"]} for d in self.inequalityConstraintNames]
+        self.equalityConstraintNames = []
+        self.a_inequalities = sp.vstack((self.a_equalities, self.a_inequalities)).tocsr()
+        self.b_lower = np.concatenate((self.b_equalities, lower))
+        self.b_upper = np.concatenate((self.b_equalities, upper))
+        self._eq.replace(None)
+        self.b_equalities = np.empty(0, dtype=np.float64)
+
+    def convert_to_all_inequalities_without_bounds(self):
+        """Also the variable bounds become rows (one per variable with a finite bound), the variables are left free
+        (reference :913-928)."""
+        self.convert_to_all_inequalities()
+        bounded = np.flatnonzero(~(np.isinf(self.lower_bounds) & np.isinf(self.upper_bounds)))
+        m_in = self.nb_inequality_constraints()
+        lower = self.b_lower if self.b_lower is not None else np.full(m_in, -np.inf)
+        pick = sp.csr_matrix((np.ones(bounded.size), (np.arange(bounded.size), bounded)),
+                             shape=(bounded.size, self.nb_variables))
+        self.a_inequalities = sp.vstack((self.a_inequalities, pick)).tocsr()
+        self.b_lower = np.concatenate((lower, self.lower_bounds[bounded]))
+        self.b_upper = np.concatenate((self.b_upper, self.upper_bounds[bounded]))
+        self.lower_bounds.fill(-np.inf)
+        self.upper_bounds.fill(np.inf)
 
     # -- solve ------------------------------------------------------------------------------------
     def solve(

@@ -9,6 +9,7 @@ import io
 
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 from oracle import ref_loader
 from test_fuzz_on_cpu import random_lp
@@ -74,3 +75,41 @@ def test_solve_equals_the_live_reference(seed, monkeypatch):
         fin = np.isfinite(r)
         scale = max(np.max(np.abs(r[fin])) if fin.any() else 0.0, 1e-30)
         assert np.all(np.abs(r[fin] - m[fin]) <= 1e-6 * np.abs(r[fin]) + 1e-9 * scale), (k, r, m)
+
+
+def _same_matrix(a, b):
+    if a is None or b is None:
+        return (a is None or a.shape[0] == 0) and (b is None or b.shape[0] == 0)
+    a, b = sp.csr_matrix(a), sp.csr_matrix(b)
+    a.sort_indices()
+    b.sort_indices()
+    return a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) \
+        and np.array_equal(a.data, b.data)
+
+
+def _same_vector(a, b):
+    if a is None or b is None:
+        return (a is None or np.size(a) == 0) and (b is None or np.size(b) == 0)
+    return np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+
+
+@pytest.mark.parametrize("conversion", ["convert_to_all_equalities", "convert_to_all_inequalities",
+                                        "convert_to_all_inequalities_without_bounds",
+                                        "convert_to_one_sided_inequality_system"])
+@pytest.mark.parametrize("seed", range(400, 412))
+def test_modeling_layer_conversions_equal_the_live_reference(seed, conversion):
+    from pysparselp_b200.SparseLP import SparseLP as Mine
+
+    args, _, _, rng = random_lp(seed)
+    if args[3] is None:
+        pytest.skip("needs an inequality block")
+    theirs = build(ref_loader.reference_sparse_lp().SparseLP, args, False, bool(seed % 2))
+    mine = build(Mine, args, False, bool(seed % 2))
+    with contextlib.redirect_stdout(io.StringIO()):
+        getattr(theirs, conversion)()
+    getattr(mine, conversion)()
+    assert mine.nb_variables == theirs.nb_variables
+    for name in ("costsvector", "lower_bounds", "upper_bounds", "b_equalities", "b_lower", "b_upper"):
+        assert _same_vector(getattr(mine, name), getattr(theirs, name)), name
+    assert _same_matrix(mine.a_equalities, theirs.a_equalities), "a_equalities"
+    assert _same_matrix(mine.a_inequalities, theirs.a_inequalities), "a_inequalities"
