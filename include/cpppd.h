@@ -247,8 +247,11 @@ int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms);
 int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_ms);
 
 /* -- state access (synchronising copies to/from HOST memory) ------------------------- */
+/* x and the best integer solution are what the reference returns (ChambollePockPPD.py:344-346) and hands to its
+ * callback (:319-329); y, xbar (x3), diag_t, diag_sigma and d are the locals of :153-217 that the parity tests compare. */
 int cpppd_get_vector(cpppd_handle h, int32_t which, double *host_dst);
-int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src); /* X, XBAR, Y only */
+/* Warm start (the reference can only start from x0, :91-94): X, XBAR, Y only. */
+int cpppd_set_vector(cpppd_handle h, int32_t which, const double *host_src);
 int cpppd_get_info(cpppd_handle h, cpppd_info *out);
 /* Ground truth for the distance curves of the stats block: values[k] is compared with x[indices[k]]
  * (original column ids).  count = 0 removes it.  With world_size > 1 every rank passes the full list. */
