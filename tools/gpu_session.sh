@@ -36,9 +36,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 1 --warmup 3 --iters-per-step 10 --e2e-steps 0 --variants 0 --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
 
 echo "== 5. ncu --set full of the hot kernels (chosen variants, and variant 1 for reference)" | tee -a $out/${tag}_session.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_primal|k_dual' --launch-skip 60 -c 4 \
+# (launches of k_primal / k_dual in quick_bench: 70 while the variants are timed at creation, 40 warm-up, 20 timed,
+#  32 with events between the kernels: skip past the first two groups)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_primal|k_dual' --launch-skip 114 -c 4 \
   -f -o $out/${tag}_hot python tools/quick_bench.py --size 4096 --iters 10 --reps 1 > $out/${tag}_ncu_hot.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_primal|k_dual' --launch-skip 60 -c 4 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_primal|k_dual' --launch-skip 44 -c 4 \
   -f -o $out/${tag}_hot_v1 python tools/quick_bench.py --size 4096 --iters 10 --reps 1 --variant 1 > $out/${tag}_ncu_hot_v1.log 2>&1
 
 echo "== 6. tiny LPs: CUDA graphs vs the persistent CTA (printed by the test)" | tee -a $out/${tag}_session.log
