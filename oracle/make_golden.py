@@ -210,7 +210,9 @@ def main(only=()):
             continue
         with quiet:
             lp_ref, gt_ref = netlib_lp(ref_netlib.get_problem, ref_slp.SparseLP, problem)
-        lp_my, gt_my = netlib_lp(my_get_problem, MySparseLP, problem)
+        # (only SC105 and AFIRO are vendored in this package: the others are parsed from the reference's data folder)
+        ref_data = os.path.join(ref_loader.REFERENCE_ROOT, "pysparselp", "data")
+        lp_my, gt_my = netlib_lp(lambda name: my_get_problem(name, data_dir=ref_data), MySparseLP, problem)
         args = solver_args_from_lp(lp_ref)
         assert_same_args(args, solver_args_from_lp(lp_my))
         assert np.array_equal(gt_ref, gt_my)

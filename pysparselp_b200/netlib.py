@@ -10,9 +10,12 @@ from .MPSparser import mps_parser
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def get_problem(problem_name):
-    lp_file = os.path.join(_HERE, "data", "netlib", problem_name.upper() + ".SIF")
-    sol_file = os.path.join(_HERE, "data", "perPlex", problem_name.lower() + ".txt")
+def get_problem(problem_name, data_dir=None):
+    """``data_dir``: a folder laid out like the reference's ``pysparselp/data`` (``netlib/NAME.SIF``,
+    ``perPlex/name.txt``) for problems that are not vendored here; default: this package's ``data/``."""
+    root = os.path.join(_HERE, "data") if data_dir is None else data_dir
+    lp_file = os.path.join(root, "netlib", problem_name.upper() + ".SIF")
+    sol_file = os.path.join(root, "perPlex", problem_name.lower() + ".txt")
     if not os.path.isfile(lp_file):
         raise FileNotFoundError(
             "netlib problem %s is not vendored (%s); downloading is not supported" % (problem_name, lp_file))
