@@ -13,8 +13,9 @@ Extra keyword-only arguments (defaults keep the reference behaviour):
 ``device`` (CUDA ordinal or torch.device), ``verbose`` (print the reference's per-block
 line), ``flags`` (CPPPD_FLAG_* bit mask), ``return_solver`` (also return the live
 ``CpPpdSolver`` for inspection), ``kernel_variant`` (0: pick the fastest variant of the two hot kernels
-automatically; see ``cpppd_problem.kernel_variant`` — the iterates do not depend on it), ``long_row_threshold`` (rows / columns with more entries are summed by
-many threads, see ``cpppd_problem.long_row_threshold``), ``distributed`` (None: use the initialised torch.distributed
+automatically; see ``cpppd_problem.kernel_variant`` — the iterates do not depend on it),
+``long_row_threshold`` (rows / columns with more entries are summed by many threads, see
+``cpppd_problem.long_row_threshold``), ``distributed`` (None: use the initialised torch.distributed
 world when it has more than one rank — one process per GPU, every rank passes the same LP and
 gets the same result; False: this GPU only; or an explicit ProcessGroup).
 """

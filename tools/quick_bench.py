@@ -28,7 +28,8 @@ s.iterate(20); s.sync()
 times = [s.time_iterations(a.iters) / a.iters for _ in range(a.reps)]
 ms = float(np.median(times))
 kp, kd = [v / 16 for v in s.time_kernels(16)]
-out = dict(kind=a.kind, size=a.size, variant=a.variant, chosen=(info["primal_variant"], info["dual_variant"]), primal_ms=kp, dual_ms=kd, n=info["n"], m=info["m_eq"] + info["m_ineq"], nnz=info["nnz"],
+out = dict(kind=a.kind, size=a.size, variant=a.variant, chosen=(info["primal_variant"], info["dual_variant"]),
+           primal_ms=kp, dual_ms=kd, n=info["n"], m=info["m_eq"] + info["m_ineq"], nnz=info["nnz"],
            build_s=round(t1 - t0, 2), setup_s=round(t2 - t1, 2), ms_per_iter=ms, it_per_s=1e3 / ms,
            algo_GBs=info["bytes_per_iteration_algorithmic"] / ms / 1e6,
            actual_GBs=info["bytes_per_iteration_actual"] / ms / 1e6, times=times,
