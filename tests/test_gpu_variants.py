@@ -87,64 +87,3 @@ def test_autotune_is_on_by_default_for_large_operands():
             ref.close()
     finally:
         solver.close()
-
-
-# (kb2: 146 distinct values but a CTA of 64 threads — the dictionary is staged in a loop)
-@pytest.mark.parametrize("name", ["sc105", "random_small", "random_small_alpha", "kb2", "afiro"])
-def test_tiny_persistent_kernel_gives_the_same_bits(name):
-    """CPPPD_FLAG_TINY_PERSISTENT: all iterations between two stats blocks in one launch of one CTA."""
-    from pysparselp_b200 import _cabi
-    from pysparselp_b200.ChambollePockPPD import chambolle_pock_ppd
-    from test_gpu_parity import assert_curves_close
-
-    args, g = case_args(name)
-    kw = CASE_PARAMS.get(name, {})
-    for flags in (_cabi.FLAG_TINY_PERSISTENT,
-                  _cabi.FLAG_TINY_PERSISTENT | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS | _cabi.FLAG_REORDER):
-        trace = []
-        x, best, solver = chambolle_pock_ppd(*args, nb_max_iter=100, nb_iter_plot=10, flags=flags, return_solver=True,
-                                             callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)),
-                                             **kw)
-        try:
-            assert solver.info()["tiny_persistent"] == 1 and solver.niter == 100
-            y = solver.get_y()
-            if "alpha" not in kw:
-                assert np.array_equal(x, g["x_100"]) and np.array_equal(y, gold_y(g))
-            else:
-                assert np.allclose(x, g["x_100"], rtol=1e-9, atol=0)
-            assert_curves_close(np.array(trace), g["trace_10"])
-        finally:
-            solver.close()
-
-
-def test_tiny_persistent_kernel_reproduces_the_sc105_regression_curve():
-    """reference tests/test_netlib.py through SparseLP.solve with the persistent kernel: 41 500 iterations in 83
-    launches of k_tiny_iterate (plus the stats blocks)."""
-    import json
-    import os
-    import time
-
-    from conftest import GOLDEN
-    from pysparselp_b200 import _cabi
-    from pysparselp_b200.netlib import get_problem
-    from pysparselp_b200.SparseLP import SparseLP
-
-    with open(os.path.join(GOLDEN, "reference_curves.json")) as f:
-        ref = json.load(f)
-    d = get_problem("SC105")
-    gt = d["solution"]
-    timings = {}
-    for flags in (0, _cabi.FLAG_TINY_PERSISTENT):
-        lp = SparseLP()
-        lp.add_variables_array(len(d["cost_vector"]), lower_bounds=d["lower_bounds"],
-                               upper_bounds=np.minimum(d["upper_bounds"], np.max(gt) * 2), costs=d["cost_vector"])
-        lp.add_equality_constraints_sparse(d["a_eq"], d["b_eq"])
-        lp.add_inequality_constraints_sparse(d["a_ineq"], d["b_lower"], d["b_upper"])
-        lp.convert_to_one_sided_inequality_system()
-        t0 = time.perf_counter()
-        lp.solve(method="chambolle_pock_ppd", get_timing=True, nb_iter=41500, max_time=100, ground_truth=gt,
-                 ground_truth_indices=np.arange(len(gt)), nb_iter_plot=500, flags=flags)
-        timings[flags] = time.perf_counter() - t0
-        assert len(lp.distance_to_ground_truth) == 83
-        np.testing.assert_almost_equal(lp.distance_to_ground_truth, ref["SC105"][:83])
-    print("SC105, 41500 iterations: CUDA graphs %.3f s, persistent CTA %.3f s" % (timings[0], timings[_cabi.FLAG_TINY_PERSISTENT]))

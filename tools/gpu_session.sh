@@ -44,7 +44,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_p
   -f -o $out/${tag}_hot_v1 python tools/quick_bench.py --size 4096 --iters 10 --reps 1 --variant 1 > $out/${tag}_ncu_hot_v1.log 2>&1
 
 echo "== 6. tiny LPs: CUDA graphs vs the persistent CTA (printed by the test)" | tee -a $out/${tag}_session.log
-timeout 300 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -k sc105_regression > $out/${tag}_tiny.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_zz_opt_in_features.py -m gpu -q -s -k sc105_regression > $out/${tag}_tiny.log 2>&1
 grep "SC105" $out/${tag}_tiny.log | tee -a $out/${tag}_session.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv >> $out/${tag}_session.log 2>&1
 echo "== done" | tee -a $out/${tag}_session.log
