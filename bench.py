@@ -251,7 +251,9 @@ def workload_config(a):
             "l2": "inputs larger than L2 (about 11 GB streamed per iteration vs 126 MB L2); no flush needed",
             "flags": a.flags,
             "parallelism": "1 GPU" if a.gpus == 1 else "%d GPUs, owner-computes row/column strips, %s halo exchange" % (
-                a.gpus, "NCCL send/recv" if a.flags & 32 else "peer-memory (NVLink) push-kernel")}
+                a.gpus, "NCCL send/recv" if a.flags & 32 else (
+                    "peer-memory (NVLink) stores fused into k_primal / k_dual" if a.flags & 128
+                    else "peer-memory (NVLink) push-kernel"))}
 
 
 def time_variant(make_solver, args, flags, iters_per_step, peak):
@@ -406,7 +408,8 @@ def run_b200(a):
                             "preconditioners on device, iterate, read x back"},
             # k_primal + k_dual per iteration; with N > 1 also k_push + k_wait after each of them (peer memory)
             # or one k_pack before each NCCL send/recv group
-            "gpu_launches": (2 if world == 1 else (4 if a.flags & 32 else 6)) * a.steps * a.iters_per_step,
+            # ... or nothing more when the halo is fused into the two kernels (flag 128)
+            "gpu_launches": (2 if world == 1 or a.flags & 128 else (4 if a.flags & 32 else 6)) * a.steps * a.iters_per_step,
             "kernel_variants": kernel_variants(info),
             "clocks": clocks.summary(),
             "partition": None if world == 1 else {k: info[k] for k in (
@@ -461,7 +464,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variants", type=int, default=1, help="also time the opt-in storage variants (N = 1)")
-    ap.add_argument("--flags", type=int, default=0, help="CPPPD_FLAG_* bit mask (8 reorder, 32 NCCL halos instead of peer memory)")
+    ap.add_argument("--flags", type=int, default=0, help="CPPPD_FLAG_* bit mask (8 reorder, 32 NCCL halos instead of peer memory, 128 halo fused into the kernels)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":
