@@ -346,6 +346,31 @@ def run_b200(a):
                       "frac_of_peak": info["bytes_per_iteration_algorithmic"] * its_per_s / 1e9 / (peak * world),
                       "note": "whole job: algorithmic bytes of the full LP x iterations/s, against n_gpus x peak"},
     }
+    # ---- the same loop with the reference's stats block every 500 iterations (its usual nb_iter_plot): SURVEY 8(d)
+    with_stats = None
+    try:
+        interval, blocks = a.stats_interval, 2
+        solver.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(blocks):
+            solver.primal_step(keep_d=True)
+            solver.stats_step(False)
+            solver.read_stats()  # the one host synchronisation of the interval
+            solver.dual_step()
+            solver.iterate(interval - 1)
+        solver.sync()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        with_stats = {"iterations_per_s": blocks * interval / dt, "nb_iter_plot": interval, "iterations": blocks * interval,
+                      "note": "device-resident, wall clock around %d stats intervals (stats block + 96-byte read-back each)" % blocks}
+    except Exception as e:
+        if world > 1:
+            raise
+        with_stats = {"error": repr(e)}
     solver.close()
     del solver
 
@@ -401,7 +426,7 @@ def run_b200(a):
             "metric": METRIC, "value": its_per_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a),
-            "roofline": roofline, "cpu_baseline": cpu, "variants": variants,
+            "roofline": roofline, "cpu_baseline": cpu, "variants": variants, "with_stats_block": with_stats,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps, "error": e2e_error,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
@@ -460,6 +485,7 @@ def main():
     ap.add_argument("--ref-iters-per-step", type=int, default=1)
     ap.add_argument("--ref-numpy-iters", type=int, default=2,
                     help="--impl reference: iterations of the numpy/scipy restatement timed beside the C port (0: skip)")
+    ap.add_argument("--stats-interval", type=int, default=500, help="nb_iter_plot of the with_stats_block measurement")
     ap.add_argument("--e2e-iters", type=int, default=500)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -104,7 +104,8 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     a = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="b200", size=24, iters_per_step=3, ref_iters_per_step=1,
-                           ref_numpy_iters=1, e2e_iters=7, e2e_steps=2, no_cpu_baseline=False, variants=1, flags=0)
+                           ref_numpy_iters=1, e2e_iters=7, e2e_steps=2, no_cpu_baseline=False, variants=1, flags=0,
+                           stats_interval=5)
     bench.run_b200(a)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -121,6 +122,7 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     e = d["e2e"]
     assert e["error"] is None and e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] == 2 * 2 * 3
+    assert d["with_stats_block"]["iterations"] == 10 and d["with_stats_block"]["iterations_per_s"] > 0
     assert set(d["variants"]) == {"reorder", "compressed", "compressed+reorder"}
     assert all("error" not in v for v in d["variants"].values()), d["variants"]
     assert d["kernel_variants"]["k_primal"]["variant"] == 1 and d["kernel_variants"]["autotuned"] is False
