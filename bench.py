@@ -14,6 +14,8 @@ A *step* is ``--iters-per-step`` (default 50) solver iterations — one pass of 
                 every e2e step uploads the whole LP from pinned host memory, builds the operator,
                 runs ``--e2e-iters`` iterations (stats block at iteration 0, as the reference
                 does) and reads x back to the host.
+* ``with_stats_block``: iterations/s of the same resident loop with the reference's stats block every
+                ``--stats-interval`` (500) iterations.
 * ``roofline``: algorithmic bytes of the dominant kernel / its CUDA-event time,
                 against MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s).
 * ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference's CPU path
