@@ -9,7 +9,7 @@
 set -e
 cd "$(dirname "$0")/../.."
 rebuild() { CPPPD_NVCC_DEFINES="$1" python -c "import sys; sys.path.insert(0, 'tests'); from emul import make_emul; make_emul.build(force=True)"; }
-small="CPPPD_FULL_SIZE_POTTS=96 CPPPD_FULL_SIZE_RANDOM_N=20000"
+small="CPPPD_FULL_SIZE_POTTS=96 CPPPD_FULL_SIZE_RANDOM_N=20000 CPPPD_FULL_SIZE_SVM_SAMPLES=3000 CPPPD_FULL_SIZE_SVM_FEATURES=20"
 
 rebuild "-fsanitize=address -fno-omit-frame-pointer"
 export ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0

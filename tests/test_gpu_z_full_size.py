@@ -1,5 +1,6 @@
-"""GPU, BASELINE.json's full sizes: the bench workload itself (Potts 4096^2, configs[4]) and a random sparse LP
-of the configs[3] family, checked through properties that do not need a golden file of that size:
+"""GPU, BASELINE.json's full sizes: the bench workload itself (Potts 4096^2, configs[4]), a random sparse LP of the
+configs[3] family and an L1-SVM LP of the configs[2] family with the bench's entry count, checked through properties
+that do not need a golden file of that size:
 
 * bit-identity with the plain-C OpenMP oracle port (oracle/cpppd_oracle.c) after a few iterations — the port
   itself is pinned to the reference goldens by tests/test_oracle_golden.py;
@@ -20,6 +21,8 @@ pytestmark = pytest.mark.gpu
 # the sizes can be scaled down to dry-run this file on the CPU emulation of the library (tests/README.md)
 POTTS_SIDE = int(os.environ.get("CPPPD_FULL_SIZE_POTTS", "4096"))
 RANDOM_N = int(os.environ.get("CPPPD_FULL_SIZE_RANDOM_N", "2000000"))
+SVM_SAMPLES = int(os.environ.get("CPPPD_FULL_SIZE_SVM_SAMPLES", "50000"))
+SVM_FEATURES = int(os.environ.get("CPPPD_FULL_SIZE_SVM_FEATURES", "1000"))
 
 
 def digest(*arrays):
@@ -94,3 +97,28 @@ def test_random_lp_with_equalities_bit_identical_to_the_c_port():
     assert np.all(x >= lp.lb) and np.all(x <= lp.ub) and np.all(y[m_eq:] >= 0)
     x2, y2, _, _ = solve_on_gpu(args, iters, flags=64)  # CPPPD_FLAG_NO_REORDER: the caller's numbering
     assert digest(x2, y2) == digest(xo, yo)
+
+
+def test_l1svm_with_1000_features_agrees_with_the_c_port():
+    """configs[2] family — 50 000 samples x 1 000 features, K = 3 (106 006 rows, 56 006 columns, 200 M entries: 1/20
+    of the samples of configs[2], the entry count of the bench workload).  Rows of 2 003 entries stay on the
+    thread-per-row path; the 3 003 weight / bias columns (66 667 entries each) go through the long-row kernels, whose fixed summation tree agrees with scipy's sequential sums to rounding: 1e-9 relative
+    (BASELINE.json's bound for the iterates), not bit for bit."""
+    from pysparselp_b200 import generators
+
+    lp, _ = generators.l1svm_lp(SVM_SAMPLES, SVM_FEATURES)
+    args = generators.lp_args(lp)
+    iters = 5
+    xo, yo = c_port_iterates(args, iters)
+    x, y, info, trace = solve_on_gpu(args, iters)
+    assert info["nnz"] == lp.a_ineq.nnz and info["long_rows"] == 0
+    if SVM_SAMPLES * 4 // 3 > 2048:
+        assert info["long_cols"] >= 3 * SVM_FEATURES and info["long_entries"] > info["nnz"] // 2
+    for got, want in ((x, xo), (y, yo)):
+        assert np.max(np.abs(got - want)) <= 1e-9 * max(np.max(np.abs(want)), 1e-300)
+    assert np.all(x >= lp.lb) and np.all(x <= lp.ub)
+    assert all(np.isfinite(row[1]) for row in trace)  # energy1 (energy2 is NaN by construction: free weights, :260-263)
+    # the same LP without the long-row path: bit for bit (one thread per weight column: slow, but exact)
+    if SVM_SAMPLES <= 5000:
+        x2, y2, info2, _ = solve_on_gpu(args, iters, long_row_threshold=-1)
+        assert info2["long_cols"] == 0 and np.array_equal(x2, xo) and np.array_equal(y2, yo)
