@@ -13,14 +13,14 @@ small="CPPPD_FULL_SIZE_POTTS=96 CPPPD_FULL_SIZE_RANDOM_N=20000 CPPPD_FULL_SIZE_S
 
 rebuild "-fsanitize=address -fno-omit-frame-pointer"
 export ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0
-LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest tests/test_library_on_cpu.py tests/test_multi_rank_on_cpu.py -x -q
+LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest tests/test_library_on_cpu.py tests/test_multi_rank_on_cpu.py tests/test_fuzz_on_cpu.py -x -q
 env $small CPPPD_EMULATE_GPU_TESTS=1 PYTHONPATH=.:tests LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
   python -m pytest tests -m gpu -p emul.patch_plugin -x -q \
   --deselect tests/test_gpu_variants.py::test_autotune_is_on_by_default_for_large_operands \
   --deselect tests/test_gpu_parity.py::test_reference_golden_curves_through_solve
 
 rebuild "-fsanitize=undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer"
-python -m pytest tests/test_library_on_cpu.py tests/test_multi_rank_on_cpu.py -x -q
+python -m pytest tests/test_library_on_cpu.py tests/test_multi_rank_on_cpu.py tests/test_fuzz_on_cpu.py -x -q
 
 rebuild ""
 echo "sanitizer runs clean"
