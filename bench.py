@@ -386,6 +386,52 @@ def run_b200(a):
             except Exception as e:  # a variant must never take the headline measurement down
                 variants[name] = {"flags": vflags, "error": repr(e)}
 
+    # ---- the two CPU-runnable configs of BASELINE.json (configs[0] Potts 50x50, configs[1] netlib SC105): launch-latency
+    #      bound ("report it/s only"); CUDA graphs of 50 iterations vs the opt-in persistent CTA
+    small = None
+    if world == 1 and a.small_configs:
+        small = {}
+        try:
+            small_lps = {"potts_50x50": generators.lp_args(generators.potts_lp(50))}
+            try:
+                from pysparselp_b200.netlib import get_problem
+                from pysparselp_b200.SparseLP import SparseLP
+
+                d = get_problem("SC105")
+                lp105 = SparseLP()
+                lp105.add_variables_array(len(d["cost_vector"]), lower_bounds=d["lower_bounds"],
+                                          upper_bounds=np.minimum(d["upper_bounds"], np.max(d["solution"]) * 2),
+                                          costs=d["cost_vector"])
+                lp105.add_equality_constraints_sparse(d["a_eq"], d["b_eq"])
+                lp105.add_inequality_constraints_sparse(d["a_ineq"], d["b_lower"], d["b_upper"])
+                lp105.convert_to_one_sided_inequality_system()
+                small_lps["netlib_sc105"] = (lp105.costsvector, lp105.a_equalities, lp105.b_equalities,
+                                             lp105.a_inequalities, lp105.b_lower, lp105.b_upper, lp105.lower_bounds,
+                                             lp105.upper_bounds)
+            except Exception as e:
+                small["netlib_sc105"] = {"error": repr(e)}
+            for name, sargs in small_lps.items():
+                small[name] = {}
+                # (the persistent CTA has not run on hardware yet: only timed on request, --small-configs 2)
+                for label, sflags in (("cuda_graphs", 0), ("persistent_cta", 512))[: 1 if a.small_configs < 2 else 2]:
+                    try:
+                        ss = make_solver(*sargs, flags=sflags)
+                        try:
+                            ss.iterate(a.small_iters)
+                            ss.sync()
+                            ms_small = ss.time_iterations(a.small_iters)
+                            used = bool(ss.info()["tiny_persistent"])
+                        finally:
+                            ss.close()
+                        if label == "persistent_cta" and not used:
+                            small[name][label] = None  # the LP does not fit one CTA: the flag is ignored
+                        else:
+                            small[name][label] = {"iterations_per_s": a.small_iters / (ms_small * 1e-3)}
+                    except Exception as e:
+                        small[name][label] = {"error": repr(e)}
+        except Exception as e:
+            small = {"error": repr(e)}
+
     # ---- end to end through the public API with host buffers -----------------------------------
     h2d = lp_nbytes(lp)
     d2h = 8 * n + 96
@@ -429,6 +475,7 @@ def run_b200(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a),
             "roofline": roofline, "cpu_baseline": cpu, "variants": variants, "with_stats_block": with_stats,
+            "latency_bound_configs": small,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps, "error": e2e_error,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
@@ -487,6 +534,8 @@ def main():
     ap.add_argument("--ref-iters-per-step", type=int, default=1)
     ap.add_argument("--ref-numpy-iters", type=int, default=2,
                     help="--impl reference: iterations of the numpy/scipy restatement timed beside the C port (0: skip)")
+    ap.add_argument("--small-configs", type=int, default=1, help="also time Potts 50x50 and SC105 (N = 1); 2: also with the opt-in persistent CTA")
+    ap.add_argument("--small-iters", type=int, default=5000)
     ap.add_argument("--stats-interval", type=int, default=500, help="nb_iter_plot of the with_stats_block measurement")
     ap.add_argument("--e2e-iters", type=int, default=500)
     ap.add_argument("--e2e-steps", type=int, default=2)

@@ -105,7 +105,7 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
         monkeypatch.delenv(k, raising=False)
     a = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="b200", size=24, iters_per_step=3, ref_iters_per_step=1,
                            ref_numpy_iters=1, e2e_iters=7, e2e_steps=2, no_cpu_baseline=False, variants=1, flags=0,
-                           stats_interval=5)
+                           stats_interval=5, small_configs=2, small_iters=30)
     bench.run_b200(a)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -123,6 +123,10 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     assert e["error"] is None and e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] == 2 * 2 * 3
     assert d["with_stats_block"]["iterations"] == 10 and d["with_stats_block"]["iterations_per_s"] > 0
+    small = d["latency_bound_configs"]
+    assert small["potts_50x50"]["cuda_graphs"]["iterations_per_s"] > 0 and small["potts_50x50"]["persistent_cta"] is None
+    assert small["netlib_sc105"]["cuda_graphs"]["iterations_per_s"] > 0
+    assert small["netlib_sc105"]["persistent_cta"]["iterations_per_s"] > 0
     assert set(d["variants"]) == {"reorder", "compressed", "compressed+reorder"}
     assert all("error" not in v for v in d["variants"].values()), d["variants"]
     assert d["kernel_variants"]["k_primal"]["variant"] == 1 and d["kernel_variants"]["autotuned"] is False

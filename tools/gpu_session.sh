@@ -45,6 +45,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_p
 
 echo "== 6. tiny LPs: CUDA graphs vs the persistent CTA (printed by the test)" | tee -a $out/${tag}_session.log
 timeout 300 python -m pytest tests/test_gpu_zz_opt_in_features.py -m gpu -q -s -k sc105_regression > $out/${tag}_tiny.log 2>&1
+timeout 300 python bench.py --size 256 --steps 2 --warmup 3 --e2e-steps 0 --variants 0 --no-cpu-baseline --small-configs 2 > $out/${tag}_small_configs.json 2>> $out/${tag}_tiny.log
 grep "SC105" $out/${tag}_tiny.log | tee -a $out/${tag}_session.log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv >> $out/${tag}_session.log 2>&1
 echo "== done" | tee -a $out/${tag}_session.log
