@@ -16,6 +16,8 @@ A *step* is ``--iters-per-step`` (default 50) solver iterations — one pass of 
                 does) and reads x back to the host.
 * ``with_stats_block``: iterations/s of the same resident loop with the reference's stats block every
                 ``--stats-interval`` (500) iterations.
+* ``latency_bound_configs``: iterations/s of BASELINE.json's two small configs (Potts 50x50, netlib SC105), which fit
+                the caches and are bound by launch latency, not bandwidth (extra information, N = 1).
 * ``roofline``: algorithmic bytes of the dominant kernel / its CUDA-event time,
                 against MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s).
 * ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference's CPU path
