@@ -168,16 +168,14 @@ def cpu_baselines(lp, sample_note, numpy_iters=2, c_iters=6):
         o.dual_step()
     out["numpy"] = numpy_iters / (time.perf_counter() - t0)
     del o
+    from oracle import c_port
+
+    cores = c_port.set_threads()  # every core of the box, whatever OMP_NUM_THREADS the launcher exported
     co = COracle(*args)
     co.iterate(1)
     t0 = time.perf_counter()
     co.iterate(c_iters)
     out["c_openmp"] = c_iters / (time.perf_counter() - t0)
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
     return {
         "value": out["c_openmp"], "unit": UNIT, "cores": cores, "kind": "port",
         "sample": "%s; oracle/cpppd_oracle.c (OpenMP, %d threads) %d iterations after 1 warm-up; "
@@ -192,9 +190,12 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import c_port
     from oracle.c_port import COracle
     from pysparselp_b200 import generators
 
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks: ask for every core explicitly and report what OpenMP uses
+    cores = c_port.set_threads()
     # bounded sample: full size when the requested number of steps allows it, else a smaller image
     size = a.size
     budget_iters = (a.steps + a.warmup) * a.ref_iters_per_step
@@ -211,7 +212,6 @@ def run_reference(a):
         co.iterate(a.ref_iters_per_step)
     dt = time.perf_counter() - t0
     its = a.steps * a.ref_iters_per_step / dt * scale
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     del co
     # beside it: the reference's own arithmetic (scipy csr_matvec / csc_matvec + numpy ufuncs, one thread by
     # construction) on the same sample — what a PySparseLP user runs today

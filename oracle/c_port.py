@@ -51,6 +51,19 @@ def lib():
     return _lib
 
 
+def set_threads(threads=None):
+    """Use `threads` OpenMP threads (default: every core this process may run on) whatever OMP_NUM_THREADS
+    says — torchrun exports OMP_NUM_THREADS=1 to its ranks.  Returns the count the loops really use."""
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    fn = lib().cpppd_c_set_threads
+    fn.restype = C.c_int
+    return int(fn(C.c_int(int(threads))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

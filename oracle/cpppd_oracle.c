@@ -18,6 +18,22 @@
  */
 #include <math.h>
 #include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 to their children; the CPU baseline must not
+ * silently inherit that.  threads <= 0 leaves the runtime's setting alone.  Returns the thread count the
+ * parallel loops below will use. */
+int cpppd_c_set_threads(int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+  return omp_get_max_threads();
+#else
+  (void)threads;
+  return 1;
+#endif
+}
 
 void cpppd_c_primal(int64_t n, int64_t m_eq, int has_eq, int has_ineq, const int64_t *colptr,
                     const int32_t *rowidx, const double *cval, const double *y, const double *c,

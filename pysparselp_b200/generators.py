@@ -129,6 +129,99 @@ def random_sparse_lp(nbvar, n_ineq, n_eq=0, nnz_per_row=8, seed=0):
     return LPArrays(costs, a_eq, b_eq, a_ineq, None, b_upper, lb, ub), x_f
 
 
+def random_sparse_lp_chunked(nbvar, n_ineq, n_eq=0, nnz_per_row=8, seed=0, chunk_rows=1 << 20, threads=None, empty=np.empty):
+    """``random_sparse_lp`` for benchmark sizes (BASELINE configs[3]: 20 M variables, 40 M rows, 320 M entries).
+
+    Same distributions and the same LP family as ``random_sparse_lp`` (reference ``pysparselp/randomLP.py:14-75``,
+    see there), but the rows are drawn in independent chunks of ``chunk_rows`` rows, every chunk from its own child
+    of ``np.random.SeedSequence(seed)``, written straight into the final CSR arrays.  The result depends on
+    ``(seed, chunk_rows)`` only — not on ``threads``, the number of worker threads the chunks are spread over
+    (numpy's generators and sorts release the GIL).  ``empty`` is the array allocator (e.g. pinned host memory).
+    """
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+
+    n, k = int(nbvar), int(nnz_per_row)
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    threads = max(1, min(int(threads), 64))
+    root = np.random.SeedSequence(seed)
+    vec_seed, eq_seed, ineq_seed = root.spawn(3)
+
+    def rvals(rng, size):
+        v = rng.standard_normal(size)
+        v *= 100
+        np.round(v, out=v)
+        v /= 100
+        return v
+
+    # vectors of length n, drawn in chunks as well
+    ncols_chunks = [(s, min(n, s + chunk_rows)) for s in range(0, n, chunk_rows)]
+    x_f, costs, t = (empty(n, dtype=np.float64) for _ in range(3))
+
+    def fill_vec(job):
+        (s, e), ss = job
+        rng = np.random.default_rng(ss)
+        x_f[s:e] = rvals(rng, e - s)
+        costs[s:e] = rvals(rng, e - s)
+        t[s:e] = rvals(rng, e - s)
+
+    def block(rows, ss_root):
+        rows = int(rows)
+        indices = empty(rows * k, dtype=np.int32)
+        data = empty(rows * k, dtype=np.float64)
+        rhs = empty(rows, dtype=np.float64)
+        noise = empty(rows, dtype=np.float64)
+        chunks = [(s, min(rows, s + chunk_rows)) for s in range(0, rows, chunk_rows)]
+
+        def fill(job):
+            (s, e), ss = job
+            rng = np.random.default_rng(ss)
+            cols = rng.integers(0, n, size=(e - s, k), dtype=np.int32)
+            cols.sort(axis=1)
+            while True:  # re-draw the (rare) rows with a repeated column
+                bad = np.flatnonzero(np.any(cols[:, 1:] == cols[:, :-1], axis=1))
+                if bad.size == 0:
+                    break
+                cols[bad] = np.sort(rng.integers(0, n, size=(bad.size, k), dtype=np.int32), axis=1)
+            vals = rvals(rng, (e - s, k))
+            vals[vals == 0] = 0.01
+            indices[s * k:e * k] = cols.reshape(-1)
+            data[s * k:e * k] = vals.reshape(-1)
+            acc = np.zeros(e - s)
+            for q in range(k):  # A x_f accumulated in stored order, like scipy's csr_matvec
+                acc += vals[:, q] * x_f[cols[:, q]]
+            rhs[s:e] = acc
+            noise[s:e] = np.abs(rvals(rng, e - s))
+
+        with ThreadPoolExecutor(threads) as pool:
+            list(pool.map(fill, zip(chunks, ss_root.spawn(len(chunks)))))
+        idt = np.int32 if rows * k < 2**31 - 1 else np.int64
+        indptr = empty(rows + 1, dtype=idt)
+        indptr[:] = np.arange(0, rows * k + 1, k, dtype=idt)
+        return _csr_unchecked(data, indices, indptr, (rows, n)), rhs, noise
+
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(fill_vec, zip(ncols_chunks, vec_seed.spawn(len(ncols_chunks)))))
+    a_ineq, rhs, noise = block(n_ineq, ineq_seed)
+    b_upper = rhs
+    b_upper += noise
+    b_upper *= 1000
+    np.ceil(b_upper, out=b_upper)
+    b_upper /= 1000
+    lb = empty(n, dtype=np.float64)
+    ub = empty(n, dtype=np.float64)
+    np.add(x_f, np.minimum(0, t), out=lb)
+    np.add(x_f, np.maximum(0, t), out=ub)
+    a_eq = b_eq = None
+    if n_eq > 0:
+        a_eq, b_eq, _ = block(n_eq, eq_seed)
+    return LPArrays(costs, a_eq, b_eq, a_ineq, None, b_upper, lb, ub), x_f
+
+
 def l1svm_lp(nb_examples, nb_features, nb_classes=3, seed=1):
     """L1-SVM LP of ``examples/example_l1_svm.L1SVM.set_data`` emitted directly.
 

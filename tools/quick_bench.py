@@ -17,7 +17,7 @@ t0 = time.time()
 if a.kind == "potts":
     lp = generators.potts_lp(a.size)
 elif a.kind == "random":
-    lp, _ = generators.random_sparse_lp(a.size, 2 * a.size, nnz_per_row=8)
+    lp, _ = generators.random_sparse_lp_chunked(a.size, 2 * a.size, nnz_per_row=8)
 t1 = time.time()
 a_in, b_in = one_sided_rows(lp.a_ineq, lp.b_lower, lp.b_upper)
 A, b, m_eq = stack_operator(lp.a_eq, lp.b_eq, a_in, b_in, lp.c.size)
