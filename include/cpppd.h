@@ -26,6 +26,9 @@
  *   CPPPD_KERNEL_VARIANT    like cpppd_problem.kernel_variant when that field is 0
  *   CPPPD_AUTOTUNE_MIN_NNZ  smallest operand (entries) whose kernel variants are timed at creation (default 2^22)
  *   CPPPD_AUTOTUNE_CACHE    0: time the variants at every creation instead of once per operand shape and process
+ *   CPPPD_BAND_WINDOW_MB    megabytes of the gathered vector per window of a banded operand (default 48)
+ *   CPPPD_BAND_WINDOW       the same in elements (tests: windows of a few dozen elements on small LPs); both are
+ *                           only read when cpppd_problem.band_window is 0
  *
  * Problem statement (reference ChambollePockPPD.py:55-65 after the one-sided
  * conversion of :74-88, which stays in Python):
@@ -43,7 +46,7 @@
 extern "C" {
 #endif
 
-#define CPPPD_ABI_VERSION 6
+#define CPPPD_ABI_VERSION 7
 
 #define CPPPD_KERNEL_VARIANTS 7
 
@@ -94,7 +97,16 @@ enum {
    * together, e.g. netlib SC105): cpppd_iterate(k) runs all k iterations in ONE launch of one CTA instead of 2k
    * graph nodes — such LPs are bound by launch latency, not bandwidth.  Same per-row code, same bits.
    * (Opt-in until it has been measured on hardware.) */
-  CPPPD_FLAG_TINY_PERSISTENT = 1u << 9
+  CPPPD_FLAG_TINY_PERSISTENT = 1u << 9,
+  /* one GPU, caller's numbering: store A and A^T window-major ("banded") and run one launch per window of the
+   * gathered vector, so that the gathers of a launch stay inside a window that fits the L2 (cpppd_banded.cuh).
+   * Without this flag the banded copies are built only for patterns without locality over vectors of more than
+   * two windows (random sparse LPs) and used only if they time faster than the SELL kernels at creation; with
+   * it they are built and used whenever the entry order allows (ascending window index along every row —
+   * otherwise the operand silently stays with the SELL kernels; see cpppd_info.band_in_use).  Same bits. */
+  CPPPD_FLAG_BANDED = 1u << 10,
+  /* never build the banded copies */
+  CPPPD_FLAG_NO_BANDED = 1u << 11
 };
 
 typedef struct {
@@ -140,6 +152,9 @@ typedef struct {
                            4096-entry segment instead of by one thread (skewed patterns: L1-SVM weight columns, dense
                            budget rows).  0: default (2048); < 0: never.  LPs with such rows agree with the reference
                            to rounding (fixed summation tree) instead of bit for bit; others are unaffected. */
+  int64_t band_window;  /* banded operands: elements of the gathered vector per window.  0: CPPPD_BAND_WINDOW_MB
+                           megabytes (default 48 MB = 6 291 456 elements, the L2-resident plateau measured by
+                           tools/probe/gather_probe.cu) */
 } cpppd_problem;
 
 /* The numbers the reference's stats block produces (ChambollePockPPD.py:242-291). */
@@ -192,6 +207,12 @@ typedef struct {
   int32_t balanced_split;       /* world_size > 1: the locality buckets left some rank with more than 1.5x its share of
                                    the row or column entries, so rows / columns were dealt out by prefix sums instead */
   int32_t tiny_persistent;      /* iterations run in one persistent CTA (CPPPD_FLAG_TINY_PERSISTENT and a tiny LP) */
+  /* banded operands (CPPPD_FLAG_BANDED; [0]: A, used by the dual half, [1]: A^T, used by the primal half) */
+  int32_t band_windows[2];      /* windows of the gathered vector (= launches per half-iteration); 0: not built */
+  int32_t band_in_use[2];       /* the half-iteration runs the banded kernels */
+  float band_ms[2];             /* milliseconds per half-iteration measured at creation; 0 = not timed */
+  float band_sectors_per_gather[2]; /* sampled locality of the operand: distinct 32-byte sectors per gather of a warp */
+  int64_t band_window_bytes;    /* bytes of the gathered vector per window (largest window) */
 } cpppd_info;
 
 typedef enum {

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 KERNEL_VARIANTS = 7
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
@@ -26,6 +26,8 @@ FLAG_NO_REORDER = 1 << 6
 FLAG_FUSED_HALO = 1 << 7
 FLAG_NO_AUTOTUNE = 1 << 8
 FLAG_TINY_PERSISTENT = 1 << 9
+FLAG_BANDED = 1 << 10
+FLAG_NO_BANDED = 1 << 11
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 
@@ -42,6 +44,7 @@ class Problem(C.Structure):
         ("alloc", ALLOC_FN), ("free", FREE_FN), ("alloc_user", C.c_void_p),
         ("rank", C.c_int32), ("world_size", C.c_int32), ("comm_id", C.c_void_p),
         ("partition_granule", C.c_int64), ("comm", C.c_void_p), ("long_row_threshold", C.c_int64),
+        ("band_window", C.c_int64),
     ]
 
 
@@ -75,10 +78,15 @@ class Info(C.Structure):
         ("dual_variant", C.c_int32), ("autotuned", C.c_int32), ("variant_ms", (C.c_float * KERNEL_VARIANTS) * 2),
         ("long_rows", C.c_int64), ("long_cols", C.c_int64), ("long_entries", C.c_int64),
         ("balanced_split", C.c_int32), ("tiny_persistent", C.c_int32),
+        ("band_windows", C.c_int32 * 2), ("band_in_use", C.c_int32 * 2), ("band_ms", C.c_float * 2),
+        ("band_sectors_per_gather", C.c_float * 2), ("band_window_bytes", C.c_int64),
     ]
 
     def as_dict(self):
-        out = {name: getattr(self, name) for name, _ in self._fields_ if name not in ("variant_ms", "reserved")}
+        arrays = ("band_windows", "band_in_use", "band_ms", "band_sectors_per_gather")
+        out = {name: getattr(self, name) for name, _ in self._fields_ if name not in ("variant_ms", "reserved") + arrays}
+        for name in arrays:  # [A (dual half), A^T (primal half)]
+            out[name] = list(getattr(self, name))
         out["variant_ms"] = {"k_primal": list(self.variant_ms[0]), "k_dual": list(self.variant_ms[1])}
         return out
 

@@ -164,6 +164,7 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
   h->granule = P->partition_granule;
   h->variant_request = P->kernel_variant;
   h->long_threshold = P->long_row_threshold == 0 ? kLongDefault : P->long_row_threshold;
+  h->band_window = P->band_window;
   h->rank = P->rank;
   h->world = world;
   h->alloc = P->alloc;
@@ -481,9 +482,27 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   out->long_cols = h->longAT.count;
   out->long_entries = h->longA.nnz + h->longAT.nnz;
   vec_bytes += 12 * (h->longA.nnz + h->longAT.nnz) + 8 * (h->longA.nnz + h->longAT.nnz);  // entries + their gathers
-  out->bytes_per_iteration_actual = (h->A.padded + h->AT.padded) * entry_bytes +
-                                    (h->A.uniform_width >= 0 ? 0 : 8 * (h->A.nslices + 1)) +
-                                    (h->AT.uniform_width >= 0 ? 0 : 8 * (h->AT.nslices + 1)) + vec_bytes;
+  // an operand streams either its SELL slices or — banded — its entries once, one 4-byte pointer per row and
+  // window, and the carries (read + written between consecutive windows of a kind)
+  int64_t op_bytes[2];
+  const Sell *sell[2] = {&h->A, &h->AT};
+  const Band *band[2] = {&h->bandA, &h->bandAT};
+  for (int k = 0; k < 2; ++k) {
+    const Band &B = *band[k];
+    if (B.in_use) {
+      const int kinds = (B.geo.eq_windows ? 1 : 0) + (B.geo.windows > B.geo.eq_windows ? 1 : 0);
+      op_bytes[k] = 12 * B.nnz + 4 * (int64_t)B.geo.windows * (B.nrows + 1) + 16 * B.nrows * (B.geo.windows - kinds) +
+                    (kinds == 2 ? 16 * B.nrows : 0);
+    } else {
+      op_bytes[k] = sell[k]->padded * entry_bytes + (sell[k]->uniform_width >= 0 ? 0 : 8 * (sell[k]->nslices + 1));
+    }
+    out->band_windows[k] = B.built ? B.geo.windows : 0;
+    out->band_in_use[k] = B.in_use ? 1 : 0;
+    out->band_ms[k] = B.ms;
+    out->band_sectors_per_gather[k] = (float)B.sectors_per_gather;
+    if (B.built) out->band_window_bytes = std::max(out->band_window_bytes, B.win_bytes);
+  }
+  out->bytes_per_iteration_actual = op_bytes[0] + op_bytes[1] + vec_bytes;
   out->value_bytes = h->A.dict ? 0 : 8;
   out->const_vector_mask = h->const_mask;
   out->sm_count = h->sm_count;

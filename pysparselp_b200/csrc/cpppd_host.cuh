@@ -86,6 +86,90 @@ int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   return 0;
 }
 
+// elements of the gathered vector per window: cpppd_problem.band_window, CPPPD_BAND_WINDOW_MB, or 48 MB — the
+// largest window tools/probe/gather_probe.cu still found at the L2-hit plateau with the matrix streaming past it
+int64_t band_window_elems(const cpppd_solver *h) {
+  if (h->band_window > 0) return h->band_window;
+  if (const char *env = getenv("CPPPD_BAND_WINDOW"))
+    if (atoll(env) > 0) return atoll(env);
+  double mb = 48.0;
+  if (const char *env = getenv("CPPPD_BAND_WINDOW_MB")) mb = atof(env);
+  return std::max<int64_t>(32, (int64_t)(mb * 1048576.0 / 8.0));
+}
+
+// sampled sectors per gather of a thread-per-row kernel on this CSR (1.0: no two lanes ever share a sector)
+int band_locality(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, int64_t nrows, double *out) {
+  *out = 0.0;
+  if (nrows == 0) return 0;
+  Scratch tmp(h);
+  unsigned long long *acc = nullptr, host[2] = {0, 0};
+  if (int rc = tmp.get(&acc, 2)) return rc;
+  CK(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), h->stream));
+  const int64_t warps = (nrows + 31) / 32, sampled = std::min<int64_t>(warps, 8192), stride = std::max<int64_t>(1, warps / sampled);
+  k_band_locality<<<grid_for(sampled * 32), kBlock, 0, h->stream>>>(rowptr, indices, nrows, stride, acc);
+  CK(cudaMemcpyAsync(host, acc, sizeof host, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (host[1]) *out = (double)host[0] / (double)host[1];
+  return 0;
+}
+
+// CSR (device, int64 rowptr; A^T entries may carry kEqBit) -> window-major copy (cpppd_banded.cuh).
+// vec_len: length of the gathered vector; split: its first element that belongs to an inequality row (A^T) or 0.
+// Leaves out->built false (and frees nothing it did not allocate persistently) when the operand does not qualify.
+int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, const double *values, int64_t nrows,
+               int64_t nnz, int64_t vec_len, int64_t split, bool forced, Band *out) {
+  if (nrows == 0 || nnz == 0 || vec_len == 0) return 0;
+  cudaStream_t st = h->stream;
+  const int64_t target = band_window_elems(h);
+  if (int rc = band_locality(h, rowptr, indices, nrows, &out->sectors_per_gather)) return rc;
+  // worth it when the gathers of a row-streaming pass cannot stay in L2 on their own: a vector of more than two
+  // windows gathered without locality
+  if (!forced && !(vec_len > 2 * target && out->sectors_per_gather > 0.6)) return 0;
+  BandGeometry geo{split, 1, 1, 0, 0};
+  if (split > 0) {
+    geo.eq_windows = (int)((split + target - 1) / target);
+    geo.eq_elems = (split + geo.eq_windows - 1) / geo.eq_windows;
+  }
+  int in_windows = 0;
+  if (vec_len > split) {
+    in_windows = (int)((vec_len - split + target - 1) / target);
+    geo.in_elems = (vec_len - split + in_windows - 1) / in_windows;
+  }
+  geo.windows = geo.eq_windows + in_windows;
+  if (geo.windows > 4096) return 0;
+  const int64_t stride = nrows + 1, cells = (int64_t)geo.windows * stride;
+  Scratch tmp(h);
+  uint32_t *cnt = nullptr, *ptr = nullptr;
+  int *flag = nullptr;
+  if (int rc = tmp.get(&cnt, cells)) return rc;
+  if (int rc = tmp.get(&flag, 1)) return rc;
+  CK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * cells, st));
+  CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  k_band_count<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, nrows, geo, cnt, flag);
+  int unordered = 0;
+  CK(cudaMemcpyAsync(&unordered, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (unordered) return 0;  // some row visits its windows out of order: banding would change its summation order
+  if (int rc = alloc_array(h, &ptr, cells)) return rc;
+  if (int rc = exclusive_scan(h, cnt, ptr, cells)) return rc;
+  tmp.release(cnt);
+  out->ptr = ptr;
+  if (int rc = alloc_array(h, &out->idx, nnz)) return rc;
+  if (int rc = alloc_array(h, &out->val, nnz)) return rc;
+  if (int rc = alloc_array(h, &out->carry, nrows)) return rc;
+  if (geo.eq_windows && in_windows)
+    if (int rc = alloc_array(h, &out->carry_eq, nrows)) return rc;
+  k_band_fill<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, values, nrows, geo, ptr, out->idx, out->val);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  out->geo = geo;
+  out->nrows = nrows;
+  out->nnz = nnz;
+  out->win_bytes = 8 * std::max(geo.eq_windows ? geo.eq_elems : 0, in_windows ? geo.in_elems : 0);
+  out->built = true;
+  return 0;
+}
+
 int upload_f64(cpppd_solver *h, double *dst, const double *src, int64_t count) {
   if (count == 0) return 0;
   CK(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
@@ -497,7 +581,17 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   if (nnz) k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, entry_id);
 
   bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
-  if (!reorder && nnz && !(h->flags & CPPPD_FLAG_NO_REORDER)) {
+  // Banded operands (cpppd_banded.cuh) keep the caller's numbering: the window order along a row is what keeps
+  // the sums bit-exact.  Candidates: forced by flag, or a pattern without locality over vectors of several windows.
+  const bool band_ok = !reorder && nnz > 0 && !(h->flags & (CPPPD_FLAG_NO_BANDED | CPPPD_FLAG_VALUE_DICT));
+  const bool band_forced = band_ok && (h->flags & CPPPD_FLAG_BANDED);
+  bool band_candidate = band_forced;
+  if (band_ok && !band_forced && std::max(n, m) > 2 * band_window_elems(h)) {
+    double spg = 0.0;
+    if (int rc = band_locality(h, rowptr, indices, m, &spg)) return rc;
+    band_candidate = spg > 0.6;
+  }
+  if (!reorder && nnz && !band_candidate && !(h->flags & CPPPD_FLAG_NO_REORDER)) {
     // keep the caller's numbering unless SELL-32 would pad it by more than 15 %: then renumber
     // (rows / columns of equal length are grouped inside locality buckets)
     int32_t *col_len = nullptr;
@@ -744,6 +838,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
     } else {
       if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
+      if (band_candidate)
+        if (int rc = build_band(h, rowptr, indices, values, m, nnz, n, 0, band_forced, &h->bandA)) return rc;
     }
   } else {
     int64_t *len = nullptr, *lrowptr = nullptr;
@@ -821,6 +917,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
     } else {
       if (int rc = build_sell(h, lcolptr, t_idx, t_val, nloc, &h->AT)) return rc;
+      if (band_candidate && !reorder)
+        if (int rc = build_band(h, lcolptr, t_idx, t_val, nloc, lnnz, mloc, m_eq, band_forced, &h->bandAT)) return rc;
     }
     tmp.release(lcolptr); tmp.release(t_idx); tmp.release(t_val);
   }
@@ -906,6 +1004,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   CK(cudaStreamSynchronize(st));
   // a single CTA can carry a whole iteration when both operands fit the L1 of one SM (see k_tiny_iterate)
   h->tiny = (h->flags & CPPPD_FLAG_TINY_PERSISTENT) && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
+            !h->bandA.built && !h->bandAT.built &&
             std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
   if (int rc = tune_kernels(h)) return rc;
   if (want_p2p)
@@ -929,7 +1028,50 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
 
 // Primal half + xbar halo.  world > 1: k_push / k_wait kernels over peer memory (default), the kernel itself
 // waits, pushes and signals (CPPPD_FLAG_FUSED_HALO), or NCCL send/recv (CPPPD_FLAG_NO_P2P).
+// one launch per window of the gathered vector (cpppd_banded.cuh)
+constexpr int kBandVariant = -2;  // `variant` argument of launch_primal / launch_dual: time the banded kernels
+int launch_primal_band(cpppd_solver *h, bool write_d) {
+  const Band &B = h->bandAT;
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  const int grid = grid_for(B.nrows);
+  for (int w = 0; w < B.geo.windows; ++w) {
+    const bool eq = w < B.geo.eq_windows;
+    const int mode = ((w == 0 || w == B.geo.eq_windows) ? kBandStart : 0) | (w == B.geo.windows - 1 ? kBandLast : 0) |
+                     (eq ? kBandEq : 0);
+    const uint32_t *ptr = B.ptr + (int64_t)w * (B.nrows + 1);
+    double *ceq = B.carry_eq ? B.carry_eq : B.carry;  // one kind of rows only: a single carry serves it
+    if (write_d)
+      k_primal_band<true><<<grid, kBlock, 0, h->stream>>>(ptr, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb,
+                                                         h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
+                                                         h->one_plus_theta);
+    else
+      k_primal_band<false><<<grid, kBlock, 0, h->stream>>>(ptr, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb,
+                                                          h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
+                                                          h->one_plus_theta);
+  }
+  return 0;
+}
+
+int launch_dual_band(cpppd_solver *h) {
+  const Band &B = h->bandA;
+  const int grid = grid_for(B.nrows), W = B.geo.windows;
+  for (int w = 0; w < W; ++w) {
+    const uint32_t *ptr = B.ptr + (int64_t)w * (B.nrows + 1);
+    const bool first = w == 0, last = w == W - 1;
+#define CPPPD_DUAL_BAND(F, L)                                                                                       \
+  k_dual_band<F, L><<<grid, kBlock, 0, h->stream>>>(ptr, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, h->m, \
+                                                    h->m_eq)
+    if (first && last) CPPPD_DUAL_BAND(true, true);
+    else if (first) CPPPD_DUAL_BAND(true, false);
+    else if (last) CPPPD_DUAL_BAND(false, true);
+    else CPPPD_DUAL_BAND(false, false);
+#undef CPPPD_DUAL_BAND
+  }
+  return 0;
+}
+
 int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
+  if (variant == kBandVariant || (variant == -1 && h->bandAT.in_use)) return launch_primal_band(h, write_d);
   P2P &pp = h->p2p;
   const FusedComm *cm = pp.use_fused ? pp.fused[0] : nullptr;
   if (int rc = long_pass(h, h->longAT, h->y, h->y)) return rc;  // long columns: their A^T y into the tail of y
@@ -947,6 +1089,7 @@ int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
 }
 
 int launch_dual(cpppd_solver *h, int variant = -1) {
+  if (variant == kBandVariant || (variant == -1 && h->bandA.in_use)) return launch_dual_band(h);
   P2P &pp = h->p2p;
   const FusedComm *cm = pp.use_fused ? pp.fused[1] : nullptr;
   if (int rc = long_pass(h, h->longA, h->xbar, h->xbar)) return rc;  // long rows: their A xbar into the tail of xbar
@@ -963,10 +1106,12 @@ int launch_dual(cpppd_solver *h, int variant = -1) {
 
 // Process-wide memory of tune_kernels(): the timings depend on the device and on the shape of the two SELL
 // operands (slices, stored entries, uniform widths, long rows, storage variant, numbering), not on the values.
-using TuneKey = std::array<int64_t, 15>;
+using TuneKey = std::array<int64_t, 17>;
 struct TuneChoice {
   int primal = 0, dual = 0;
   float ms[2][CPPPD_KERNEL_VARIANTS] = {};
+  bool band_primal = false, band_dual = false;
+  float band_ms[2] = {0.f, 0.f};
 };
 std::map<TuneKey, TuneChoice> g_tune_cache;
 std::mutex g_tune_mutex;
@@ -975,7 +1120,8 @@ TuneKey tune_key(const cpppd_solver *h) {
   return TuneKey{h->device,          h->n,          h->m,           h->A.nslices,        h->A.padded,
                  h->A.uniform_width, h->AT.nslices, h->AT.padded,   h->AT.uniform_width, h->longA.nnz,
                  h->longAT.nnz,      h->A.dict ? h->ndict : 0, h->const_mask, h->hx.ghost + h->hy.ghost,
-                 h->identity_layout ? 0 : 1 + h->granule};
+                 h->identity_layout ? 0 : 1 + h->granule,
+                 h->bandA.built ? h->bandA.geo.windows : 0, h->bandAT.built ? h->bandAT.geo.windows : 0};
 }
 
 // Choose the kernel variants (called at the end of setup(), before any neighbour may write into this
@@ -986,6 +1132,9 @@ TuneKey tune_key(const cpppd_solver *h) {
 // The iterates do not depend on the choice; the state (x, xbar, y) is put back afterwards.  A measured choice is
 // remembered per process and operand shape (g_tune_cache; CPPPD_AUTOTUNE_CACHE=0 measures every time).
 int tune_kernels(cpppd_solver *h) {
+  // a banded operand is used unless the timing below finds the SELL kernel faster
+  h->bandA.in_use = h->bandA.built;
+  h->bandAT.in_use = h->bandAT.built;
   int request = h->variant_request;
   if (request == 0)
     if (const char *env = getenv("CPPPD_KERNEL_VARIANT")) request = atoi(env);
@@ -995,6 +1144,7 @@ int tune_kernels(cpppd_solver *h) {
       return fail(h, CPPPD_ERR_INVALID, "kernel_variant %d: variants are 1 .. %d", request, kNumVariants);
     h->primal_variant = p - 1;
     h->dual_variant = d - 1;
+    if (!(h->flags & CPPPD_FLAG_BANDED)) h->bandA.in_use = h->bandAT.in_use = false;  // the caller asked for a SELL variant
     return 0;
   }
   int64_t min_nnz = (int64_t)1 << 22;
@@ -1012,6 +1162,10 @@ int tune_kernels(cpppd_solver *h) {
       h->primal_variant = hit->second.primal;
       h->dual_variant = hit->second.dual;
       memcpy(h->variant_ms, hit->second.ms, sizeof h->variant_ms);
+      h->bandAT.in_use = hit->second.band_primal;
+      h->bandA.in_use = hit->second.band_dual;
+      h->bandAT.ms = hit->second.band_ms[0];
+      h->bandA.ms = hit->second.band_ms[1];
       h->autotuned = true;
       return 0;
     }
@@ -1049,6 +1203,23 @@ int tune_kernels(cpppd_solver *h) {
       if (h->variant_ms[kind][v] < h->variant_ms[kind][best]) best = v;
     if (best != 0 && h->variant_ms[kind][best] > 0.98f * h->variant_ms[kind][0]) best = 0;
     (kind == 0 ? h->primal_variant : h->dual_variant) = best;
+    // the banded copy of the operand, when it was built: same protocol, against the best SELL variant
+    Band &band = kind == 0 ? h->bandAT : h->bandA;
+    if (band.built && !(h->flags & CPPPD_FLAG_BANDED)) {
+      for (int pass = 0; pass < 3 && !rc; ++pass) {
+        float ms = 0.f;
+        if (pass > 0) CK(cudaEventRecord(e0, st));
+        for (int rep = 0; rep < (pass > 0 ? 2 : 1) && !rc; ++rep)
+          rc = kind == 0 ? launch_primal(h, false, kBandVariant) : launch_dual(h, kBandVariant);
+        if (rc || pass == 0) continue;
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= 2;
+        if (pass == 1 || ms < band.ms) band.ms = ms;
+      }
+      band.in_use = !rc && band.ms < 0.98f * h->variant_ms[kind][best];
+    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
@@ -1059,6 +1230,10 @@ int tune_kernels(cpppd_solver *h) {
     choice.primal = h->primal_variant;
     choice.dual = h->dual_variant;
     memcpy(choice.ms, h->variant_ms, sizeof choice.ms);
+    choice.band_primal = h->bandAT.in_use;
+    choice.band_dual = h->bandA.in_use;
+    choice.band_ms[0] = h->bandAT.ms;
+    choice.band_ms[1] = h->bandA.ms;
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     g_tune_cache[key] = choice;
   }

@@ -27,6 +27,7 @@
 #include "cpppd_device_types.cuh"
 #include "cpppd_device.cuh"
 #include "cpppd_long_rows.cuh"
+#include "cpppd_banded.cuh"
 
 namespace {
 
@@ -42,6 +43,20 @@ struct Sell {
   // 32-bit word  [pad:1][eq:1][code][index]  and its value is dict[code] (the exact original double)
   const double *dict = nullptr;
   int idx_bits = 30, ndict = 0;
+};
+
+// Window-major copy of an operand for patterns without locality (cpppd_banded.cuh)
+struct Band {
+  bool built = false;   // the window-major arrays exist
+  bool in_use = false;  // the half-iteration runs k_*_band (one launch per window) instead of the SELL kernel
+  BandGeometry geo{0, 1, 1, 0, 0};
+  int64_t nrows = 0, nnz = 0, win_bytes = 0;
+  uint32_t *ptr = nullptr;  // windows * (nrows + 1) offsets into idx / val (exclusive scan, window-major)
+  int32_t *idx = nullptr;
+  double *val = nullptr;
+  double *carry = nullptr, *carry_eq = nullptr;  // partial sums between windows (carry_eq: A^T with both row kinds)
+  double sectors_per_gather = 0;                  // sampled locality of the operand (k_band_locality)
+  float ms = 0.f;                                 // per half-iteration, measured by tune_kernels()
 };
 
 struct StatsDev {  // device-resident, copied verbatim into cpppd_stats
@@ -155,6 +170,8 @@ struct cpppd_solver {
   std::vector<void *> owned;
   int64_t device_bytes = 0;
   Sell A, AT;
+  Band bandA, bandAT;            // window-major copies for patterns without locality (cpppd_banded.cuh)
+  int64_t band_window = 0;       // elements of the gathered vector per window (cpppd_problem.band_window)
   LongRows longA, longAT;        // rows of A / columns of A cut out of the SELL operands (cpppd_long_rows.cuh)
   int64_t long_threshold = 0;    // rows with more entries are long; < 0: never
   int64_t x_len = 0, y_len = 0;  // allocated length of x-like / y-like vectors (owned + ghosts + long-row tails)

@@ -228,6 +228,7 @@ template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldca(const T *p) { return *p; }
 template <typename T> inline T __ldcg(const T *p) { return *p; }
+template <typename T> inline void __stcs(T *p, T v) { *p = v; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }

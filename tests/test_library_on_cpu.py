@@ -383,3 +383,37 @@ def test_emulated_tiny_persistent_kernel(name, flags):
     x, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=20, nb_iter_plot=10, flags=_cabi.FLAG_TINY_PERSISTENT)
     assert solver.info()["tiny_persistent"] == 0
     solver.close()
+
+
+@pytest.mark.parametrize("window", ["small", "single"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_emulated_banded_operands_give_the_same_bits(name, window, monkeypatch):
+    """CPPPD_FLAG_BANDED (cpppd_banded.cuh): window-major operands, one launch per window of the gathered vector,
+    partial row sums carried in memory between windows.  Rows with ascending column indices keep their summation
+    order, so the iterates are the golden bits for every window size (7 elements: dozens of windows per pass;
+    100000: a single window).  Operands whose rows are not window-ordered must stay with the SELL kernels."""
+    window = 100000 if window == "single" else (997 if name in ("potts50", "l1svm") else 7)
+    monkeypatch.setenv("CPPPD_BAND_WINDOW", str(window))
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    trace = []
+    x, best, solver = emulated_chambolle_pock_ppd(
+        *args, nb_max_iter=100, nb_iter_plot=10, flags=_cabi.FLAG_BANDED,
+        callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)), **kw)
+    try:
+        info = solver.info()
+        y = solver.get_y()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        # A^T is window-ordered by construction (columns sorted by source row): always banded
+        assert info["band_in_use"][1] == 1 and info["band_windows"][1] >= 1
+        if window < 100000:
+            assert info["band_windows"][1] > 2
+        if name in ("sc105", "random_small", "afiro", "kb2"):  # rows with ascending column indices: A as well
+            assert info["band_in_use"][0] == 1
+        if "alpha" not in kw:
+            assert np.array_equal(x, g["x_100"]) and np.array_equal(y, y_gold)
+        else:
+            assert rel_inf(x, g["x_100"]) <= 1e-9 and rel_inf(y, y_gold) <= 1e-9
+        curves_close(np.array(trace), g["trace_10"])
+    finally:
+        solver.close()

@@ -11,6 +11,11 @@ echo "== 0. box" | tee $log
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.limit --format=csv >> $log 2>&1
 nproc >> $log; free -g | head -2 >> $log
 
+echo "== 0b. GPU tests" | tee -a $log
+timeout 600 python -m pytest tests -m gpu -x -q --durations=10 > $out/${tag}_pytest_gpu.log 2>&1
+echo "pytest exit $?" | tee -a $log
+tail -3 $out/${tag}_pytest_gpu.log | tee -a $log
+
 echo "== 1. gather probe (L2 window sweep)" | tee -a $log
 timeout 300 tools/probe/gather_probe > $out/${tag}_gather_probe.jsonl 2>&1
 echo "probe exit $?" | tee -a $log
