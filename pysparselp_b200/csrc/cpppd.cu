@@ -177,6 +177,10 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
       break;
     }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    // experiment knob: bytes the L2 fetches from DRAM per missing sector (device-wide limit, default 64).  Random
+    // 8-byte gathers that miss L2 otherwise pull two sectors for one (profiles/r02_random_lp.md)
+    if (const char *env = getenv("CPPPD_L2_FETCH_GRANULARITY"))
+      if (atoi(env) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(env));
     if (P->stream) {
       h->stream = (cudaStream_t)P->stream;
     } else {
@@ -482,8 +486,8 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   out->long_cols = h->longAT.count;
   out->long_entries = h->longA.nnz + h->longAT.nnz;
   vec_bytes += 12 * (h->longA.nnz + h->longAT.nnz) + 8 * (h->longA.nnz + h->longAT.nnz);  // entries + their gathers
-  // an operand streams either its SELL slices or — banded — its entries once, one 4-byte pointer per row and
-  // window, and the carries (read + written between consecutive windows of a kind)
+  // an operand streams either its SELL slices or — banded — its entries once, one count byte per row and one offset
+  // per tile and window, and the carries (read + written between consecutive windows of a kind)
   int64_t op_bytes[2];
   const Sell *sell[2] = {&h->A, &h->AT};
   const Band *band[2] = {&h->bandA, &h->bandAT};
@@ -491,7 +495,7 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
     const Band &B = *band[k];
     if (B.in_use) {
       const int kinds = (B.geo.eq_windows ? 1 : 0) + (B.geo.windows > B.geo.eq_windows ? 1 : 0);
-      op_bytes[k] = 12 * B.nnz + 4 * (int64_t)B.geo.windows * (B.nrows + 1) + 16 * B.nrows * (B.geo.windows - kinds) +
+      op_bytes[k] = 12 * B.nnz + (int64_t)B.geo.windows * (B.rows_pad + B.rows_pad / 8) + 16 * B.nrows * (B.geo.windows - kinds) +
                     (kinds == 2 ? 16 * B.nrows : 0);
     } else {
       op_bytes[k] = sell[k]->padded * entry_bytes + (sell[k]->uniform_width >= 0 ? 0 : 8 * (sell[k]->nslices + 1));

@@ -137,31 +137,42 @@ int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   }
   geo.windows = geo.eq_windows + in_windows;
   if (geo.windows > 4096) return 0;
-  const int64_t stride = nrows + 1, cells = (int64_t)geo.windows * stride;
+  const int64_t rows_pad = (nrows + 31) / 32 * 32, ntiles = rows_pad / 32, cells = (int64_t)geo.windows * ntiles;
   Scratch tmp(h);
-  uint32_t *cnt = nullptr, *ptr = nullptr;
+  uint32_t *total = nullptr;
   int *flag = nullptr;
-  if (int rc = tmp.get(&cnt, cells)) return rc;
+  if (int rc = tmp.get(&total, cells + 1)) return rc;
   if (int rc = tmp.get(&flag, 1)) return rc;
-  CK(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * cells, st));
+  unsigned char *cnt = static_cast<unsigned char *>(dev_alloc(h, (size_t)geo.windows * rows_pad, false));
+  if (!cnt) return fail(h, CPPPD_ERR_NOMEM, "device allocation of the window counts failed");
+  CK(cudaMemsetAsync(cnt, 0, (size_t)geo.windows * rows_pad, st));
   CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
-  k_band_count<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, nrows, geo, cnt, flag);
-  int unordered = 0;
-  CK(cudaMemcpyAsync(&unordered, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemsetAsync(total + cells, 0, sizeof(uint32_t), st));
+  k_band_count<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, nrows, rows_pad, geo, cnt, flag);
+  int bad = 0;
+  CK(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (unordered) return 0;  // some row visits its windows out of order: banding would change its summation order
-  if (int rc = alloc_array(h, &ptr, cells)) return rc;
-  if (int rc = exclusive_scan(h, cnt, ptr, cells)) return rc;
-  tmp.release(cnt);
-  out->ptr = ptr;
+  if (bad) {  // a row visits its windows out of order (banding would change its summation order) or is too dense
+    dev_free(h, cnt);
+    return 0;
+  }
+  h->owned.push_back(cnt);
+  h->device_bytes += (int64_t)geo.windows * rows_pad;
+  out->cnt = cnt;
+  k_band_tile_totals<<<grid_for(cells), kBlock, 0, st>>>(cnt, cells, total);
+  if (int rc = alloc_array(h, &out->tile_base, cells + 1)) return rc;
+  if (int rc = exclusive_scan(h, total, out->tile_base, cells + 1)) return rc;
+  tmp.release(total);
   if (int rc = alloc_array(h, &out->idx, nnz)) return rc;
   if (int rc = alloc_array(h, &out->val, nnz)) return rc;
   if (int rc = alloc_array(h, &out->carry, nrows)) return rc;
   if (geo.eq_windows && in_windows)
     if (int rc = alloc_array(h, &out->carry_eq, nrows)) return rc;
-  k_band_fill<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, values, nrows, geo, ptr, out->idx, out->val);
+  k_band_fill<<<grid_for(rows_pad), kBlock, 0, st>>>(rowptr, indices, values, nrows, rows_pad, geo.windows, cnt, out->tile_base,
+                                                    out->idx, out->val);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
+  out->rows_pad = rows_pad;
   out->geo = geo;
   out->nrows = nrows;
   out->nnz = nnz;
@@ -1033,34 +1044,38 @@ constexpr int kBandVariant = -2;  // `variant` argument of launch_primal / launc
 int launch_primal_band(cpppd_solver *h, bool write_d) {
   const Band &B = h->bandAT;
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-  const int grid = grid_for(B.nrows);
+  const int grid = grid_for(B.rows_pad);
+  const int64_t ntiles = B.rows_pad / 32;
   for (int w = 0; w < B.geo.windows; ++w) {
     const bool eq = w < B.geo.eq_windows;
     const int mode = ((w == 0 || w == B.geo.eq_windows) ? kBandStart : 0) | (w == B.geo.windows - 1 ? kBandLast : 0) |
                      (eq ? kBandEq : 0);
-    const uint32_t *ptr = B.ptr + (int64_t)w * (B.nrows + 1);
+    const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
+    const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     double *ceq = B.carry_eq ? B.carry_eq : B.carry;  // one kind of rows only: a single carry serves it
     if (write_d)
-      k_primal_band<true><<<grid, kBlock, 0, h->stream>>>(ptr, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb,
-                                                         h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
-                                                         h->one_plus_theta);
+      k_primal_band<true><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT,
+                                                         h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, B.rows_pad, has_eq,
+                                                         has_ineq, h->theta, h->one_plus_theta);
     else
-      k_primal_band<false><<<grid, kBlock, 0, h->stream>>>(ptr, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb,
-                                                          h->vub, h->x, h->xbar, h->dbuf, h->n, has_eq, has_ineq, h->theta,
-                                                          h->one_plus_theta);
+      k_primal_band<false><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT,
+                                                          h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, B.rows_pad, has_eq,
+                                                          has_ineq, h->theta, h->one_plus_theta);
   }
   return 0;
 }
 
 int launch_dual_band(cpppd_solver *h) {
   const Band &B = h->bandA;
-  const int grid = grid_for(B.nrows), W = B.geo.windows;
+  const int grid = grid_for(B.rows_pad), W = B.geo.windows;
+  const int64_t ntiles = B.rows_pad / 32;
   for (int w = 0; w < W; ++w) {
-    const uint32_t *ptr = B.ptr + (int64_t)w * (B.nrows + 1);
+    const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
+    const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     const bool first = w == 0, last = w == W - 1;
-#define CPPPD_DUAL_BAND(F, L)                                                                                       \
-  k_dual_band<F, L><<<grid, kBlock, 0, h->stream>>>(ptr, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, h->m, \
-                                                    h->m_eq)
+#define CPPPD_DUAL_BAND(F, L)                                                                                          \
+  k_dual_band<F, L><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, \
+                                                    h->m, B.rows_pad, h->m_eq)
     if (first && last) CPPPD_DUAL_BAND(true, true);
     else if (first) CPPPD_DUAL_BAND(true, false);
     else if (last) CPPPD_DUAL_BAND(false, true);
@@ -1162,8 +1177,10 @@ int tune_kernels(cpppd_solver *h) {
       h->primal_variant = hit->second.primal;
       h->dual_variant = hit->second.dual;
       memcpy(h->variant_ms, hit->second.ms, sizeof h->variant_ms);
-      h->bandAT.in_use = hit->second.band_primal;
-      h->bandA.in_use = hit->second.band_dual;
+      if (!(h->flags & CPPPD_FLAG_BANDED)) {  // (forced: stays in use whatever an earlier timing said)
+        h->bandAT.in_use = hit->second.band_primal;
+        h->bandA.in_use = hit->second.band_dual;
+      }
       h->bandAT.ms = hit->second.band_ms[0];
       h->bandA.ms = hit->second.band_ms[1];
       h->autotuned = true;
@@ -1205,7 +1222,7 @@ int tune_kernels(cpppd_solver *h) {
     (kind == 0 ? h->primal_variant : h->dual_variant) = best;
     // the banded copy of the operand, when it was built: same protocol, against the best SELL variant
     Band &band = kind == 0 ? h->bandAT : h->bandA;
-    if (band.built && !(h->flags & CPPPD_FLAG_BANDED)) {
+    if (band.built) {
       for (int pass = 0; pass < 3 && !rc; ++pass) {
         float ms = 0.f;
         if (pass > 0) CK(cudaEventRecord(e0, st));
@@ -1218,7 +1235,7 @@ int tune_kernels(cpppd_solver *h) {
         ms /= 2;
         if (pass == 1 || ms < band.ms) band.ms = ms;
       }
-      band.in_use = !rc && band.ms < 0.98f * h->variant_ms[kind][best];
+      band.in_use = (h->flags & CPPPD_FLAG_BANDED) || (!rc && band.ms < 0.98f * h->variant_ms[kind][best]);
     }
   }
   cudaEventDestroy(e0);
@@ -1230,8 +1247,8 @@ int tune_kernels(cpppd_solver *h) {
     choice.primal = h->primal_variant;
     choice.dual = h->dual_variant;
     memcpy(choice.ms, h->variant_ms, sizeof choice.ms);
-    choice.band_primal = h->bandAT.in_use;
-    choice.band_dual = h->bandA.in_use;
+    choice.band_primal = h->bandAT.built && h->bandAT.ms > 0.f && h->bandAT.ms < 0.98f * h->variant_ms[0][h->primal_variant];
+    choice.band_dual = h->bandA.built && h->bandA.ms > 0.f && h->bandA.ms < 0.98f * h->variant_ms[1][h->dual_variant];
     choice.band_ms[0] = h->bandAT.ms;
     choice.band_ms[1] = h->bandA.ms;
     std::lock_guard<std::mutex> lock(g_tune_mutex);

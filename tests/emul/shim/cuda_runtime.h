@@ -210,6 +210,23 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   emul::arrive_and_wait(b.warp_bar[w], b.warp_live[w]);
   return out;
 }
+inline unsigned __ballot_sync(unsigned, int pred) {
+  emul::BlockState &b = emul::g_block;
+  const int t = b.current, w = t >> 5;
+  const int v = pred ? 1 : 0;
+  memcpy(b.slot[t], &v, sizeof v);
+  emul::arrive_and_wait(b.warp_bar[w], b.warp_live[w]);
+  unsigned out = 0;
+  for (int l = 0; l < 32; ++l) {
+    const int src = (t & ~31) | l;
+    int sv = 0;
+    if (src < b.nthreads && !b.fibers[src].done) memcpy(&sv, b.slot[src], sizeof sv);
+    if (sv) out |= 1u << l;
+  }
+  emul::arrive_and_wait(b.warp_bar[w], b.warp_live[w]);
+  return out;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __any_sync(unsigned, int pred) {
   int v = pred ? 1 : 0;
   for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
@@ -264,6 +281,8 @@ inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 4; return cudaSuccess; }  // 4 "SMs"
+enum { cudaLimitMaxL2FetchGranularity = 5 };
+inline cudaError_t cudaDeviceSetLimit(int, size_t) { return cudaSuccess; }
 // Device memory is NOT zero-initialised on a GPU (and torch's caching allocator hands out recycled blocks), while
 // a fresh malloc usually is: every allocation is filled with a poison byte so that a kernel relying on zeros fails
 // here too (0x5A: doubles become 5.6e129, int32 indices 1.5e9).  CPPPD_EMUL_POISON=<byte> changes it, -1 disables.

@@ -29,7 +29,9 @@ def test_banded_iterates_vs_golden(name, window, monkeypatch):
     from pysparselp_b200 import _cabi
     from pysparselp_b200.ChambollePockPPD import chambolle_pock_ppd
 
-    if window == 7 and name in ("potts50", "l1svm"):
+    if name == "l1svm":
+        window = 199 if window == 7 else 251  # (weight columns of ~1 350 entries: at most 255 per window, one count byte)
+    elif window == 7 and name == "potts50":
         window = 997  # (1400 launches per half-iteration otherwise)
     monkeypatch.setenv("CPPPD_BAND_WINDOW", str(window))
     args, g = case_args(name)

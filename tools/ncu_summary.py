@@ -19,10 +19,33 @@ METRICS = [
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
 ]
 
+VARIANTS = {(0, 8, 1): "loop-unroll4/8cta", (2, 8, 1): "chunk2/8cta", (4, 6, 1): "chunk4/6cta", (4, 4, 1): "chunk4/4cta",
+            (8, 4, 1): "chunk8/4cta", (4, 3, 2): "rows2-chunk4/3cta", (2, 4, 2): "rows2-chunk2/4cta"}
+
+
 def short(name):
-    for k in ("k_primal", "k_dual", "k_stats_rows", "k_stats_cols", "k_stats_final", "k_precond", "k_fill_sell"):
+    """k_primal<kWriteD, kDict, kChunk, kMinB, kComm, kRows> / k_dual<kDict, kChunk, kMinB, kComm, kRows> ->
+    'k_primal[chunk2/8cta]' (+ ',dict' / ',write_d' / ',fused-halo'): the key bench.py looks its traffic up with."""
+    import re
+
+    m = re.search(r"(k_primal|k_dual)<([^>]*)>", name)
+    if m:
+        t = [int(v.replace("(bool)", "").replace("(int)", "")) for v in m.group(2).split(",")]
+        if m.group(1) == "k_primal":
+            write_d, dict_, chunk, minb, comm, rows = (t + [1])[:6]
+        else:
+            write_d = 0
+            dict_, chunk, minb, comm, rows = (t + [1])[:5]
+        tags = [VARIANTS.get((chunk, minb, rows), "chunk%d/%dcta/rows%d" % (chunk, minb, rows))]
+        tags += ["dict"] * bool(dict_) + ["write_d"] * bool(write_d) + ["fused-halo"] * bool(comm)
+        return "%s[%s]" % (m.group(1), ",".join(tags))
+    m = re.search(r"(k_primal_band|k_dual_band)<([^>]*)>", name)
+    if m:
+        return "%s<%s>" % (m.group(1), m.group(2).replace(" ", "").replace("(bool)", ""))
+    for k in ("k_stats_rows", "k_stats_cols", "k_stats_final", "k_precond", "k_fill_sell", "k_push", "k_wait", "k_long_partial",
+              "k_long_finish", "k_tiny_iterate"):
         if k in name:
-            return k + ("<write_d>" if "k_primal<1>" in name or "k_primal<(bool)1>" in name else "")
+            return k
     return name.split("(")[0][-60:]
 
 def to_bytes(val, unit):
@@ -47,7 +70,7 @@ if a.rep:
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, body = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
-    out_rows, per = [], collections.defaultdict(list)
+    out_rows, per, extra = [], collections.defaultdict(list), {}
     for r in body:
         name = short(r[idx["Kernel Name"]])
         rec = {"kernel": name}
@@ -58,6 +81,8 @@ if a.rep:
         wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
         rec["dram_bytes_total"] = rd + wr
         per[name].append(rd + wr)
+        extra.setdefault(name, []).append((float(r[idx["gpu__time_duration.sum"]].replace(",", "")), units[idx["gpu__time_duration.sum"]],
+                                           float(r[idx["lts__t_sector_hit_rate.pct"]].replace(",", ""))))
         out_rows.append(rec)
     with open(os.path.join(ROOT, "profiles", a.tag + "_kernels.csv"), "w", newline="") as f:
         w = csv.DictWriter(f, fieldnames=["kernel", "dram_bytes_total"] + [m for m in METRICS if m in idx])
@@ -66,6 +91,8 @@ if a.rep:
             w.writerow(rec)
     for name, vals in per.items():
         summary["kernels"][name] = {"dram_bytes_per_launch": sum(vals) / len(vals), "launches_captured": len(vals),
+                                    "duration_%s" % extra[name][0][1]: sum(e[0] for e in extra[name]) / len(vals),
+                                    "l2_sector_hit_rate_pct": sum(e[2] for e in extra[name]) / len(vals),
                                     "source": a.tag + "_kernels.csv (ncu --set full --clock-control none)"}
     print("captured launches:", {k: len(v) for k, v in per.items()})
 
