@@ -81,18 +81,23 @@ def one_sided_rows(a_ineq, b_lower, b_upper):
 class _TorchBuffers:
     """Device buffer provider for libcpppd: every buffer is a ``torch.uint8`` CUDA tensor."""
 
-    def __init__(self, device):
+    def __init__(self, device, stream=None):
         import torch
 
         self.torch = torch
         self.device = device
+        self.stream = stream  # torch.cuda.Stream the library issues on: blocks are handed out (and reused) in its order
         self.live = {}
         self.alloc_cb = _cabi.ALLOC_FN(self._alloc)
         self.free_cb = _cabi.FREE_FN(self._free)
 
     def _alloc(self, nbytes, _user):
         try:
-            t = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+            if self.stream is not None:
+                with self.torch.cuda.stream(self.stream):
+                    t = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
+            else:
+                t = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.device)
         except Exception:  # out of memory -> NULL -> CPPPD_ERR_NOMEM
             return None
         self.live[t.data_ptr()] = t
@@ -296,9 +301,20 @@ class CpPpdSolver(SolverHandle):
         p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant,
                                   long_row_threshold)
         self.n, self.m, self.m_eq = int(p.n), int(p.m_eq + p.m_ineq), int(p.m_eq)
-        self._buffers = _TorchBuffers(dev)
+        # Stream contract: the solver issues everything on ONE stream that torch knows about, and
+        # its buffers come from torch's caching allocator *on that stream*, so a block torch recycles is never
+        # handed out while work that still uses it is pending.  The caller's current stream is used as is unless
+        # it is the legacy default stream (handle 0): then the solver gets a stream of its own that first waits
+        # for the work already queued on the default stream.
+        current = torch.cuda.current_stream(dev)
+        if current.cuda_stream == 0:
+            self._stream = torch.cuda.Stream(dev)
+            self._stream.wait_stream(current)
+        else:
+            self._stream = current
+        self._buffers = _TorchBuffers(dev, self._stream)
         p.device = dev.index
-        p.stream = torch.cuda.current_stream(dev).cuda_stream or None
+        p.stream = self._stream.cuda_stream
         p.alloc = self._buffers.alloc_cb
         p.free = self._buffers.free_cb
         p.alloc_user = None
@@ -325,6 +341,23 @@ class CpPpdSolver(SolverHandle):
             super().close()
             self._buffers.live.clear()
 
+    def agree(self, flag, any_rank=False):
+        """One decision for all ranks of a distributed solve: rank 0's `flag` (default) or the OR over the ranks.
+        The schedule branches on it (time-out, "does anybody have a callback"): ranks that decided differently
+        would issue different collectives and hang."""
+        if self.world <= 1:
+            return bool(flag)
+        import torch
+        import torch.distributed as dist
+
+        on_gpu = dist.get_backend(self._group) == "nccl"
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=self.device if on_gpu else "cpu")
+        if any_rank:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._group)
+        else:
+            dist.broadcast(t, src=dist.get_global_rank(self._group, 0), group=self._group)
+        return bool(int(t.item()))
+
     def _shared_comm(self, group, dev):
         """NCCL communicator of (process group, device), built once and kept for later solves: rank 0
         draws the id, torch.distributed broadcasts it, cpppd_comm_create joins."""
@@ -338,7 +371,9 @@ class CpPpdSolver(SolverHandle):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world == 1:
             return None
-        key = ("WORLD" if group is dist.group.WORLD else id(group), dev.index)
+        self._group = group
+        # keyed by the member ranks, not by id(group): ids are reused after garbage collection
+        key = (tuple(dist.get_process_group_ranks(group)), dev.index)
         if key in _COMM_CACHE:
             return _COMM_CACHE[key]
         if "CPPPD_NCCL_LIB" not in os.environ:  # use the NCCL that torch itself loaded
@@ -444,14 +479,25 @@ def run_schedule(solver, nb_max_iter, callback_func=None, max_time=None, force_i
     if nb_iter_plot < 1:
         raise ValueError("nb_iter_plot must be >= 1")
     niter = 0
+    agree = getattr(solver, "agree", None) if getattr(solver, "world", 1) > 1 else None
+    # get_x() is a collective when the solve is distributed: every rank fetches x if any rank has a callback
+    fetch_x = callback_func is not None
+    if agree is not None:
+        fetch_x = agree(fetch_x, any_rank=True)
     while niter < nb_max_iter:
         # iteration `niter` is a stats iteration (niter % nb_iter_plot == 0 by construction)
         solver.primal_step(keep_d=True)
-        if max_time is not None:
-            solver.sync()
+        # the reference reads its clock after the (synchronous) primal step (:243): wait for the device first, so
+        # that `elapsed` — the time-out test and the time axis of the caller's curves — includes the block of
+        # iterations that was queued before this one
+        solver.sync()
         elapsed = time.perf_counter() - start
-        if max_time is not None and elapsed > max_time:
-            break
+        if max_time is not None:
+            timed_out = elapsed > max_time
+            if agree is not None:  # ranks read different clocks: rank 0 decides for all
+                timed_out = agree(timed_out)
+            if timed_out:
+                break
         solver.stats_step(force_integer)
         st = solver.read_stats()
         if verbose:
@@ -461,9 +507,11 @@ def run_schedule(solver, nb_max_iter, callback_func=None, max_time=None, force_i
                       st["max_violated_equality"], 100 * st["frac_zero_xbar"]))
         if stats_func is not None:
             stats_func(niter, st, elapsed)
-        if callback_func is not None:
-            callback_func(niter, solver.get_x(), st["energy1"], st["energy2"], elapsed,
-                          st["max_violated_equality"], st["max_violated_inequality"])
+        if fetch_x:
+            x_now = solver.get_x()
+            if callback_func is not None:
+                callback_func(niter, x_now, st["energy1"], st["energy2"], elapsed,
+                              st["max_violated_equality"], st["max_violated_inequality"])
         solver.dual_step()
         niter += 1
         k = min(nb_iter_plot - 1, nb_max_iter - niter)

@@ -433,6 +433,7 @@ int setup_p2p(cpppd_solver *h) {
   CK(cudaMemcpyAsync(all.data(), recv, sizeof(PeerRecord) * N, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   // map the neighbours' vectors
+  int ipc_failed = 0;
   memset(pp.ptrs, 0, sizeof pp.ptrs);
   for (int t = 0; t < N; ++t) {
     if (t == me) continue;
@@ -444,13 +445,28 @@ int setup_p2p(cpppd_solver *h) {
     cudaError_t e3 = e2 == cudaSuccess ? cudaIpcOpenMemHandle(&pf, all[t].flags, cudaIpcMemLazyEnablePeerAccess) : e2;
     if (e3 != cudaSuccess) {
       cudaGetLastError();
-      return fail(h, CPPPD_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (use CPPPD_FLAG_NO_P2P for the NCCL path)",
-                  t, cudaGetErrorString(e3));
+      ipc_failed = 1;
+      fail(h, CPPPD_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (use CPPPD_FLAG_NO_P2P for the NCCL path)", t,
+           cudaGetErrorString(e3));
+      for (void *p : {px, py}) if (p) pp.opened.push_back(p);
+      break;
     }
     pp.opened.insert(pp.opened.end(), {px, py, pf});
     pp.ptrs[0].vec[t] = (double *)px;
     pp.ptrs[1].vec[t] = (double *)py;
     pp.ptrs[0].flags[t] = pp.ptrs[1].flags[t] = (unsigned long long *)pf;
+  }
+  {  // success is agreed on collectively: a rank that returned alone would leave its peers in the barrier below for ever
+    signed char any_failed = (signed char)ipc_failed;  // (world <= 64: the sum of the flags fits a byte)
+    CK(cudaMemcpyAsync(send, &any_failed, 1, cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
+    CK(cudaMemcpyAsync(&any_failed, send, 1, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (any_failed) {
+      if (!ipc_failed) fail(h, CPPPD_ERR_COMM, "a peer rank could not map this rank's halo buffers (cudaIpcOpenMemHandle); "
+                                              "use CPPPD_FLAG_NO_P2P for the NCCL path");
+      return CPPPD_ERR_COMM;
+    }
   }
   // per-entry destinations of the two send lists
   std::vector<int64_t> dst_base[2] = {std::vector<int64_t>(N, 0), std::vector<int64_t>(N, 0)};
