@@ -495,7 +495,7 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
     const Band &B = *band[k];
     if (B.in_use) {
       const int kinds = (B.geo.eq_windows ? 1 : 0) + (B.geo.windows > B.geo.eq_windows ? 1 : 0);
-      op_bytes[k] = 12 * B.nnz + (int64_t)B.geo.windows * (B.rows_pad + B.rows_pad / 8) + 16 * B.nrows * (B.geo.windows - kinds) +
+      op_bytes[k] = 12 * B.nnz + (int64_t)B.geo.windows * (B.rows_pad + B.rows_pad / 32) + 16 * B.nrows * (B.geo.windows - kinds) +
                     (kinds == 2 ? 16 * B.nrows : 0);
     } else {
       op_bytes[k] = sell[k]->padded * entry_bytes + (sell[k]->uniform_width >= 0 ? 0 : 8 * (sell[k]->nslices + 1));

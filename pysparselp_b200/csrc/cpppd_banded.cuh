@@ -10,8 +10,8 @@
 // gathers while the gathered window is <= 48-64 MB, 2.2x / 3.7x / 4.2x that at 128 / 320 / 512 MB.
 //
 // What.  The gathered vector is cut into windows of <= 48 MB; the entries of the operand are stored window-major
-// (all entries that gather from window 0, then window 1, ...); inside a window the 32 rows of a warp keep their entries
-// together, packed column-major in caller order (see k_band_fill), with one count byte per row and window.  A half-iteration is one launch PER WINDOW: thread i continues
+// (all entries that gather from window 0, then window 1, ...), in CSR order inside a window, with one count byte per
+// row and window and one offset per tile of 128 rows and window.  A half-iteration is one launch PER WINDOW: thread i continues
 // the sum of row i where the previous window left it (an fp64 carry in HBM, 16 bytes per row and window), so the
 // working set of the gathers of one launch is one window, resident in L2, while entries, counts and carries
 // stream past it with evict-first loads.  The last window runs the fused epilogue of k_dual / k_primal.
@@ -36,11 +36,11 @@ struct BandGeometry {
   }
 };
 
-// Storage of one window: the 32 rows of a warp ("tile") keep their entries of this window together, entry position
-// k of every row that has one before position k + 1 of any row, rows in lane order ("packed" column-major: no padding,
-// and the lanes that are active at position k read consecutive addresses).  Per row and window one byte holds the
-// number of entries (an operand with more than 255 entries of one row in one window is not banded), per tile and
-// window one 32-bit offset.
+// Storage of one window: plain CSR order (row-major, caller order inside a row), described by one count byte per
+// row (an operand with more than 255 entries of one row in one window is not banded) and one 32-bit offset per
+// "tile" of kBandTile = 128 consecutive rows — the rows one warp handles, four consecutive rows per lane.
+constexpr int kBandTile = 128;
+constexpr int kBandRowsPerLane = kBandTile / 32;
 
 // thread per row: entries per (window, row) into cnt[w * rows_pad + row]; flag[0] |= 1 when some row visits its
 // windows out of order (the operand then cannot be banded without changing the summation order), |= 2 when a
@@ -66,49 +66,40 @@ __global__ void k_band_count(const int64_t *__restrict__ rowptr, const int32_t *
   if (bad) atomicOr(flag, bad);
 }
 
-// thread per (window, tile): entries of the tile in the window (cnt is laid out window-major, so cell c covers
-// the 32 bytes cnt[32 c .. 32 c + 31])
+__device__ __forceinline__ uint32_t sum_bytes(uint32_t v) {
+  return (v & 0xffu) + ((v >> 8) & 0xffu) + ((v >> 16) & 0xffu) + (v >> 24);
+}
+
+// thread per (window, tile): entries of the tile in the window (cnt is laid out window-major and rows_pad is a
+// multiple of kBandTile, so cell c covers the bytes cnt[128 c .. 128 c + 127])
 __global__ void k_band_tile_totals(const unsigned char *__restrict__ cnt, int64_t cells, uint32_t *__restrict__ total) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cells) return;
-  const uint32_t *w = reinterpret_cast<const uint32_t *>(cnt + 32 * c);
+  const uint32_t *w = reinterpret_cast<const uint32_t *>(cnt + (int64_t)kBandTile * c);
   uint32_t t = 0;
-  for (int q = 0; q < 8; ++q) {
-    const uint32_t v = w[q];
-    t += (v & 0xffu) + ((v >> 8) & 0xffu) + ((v >> 16) & 0xffu) + (v >> 24);
-  }
+  for (int q = 0; q < kBandTile / 4; ++q) t += sum_bytes(w[q]);
   total[c] = t;
 }
 
-__device__ __forceinline__ int warp_max_i32(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// warp per tile: copy the entries to their packed places (tile_base = exclusive scan of the tile totals)
+// thread per row: copy the entries of the row to their places (tile_base = exclusive scan of the tile totals; the
+// rows of a tile before this one are summed from their count bytes)
 __global__ void k_band_fill(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indices,
                             const double *__restrict__ values, int64_t nrows, int64_t rows_pad, int windows,
                             const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
                             int32_t *__restrict__ idx, double *__restrict__ val) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows_pad) return;  // (whole warps: rows_pad is a multiple of 32)
-  const int lane = threadIdx.x & 31;
-  const int64_t tile = row >> 5, ntiles = rows_pad >> 5;
-  const unsigned lt = (1u << lane) - 1u;
-  int64_t e = row < nrows ? rowptr[row] : 0;
+  if (row >= nrows) return;
+  const int64_t tile = row / kBandTile, ntiles = rows_pad / kBandTile, first = tile * kBandTile;
+  int64_t e = rowptr[row];
   for (int w = 0; w < windows; ++w) {
-    const int c = cnt[(int64_t)w * rows_pad + row];
-    uint32_t off = tile_base[(int64_t)w * ntiles + tile];
-    const int widest = warp_max_i32(c);
-    for (int k = 0; k < widest; ++k) {
-      const unsigned mask = __ballot_sync(0xffffffffu, k < c);
-      if (k < c) {
-        const uint32_t pos = off + (uint32_t)__popc(mask & lt);
-        idx[pos] = indices[e + k] & kIdxMask;
-        val[pos] = values[e + k];
-      }
-      off += (uint32_t)__popc(mask);
+    const unsigned char *cw = cnt + (int64_t)w * rows_pad;
+    const int c = cw[row];
+    if (c == 0) continue;
+    uint32_t dst = tile_base[(int64_t)w * ntiles + tile];
+    for (int64_t r = first; r < row; ++r) dst += cw[r];
+    for (int k = 0; k < c; ++k) {
+      idx[dst + k] = indices[e + k] & kIdxMask;
+      val[dst + k] = values[e + k];
     }
     e += c;
   }
@@ -152,115 +143,197 @@ __global__ void k_band_locality(const int64_t *__restrict__ rowptr, const int32_
   }
 }
 
-// acc + sum of this lane's `c` entries of the tile against vec, sequentially in stored order.  The warp walks the
-// entry positions kC at a time: the ballots give every active lane its packed address, then all index / value loads
-// of the chunk are issued, then the gathers, then the sequential additions.
-template <int kC>
-__device__ __forceinline__ double band_accumulate(const int32_t *__restrict__ idx, const double *__restrict__ val,
-                                                  const double *__restrict__ vec, uint32_t off, int c, int lane, double acc) {
-  const unsigned lt = (1u << lane) - 1u;
-  const int widest = warp_max_i32(c);
-#pragma unroll 1
-  for (int k = 0; k < widest; k += kC) {
-    int32_t j[kC];
-    double a[kC], g[kC];
+// ---- the hot kernels ----------------------------------------------------------------------------------------
+// A warp owns a tile of 128 rows, lane l the rows 4 l .. 4 l + 3.  The entries of the tile in this window are one
+// contiguous run: the warp reads them FLAT, 128 at a time (lane l takes entries q + l, q + 32 + l, ...: every load
+// instruction is one contiguous 128 B / 256 B segment and every lane has four independent index loads, then four
+// independent gathers in flight, whatever the row lengths), multiplies value and gathered element, and parks the
+// products in shared memory.  Then every lane adds the products of its own rows to their sums — sequentially, in
+// stored order, exactly the additions of csr_matvec / csc_matvec.  (CSR-stream, without giving up the order.)
+constexpr int kBandChunk = 4;                  // flat entries per lane and trip
+constexpr int kBandSpan = 32 * kBandChunk;     // flat entries per warp and trip
+constexpr int kBandWarps = kBlock / 32;
+
+// four consecutive doubles of a lane (32-byte aligned: row / column ids of a lane start at a multiple of 4), as two
+// 16-byte accesses; `count` < 4 only in the last tile of an operand
+__device__ __forceinline__ void band_load4(const double *__restrict__ p, int64_t first, int64_t limit, double (&v)[4]) {
+  if (first + 4 <= limit) {
+    const double2 lo = __ldcs(reinterpret_cast<const double2 *>(p + first));
+    const double2 hi = __ldcs(reinterpret_cast<const double2 *>(p + first) + 1);
+    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+  } else {
 #pragma unroll
-    for (int u = 0; u < kC; ++u) {
-      const bool ok = k + u < c;
-      const unsigned mask = __ballot_sync(0xffffffffu, ok);
-      const uint32_t pos = off + (uint32_t)__popc(mask & lt);
-      off += (uint32_t)__popc(mask);
-      j[u] = ok ? __ldcs(idx + pos) : 0;
-      a[u] = ok ? __ldcs(val + pos) : 0.0;
+    for (int r = 0; r < 4; ++r) v[r] = first + r < limit ? __ldcs(p + first + r) : 0.0;
+  }
+}
+__device__ __forceinline__ void band_load4(const Vec &vec, int64_t first, int64_t limit, double (&v)[4]) {
+  if (vec.p) {
+    band_load4(vec.p, first, limit, v);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = vec.c;
+  }
+}
+template <bool kStream>
+__device__ __forceinline__ void band_store4(double *__restrict__ p, int64_t first, int64_t limit, const double (&v)[4]) {
+  if (first + 4 <= limit) {
+    double2 *q = reinterpret_cast<double2 *>(p + first);
+    if (kStream) {
+      __stcs(q, make_double2(v[0], v[1]));
+      __stcs(q + 1, make_double2(v[2], v[3]));
+    } else {
+      q[0] = make_double2(v[0], v[1]);
+      q[1] = make_double2(v[2], v[3]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (first + r < limit) p[first + r] = v[r];
+  }
+}
+
+struct BandRows {          // what a lane knows about its four rows in this window
+  uint32_t begin[kBandRowsPerLane + 1];  // tile-relative entry offsets: row r owns [begin[r], begin[r + 1])
+  uint32_t base, total;    // first entry of the tile (into idx / val), entries of the tile
+};
+
+__device__ __forceinline__ BandRows band_rows(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
+                                              int64_t tile, int lane) {
+  BandRows R;
+  const uint32_t c4 = __ldcs(reinterpret_cast<const uint32_t *>(cnt + tile * kBandTile) + lane);
+  const uint32_t mine = sum_bytes(c4);
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  R.total = __shfl_sync(0xffffffffu, incl, 31);
+  R.base = __ldg(tile_base + tile);
+  R.begin[0] = incl - mine;
+#pragma unroll
+  for (int r = 0; r < kBandRowsPerLane; ++r) R.begin[r + 1] = R.begin[r] + ((c4 >> (8 * r)) & 0xffu);
+  return R;
+}
+
+// acc[r] += products of row r, for the four rows of this lane
+__device__ __forceinline__ void band_accumulate(const BandRows &R, const int32_t *__restrict__ idx,
+                                                const double *__restrict__ val, const double *__restrict__ vec,
+                                                double *__restrict__ prod, int lane, double (&acc)[kBandRowsPerLane]) {
+  const int32_t *ip = idx + R.base;
+  const double *vp = val + R.base;
+#pragma unroll 1
+  for (uint32_t q = 0; q < R.total; q += kBandSpan) {
+    int32_t j[kBandChunk];
+    double a[kBandChunk], g[kBandChunk];
+#pragma unroll
+    for (int u = 0; u < kBandChunk; ++u) {
+      const uint32_t e = q + u * 32 + lane;
+      const bool ok = e < R.total;
+      j[u] = ok ? __ldcs(ip + e) : 0;
+      a[u] = ok ? __ldcs(vp + e) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < kC; ++u) g[u] = k + u < c ? __ldg(vec + j[u]) : 0.0;
+    for (int u = 0; u < kBandChunk; ++u) g[u] = q + u * 32 + lane < R.total ? __ldg(vec + j[u]) : 0.0;
 #pragma unroll
-    for (int u = 0; u < kC; ++u)
-      if (k + u < c) acc = __dadd_rn(acc, __dmul_rn(a[u], g[u]));
+    for (int u = 0; u < kBandChunk; ++u) prod[u * 32 + lane] = __dmul_rn(a[u], g[u]);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kBandRowsPerLane; ++r) {
+      const uint32_t lo = R.begin[r] > q ? R.begin[r] : q;
+      const uint32_t hi = R.begin[r + 1] < q + kBandSpan ? R.begin[r + 1] : q + kBandSpan;
+      for (uint32_t e = lo; e < hi; ++e) acc[r] = __dadd_rn(acc[r], prod[e - q]);
+    }
+    __syncwarp();
   }
-  return acc;
 }
 
-constexpr int kBandChunk = 4;
-
-// One window of the dual half-iteration (:231-240, :333-341).  Thread i owns row i of A; the warp owns a tile.
-// kFirst: the sum starts from 0.0 (csr_matvec), otherwise from the carry of the previous window.
-// kLast : fused dual step + projection, otherwise the partial sum goes to the carry.
+// One window of the dual half-iteration (:231-240, :333-341).
+// kFirst: the sums start from 0.0 (csr_matvec), otherwise from the carries of the previous window.
+// kLast : fused dual step + projection, otherwise the partial sums go to the carry.
 template <bool kFirst, bool kLast>
-__global__ void __launch_bounds__(kBlock, 8)
+__global__ void __launch_bounds__(kBlock, 4)
 k_dual_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base, const int32_t *__restrict__ idx,
             const double *__restrict__ val, const double *__restrict__ xbar, double *__restrict__ carry, Vec b, Vec sigma,
-            double *__restrict__ y, int64_t m, int64_t rows_pad, int64_t m_eq) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (i >= rows_pad) return;  // (whole warps)
-  const int lane = threadIdx.x & 31;
-  const bool live = i < m;
-  const int c = __ldcs(cnt + i);  // (zero for the padding rows of the last tile)
-  const uint32_t off = __ldg(tile_base + (i >> 5));
-  double acc = 0.0, bi = 0.0, si = 0.0, yi = 0.0;
-  if (!kFirst && live) acc = __ldcs(carry + i);
-  if (kLast && live) {
-    bi = b.at(i);
-    si = sigma.at(i);
-    yi = __ldcs(y + i);
+            double *__restrict__ y, int64_t m, int64_t ntiles, int64_t m_eq) {
+  __shared__ double prod_all[kBandWarps][kBandSpan];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
+  if (tile >= ntiles) return;  // (whole warps)
+  const int64_t i0 = tile * kBandTile + lane * kBandRowsPerLane;
+  const BandRows R = band_rows(cnt, tile_base, tile, lane);
+  double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0}, bi[kBandRowsPerLane], si[kBandRowsPerLane], yi[kBandRowsPerLane];
+  if (!kFirst) band_load4(carry, i0, m, acc);
+  if (kLast) {
+    band_load4(b, i0, m, bi);
+    band_load4(sigma, i0, m, si);
+    band_load4(y, i0, m, yi);
   }
-  acc = band_accumulate<kBandChunk>(idx, val, xbar, off, c, lane, acc);
-  if (!live) return;
+  band_accumulate(R, idx, val, xbar, prod_all[wib], lane, acc);
   if (!kLast) {
-    __stcs(carry + i, acc);
+    band_store4<true>(carry, i0, m, acc);
     return;
   }
-  const double r = __dsub_rn(acc, bi);
-  double yn = __dadd_rn(yi, __dmul_rn(si, r));
-  if (i >= m_eq) yn = (yn < 0.0) ? 0.0 : yn;
-  y[i] = yn;
+  double yn[kBandRowsPerLane];
+#pragma unroll
+  for (int r = 0; r < kBandRowsPerLane; ++r) {
+    const double res = __dsub_rn(acc[r], bi[r]);
+    yn[r] = __dadd_rn(yi[r], __dmul_rn(si[r], res));
+    if (i0 + r >= m_eq) yn[r] = (yn[r] < 0.0) ? 0.0 : yn[r];
+  }
+  band_store4<false>(y, i0, m, yn);
 }
 
-// One window of the primal half-iteration (:198-228).  Thread j owns column j of A.
-// mode bit 0: the sum of this window's kind (equality / inequality rows) starts from 0.0
+// One window of the primal half-iteration (:198-228).
+// mode bit 0: the sums of this window's kind (equality / inequality rows) start from 0.0
 //      bit 1: last window — fused primal step, clip, extrapolation
-//      bit 2: the window gathers equality duals (its sum is s_eq, kept apart from s_ineq as in :206, :216)
+//      bit 2: the window gathers equality duals (its sums are s_eq, kept apart from s_ineq as in :206, :216)
 constexpr int kBandStart = 1, kBandLast = 2, kBandEq = 4;
 template <bool kWriteD>
-__global__ void __launch_bounds__(kBlock, 6)
+__global__ void __launch_bounds__(kBlock, 4)
 k_primal_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base, const int32_t *__restrict__ idx,
               const double *__restrict__ val, const double *__restrict__ y, double *__restrict__ carry_eq,
               double *__restrict__ carry_in, int mode, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
-              double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int64_t rows_pad, int has_eq, int has_ineq,
+              double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int64_t ntiles, int has_eq, int has_ineq,
               double theta, double one_plus_theta) {
-  const int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (j >= rows_pad) return;  // (whole warps)
-  const int lane = threadIdx.x & 31;
-  const bool live = j < n;
-  const int cn = __ldcs(cnt + j);
-  const uint32_t off = __ldg(tile_base + (j >> 5));
+  __shared__ double prod_all[kBandWarps][kBandSpan];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
+  if (tile >= ntiles) return;  // (whole warps)
+  const int64_t j0 = tile * kBandTile + lane * kBandRowsPerLane;
+  const BandRows R = band_rows(cnt, tile_base, tile, lane);
   double *carry = (mode & kBandEq) ? carry_eq : carry_in;
-  double acc = 0.0, cj = 0.0, tj = 0.0, xo = 0.0, other = 0.0;
-  if (!(mode & kBandStart) && live) acc = __ldcs(carry + j);
-  if ((mode & kBandLast) && live) {
-    cj = c.at(j);
-    tj = T.at(j);
-    xo = __ldcs(x + j);
-    if (!(mode & kBandEq) && has_eq) other = __ldcs(carry_eq + j);
-  }
-  acc = band_accumulate<kBandChunk>(idx, val, y, off, cn, lane, acc);
-  if (!live) return;
+  double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0};
+  if (!(mode & kBandStart)) band_load4(carry, j0, n, acc);
+  band_accumulate(R, idx, val, y, prod_all[wib], lane, acc);
   if (!(mode & kBandLast)) {
-    __stcs(carry + j, acc);
+    band_store4<true>(carry, j0, n, acc);
     return;
   }
-  const double s_eq = (mode & kBandEq) ? acc : other, s_in = (mode & kBandEq) ? 0.0 : acc;
-  double d = cj;
-  if (has_eq) d = __dadd_rn(d, s_eq);
-  if (has_ineq) d = __dadd_rn(d, s_in);
-  const double l = lb.at(j), u = ub.at(j);
-  double x2 = __dsub_rn(xo, __dmul_rn(tj, d));
-  x2 = (l > x2) ? l : x2;
-  x2 = (u < x2) ? u : x2;
-  xbar[j] = __dsub_rn(__dmul_rn(one_plus_theta, x2), __dmul_rn(theta, xo));
-  x[j] = x2;
-  if (kWriteD) d_out[j] = d;
+  double other[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0}, xo[kBandRowsPerLane], cj[kBandRowsPerLane], tj[kBandRowsPerLane],
+         lo[kBandRowsPerLane], up[kBandRowsPerLane], x2[kBandRowsPerLane], xb[kBandRowsPerLane], dd[kBandRowsPerLane];
+  if (!(mode & kBandEq) && has_eq) band_load4(carry_eq, j0, n, other);
+  band_load4(x, j0, n, xo);
+  band_load4(c, j0, n, cj);
+  band_load4(T, j0, n, tj);
+  band_load4(lb, j0, n, lo);
+  band_load4(ub, j0, n, up);
+#pragma unroll
+  for (int r = 0; r < kBandRowsPerLane; ++r) {
+    const double s_eq = (mode & kBandEq) ? acc[r] : other[r], s_in = (mode & kBandEq) ? 0.0 : acc[r];
+    double d = cj[r];
+    if (has_eq) d = __dadd_rn(d, s_eq);
+    if (has_ineq) d = __dadd_rn(d, s_in);
+    double v = __dsub_rn(xo[r], __dmul_rn(tj[r], d));
+    v = (lo[r] > v) ? lo[r] : v;
+    v = (up[r] < v) ? up[r] : v;
+    x2[r] = v;
+    xb[r] = __dsub_rn(__dmul_rn(one_plus_theta, v), __dmul_rn(theta, xo[r]));
+    dd[r] = d;
+  }
+  band_store4<false>(xbar, j0, n, xb);
+  band_store4<false>(x, j0, n, x2);
+  if (kWriteD) band_store4<false>(d_out, j0, n, dd);
 }
 
 }  // namespace

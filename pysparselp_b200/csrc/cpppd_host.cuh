@@ -137,7 +137,8 @@ int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   }
   geo.windows = geo.eq_windows + in_windows;
   if (geo.windows > 4096) return 0;
-  const int64_t rows_pad = (nrows + 31) / 32 * 32, ntiles = rows_pad / 32, cells = (int64_t)geo.windows * ntiles;
+  const int64_t rows_pad = (nrows + kBandTile - 1) / kBandTile * kBandTile, ntiles = rows_pad / kBandTile,
+                cells = (int64_t)geo.windows * ntiles;
   Scratch tmp(h);
   uint32_t *total = nullptr;
   int *flag = nullptr;
@@ -168,7 +169,7 @@ int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   if (int rc = alloc_array(h, &out->carry, nrows)) return rc;
   if (geo.eq_windows && in_windows)
     if (int rc = alloc_array(h, &out->carry_eq, nrows)) return rc;
-  k_band_fill<<<grid_for(rows_pad), kBlock, 0, st>>>(rowptr, indices, values, nrows, rows_pad, geo.windows, cnt, out->tile_base,
+  k_band_fill<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, values, nrows, rows_pad, geo.windows, cnt, out->tile_base,
                                                     out->idx, out->val);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
@@ -1060,8 +1061,8 @@ constexpr int kBandVariant = -2;  // `variant` argument of launch_primal / launc
 int launch_primal_band(cpppd_solver *h, bool write_d) {
   const Band &B = h->bandAT;
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-  const int grid = grid_for(B.rows_pad);
-  const int64_t ntiles = B.rows_pad / 32;
+  const int64_t ntiles = B.rows_pad / kBandTile;
+  const int grid = (int)((ntiles + kBandWarps - 1) / kBandWarps);  // a warp per tile of 128 rows
   for (int w = 0; w < B.geo.windows; ++w) {
     const bool eq = w < B.geo.eq_windows;
     const int mode = ((w == 0 || w == B.geo.eq_windows) ? kBandStart : 0) | (w == B.geo.windows - 1 ? kBandLast : 0) |
@@ -1071,11 +1072,11 @@ int launch_primal_band(cpppd_solver *h, bool write_d) {
     double *ceq = B.carry_eq ? B.carry_eq : B.carry;  // one kind of rows only: a single carry serves it
     if (write_d)
       k_primal_band<true><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT,
-                                                         h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, B.rows_pad, has_eq,
+                                                         h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles, has_eq,
                                                          has_ineq, h->theta, h->one_plus_theta);
     else
       k_primal_band<false><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT,
-                                                          h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, B.rows_pad, has_eq,
+                                                          h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles, has_eq,
                                                           has_ineq, h->theta, h->one_plus_theta);
   }
   return 0;
@@ -1083,15 +1084,16 @@ int launch_primal_band(cpppd_solver *h, bool write_d) {
 
 int launch_dual_band(cpppd_solver *h) {
   const Band &B = h->bandA;
-  const int grid = grid_for(B.rows_pad), W = B.geo.windows;
-  const int64_t ntiles = B.rows_pad / 32;
+  const int W = B.geo.windows;
+  const int64_t ntiles = B.rows_pad / kBandTile;
+  const int grid = (int)((ntiles + kBandWarps - 1) / kBandWarps);
   for (int w = 0; w < W; ++w) {
     const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     const bool first = w == 0, last = w == W - 1;
 #define CPPPD_DUAL_BAND(F, L)                                                                                          \
   k_dual_band<F, L><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, \
-                                                    h->m, B.rows_pad, h->m_eq)
+                                                    h->m, ntiles, h->m_eq)
     if (first && last) CPPPD_DUAL_BAND(true, true);
     else if (first) CPPPD_DUAL_BAND(true, false);
     else if (last) CPPPD_DUAL_BAND(false, true);

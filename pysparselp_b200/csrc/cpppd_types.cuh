@@ -51,9 +51,9 @@ struct Band {
   bool in_use = false;  // the half-iteration runs k_*_band (one launch per window) instead of the SELL kernel
   BandGeometry geo{0, 1, 1, 0, 0};
   int64_t nrows = 0, nnz = 0, win_bytes = 0;
-  int64_t rows_pad = 0;             // nrows rounded up to whole tiles of 32 rows
+  int64_t rows_pad = 0;             // nrows rounded up to whole tiles of kBandTile rows
   unsigned char *cnt = nullptr;     // windows * rows_pad : entries of a row in a window
-  uint32_t *tile_base = nullptr;    // windows * (rows_pad / 32) + 1 : first entry of a tile in a window (into idx / val)
+  uint32_t *tile_base = nullptr;    // windows * (rows_pad / kBandTile) + 1 : first entry of a tile in a window (into idx / val)
   int32_t *idx = nullptr;
   double *val = nullptr;
   double *carry = nullptr, *carry_eq = nullptr;  // partial sums between windows (carry_eq: A^T with both row kinds)

@@ -210,6 +210,25 @@ inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
   emul::arrive_and_wait(b.warp_bar[w], b.warp_live[w]);
   return out;
 }
+// value of lane `src_lane` / of the lane `delta` below (own value when there is none)
+template <typename T>
+inline T emul_shfl_from(T v, int src_lane_or_delta, bool up) {
+  static_assert(sizeof(T) <= 8, "shuffle payload");
+  emul::BlockState &b = emul::g_block;
+  const int t = b.current, w = t >> 5, lane = t & 31;
+  memcpy(b.slot[t], &v, sizeof(T));
+  emul::arrive_and_wait(b.warp_bar[w], b.warp_live[w]);
+  T out = v;
+  const int sl = up ? lane - src_lane_or_delta : (src_lane_or_delta & 31);
+  if (sl >= 0) {
+    const int src = (t & ~31) | sl;
+    if (src < b.nthreads && !b.fibers[src].done) memcpy(&out, b.slot[src], sizeof(T));
+  }
+  emul::arrive_and_wait(b.warp_bar[w], b.warp_live[w]);
+  return out;
+}
+template <typename T> inline T __shfl_sync(unsigned, T v, int src_lane) { return emul_shfl_from(v, src_lane, false); }
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) { return emul_shfl_from(v, (int)delta, true); }
 inline unsigned __ballot_sync(unsigned, int pred) {
   emul::BlockState &b = emul::g_block;
   const int t = b.current, w = t >> 5;
@@ -241,6 +260,8 @@ inline void __nanosleep(unsigned) {
   emul::yield();
 }
 
+struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldca(const T *p) { return *p; }

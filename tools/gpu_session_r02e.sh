@@ -1,16 +1,16 @@
 #!/bin/bash
 # Round 2, session d (1 GPU): packed banded layout — tests, window sweep, request-rate metrics
-tag=r02d
+tag=r02e
 out=gpurun_out
 mkdir -p $out
 export PYTHONUNBUFFERED=1
 log=$out/${tag}_session.log
 echo "== 1. GPU tests" | tee $log
-timeout 900 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_banded.py -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1
 echo "pytest exit $?" | tee -a $log
 tail -3 $out/${tag}_pytest_gpu.log | tee -a $log
 echo "== 2. random LP 20M x 40M: window sweep (banded forced, flag 1024)" | tee -a $log
-for mb in 32 40 48 56 64; do
+for mb in 40 48 56 64 72; do
   CPPPD_BAND_WINDOW_MB=$mb timeout 300 python tools/quick_bench.py --kind random --size 20000000 --iters 20 --reps 3 --flags 1024 >> $out/${tag}_random.jsonl 2>> $out/${tag}_random.err
 done
 echo "== 3. ncu of the banded kernels (selected metrics)" | tee -a $log
