@@ -275,7 +275,7 @@ def run_reference(a):
             size //= 2
     lp, _ = build_workload(a.workload, size, pinned=False)
     co = COracle(*generators.lp_args(lp))
-    nnz = int(co.nnz)
+    nnz = int(co.val.size)
     scale = nnz / float(workload_nnz(a.workload, a.size))
     for _ in range(a.warmup):
         co.iterate(a.ref_iters_per_step)
@@ -438,7 +438,7 @@ def storage_summary(info, t_build, t_setup):
                        "sectors_per_gather": info["band_sectors_per_gather"]}}
 
 
-def secondary_workload(kind, size, a, torch, make_solver, chambolle_pock_ppd, peak, peak_src):
+def secondary_workload(kind, size, a, torch, local_rank, make_solver, chambolle_pock_ppd, peak, peak_src):
     """Device-resident measurement of another BASELINE config on one GPU (after the headline, own roofline)."""
     from pysparselp_b200 import generators
 
@@ -453,7 +453,7 @@ def secondary_workload(kind, size, a, torch, make_solver, chambolle_pock_ppd, pe
     try:
         info = solver.info()
         steps = max(2, a.steps // 4)
-        ms, clocks = time_resident(solver, a, torch, None, torch.cuda.current_device(), steps, 3)
+        ms, clocks = time_resident(solver, a, torch, None, local_rank, steps, 3)
         its = steps * a.iters_per_step / (ms * 1e-3)
         out.update({"value": its, "unit": UNIT, "steps": steps, "warmup": 3, "ms_per_step": ms / steps, "clocks": clocks,
                     "roofline": roofline_block(solver, info, its, 1, peak, peak_src),
@@ -620,8 +620,8 @@ def run_b200(a):
             kind = kind.strip()
             try:
                 size2 = DEFAULT_SIZE[kind] if not a.secondary_size else a.secondary_size
-                secondary[workload_name(kind, size2)] = secondary_workload(kind, size2, a, torch, make_solver, chambolle_pock_ppd,
-                                                                           peak, peak_src)
+                secondary[workload_name(kind, size2)] = secondary_workload(kind, size2, a, torch, local_rank, make_solver,
+                                                                           chambolle_pock_ppd, peak, peak_src)
             except Exception as e:
                 secondary[kind] = {"error": repr(e)}
 

@@ -80,11 +80,14 @@ class Info(C.Structure):
         ("balanced_split", C.c_int32), ("tiny_persistent", C.c_int32),
         ("band_windows", C.c_int32 * 2), ("band_in_use", C.c_int32 * 2), ("band_ms", C.c_float * 2),
         ("band_sectors_per_gather", C.c_float * 2), ("band_window_bytes", C.c_int64),
+        ("band_shape", C.c_int32 * 2), ("band_shape_ms", (C.c_float * 4) * 2),
     ]
 
     def as_dict(self):
-        arrays = ("band_windows", "band_in_use", "band_ms", "band_sectors_per_gather")
-        out = {name: getattr(self, name) for name, _ in self._fields_ if name not in ("variant_ms", "reserved") + arrays}
+        arrays = ("band_windows", "band_in_use", "band_ms", "band_sectors_per_gather", "band_shape")
+        out = {name: getattr(self, name) for name, _ in self._fields_
+               if name not in ("variant_ms", "band_shape_ms", "reserved") + arrays}
+        out["band_shape_ms"] = [list(self.band_shape_ms[0]), list(self.band_shape_ms[1])]
         for name in arrays:  # [A (dual half), A^T (primal half)]
             out[name] = list(getattr(self, name))
         out["variant_ms"] = {"k_primal": list(self.variant_ms[0]), "k_dual": list(self.variant_ms[1])}

@@ -504,6 +504,8 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
     out->band_in_use[k] = B.in_use ? 1 : 0;
     out->band_ms[k] = B.ms;
     out->band_sectors_per_gather[k] = (float)B.sectors_per_gather;
+    out->band_shape[k] = B.shape;
+    memcpy(out->band_shape_ms[k], B.shape_ms, sizeof B.shape_ms);
     if (B.built) out->band_window_bytes = std::max(out->band_window_bytes, B.win_bytes);
   }
   out->bytes_per_iteration_actual = op_bytes[0] + op_bytes[1] + vec_bytes;

@@ -150,99 +150,90 @@ __global__ void k_band_locality(const int64_t *__restrict__ rowptr, const int32_
 // independent gathers in flight, whatever the row lengths), multiplies value and gathered element, and parks the
 // products in shared memory.  Then every lane adds the products of its own rows to their sums — sequentially, in
 // stored order, exactly the additions of csr_matvec / csc_matvec.  (CSR-stream, without giving up the order.)
-constexpr int kBandChunk = 4;                  // flat entries per lane and trip
-constexpr int kBandSpan = 32 * kBandChunk;     // flat entries per warp and trip
+// kChunk = flat entries per lane and trip (32 kChunk per warp); the kernels are compiled in a few (kChunk, CTAs per SM)
+// shapes — more entries in flight per warp against more warps per SM — and cpppd_create() times them (kBandShapes).
 constexpr int kBandWarps = kBlock / 32;
 
-// four consecutive doubles of a lane (32-byte aligned: row / column ids of a lane start at a multiple of 4), as two
-// 16-byte accesses; `count` < 4 only in the last tile of an operand
-__device__ __forceinline__ void band_load4(const double *__restrict__ p, int64_t first, int64_t limit, double (&v)[4]) {
-  if (first + 4 <= limit) {
-    const double2 lo = __ldcs(reinterpret_cast<const double2 *>(p + first));
-    const double2 hi = __ldcs(reinterpret_cast<const double2 *>(p + first) + 1);
-    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = first + r < limit ? __ldcs(p + first + r) : 0.0;
-  }
+// Per-row vectors: a lane owns four consecutive elements (32-byte aligned: its first row / column id is a multiple of
+// 4), moved as two 16-byte accesses; elements behind `limit` (last tile of an operand only) are skipped.
+__device__ __forceinline__ double2 band_load2(const double *__restrict__ p, int64_t first, int64_t limit) {
+  if (first + 2 <= limit) return __ldcs(reinterpret_cast<const double2 *>(p + first));
+  return make_double2(first < limit ? __ldcs(p + first) : 0.0, 0.0);
 }
-__device__ __forceinline__ void band_load4(const Vec &vec, int64_t first, int64_t limit, double (&v)[4]) {
-  if (vec.p) {
-    band_load4(vec.p, first, limit, v);
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) v[r] = vec.c;
-  }
+__device__ __forceinline__ double2 band_load2(const Vec &vec, int64_t first, int64_t limit) {
+  return vec.p ? band_load2(vec.p, first, limit) : make_double2(vec.c, vec.c);
 }
 template <bool kStream>
-__device__ __forceinline__ void band_store4(double *__restrict__ p, int64_t first, int64_t limit, const double (&v)[4]) {
-  if (first + 4 <= limit) {
-    double2 *q = reinterpret_cast<double2 *>(p + first);
-    if (kStream) {
-      __stcs(q, make_double2(v[0], v[1]));
-      __stcs(q + 1, make_double2(v[2], v[3]));
-    } else {
-      q[0] = make_double2(v[0], v[1]);
-      q[1] = make_double2(v[2], v[3]);
-    }
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-      if (first + r < limit) p[first + r] = v[r];
+__device__ __forceinline__ void band_store2(double *__restrict__ p, int64_t first, int64_t limit, double2 v) {
+  if (first + 2 <= limit) {
+    if (kStream) __stcs(reinterpret_cast<double2 *>(p + first), v); else *reinterpret_cast<double2 *>(p + first) = v;
+  } else if (first < limit) {
+    p[first] = v.x;
   }
+}
+__device__ __forceinline__ void band_load4(const double *__restrict__ p, int64_t first, int64_t limit, double (&v)[4]) {
+  const double2 lo = band_load2(p, first, limit), hi = band_load2(p, first + 2, limit);
+  v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+}
+__device__ __forceinline__ void band_store4(double *__restrict__ p, int64_t first, int64_t limit, const double (&v)[4]) {
+  band_store2<true>(p, first, limit, make_double2(v[0], v[1]));
+  band_store2<true>(p, first + 2, limit, make_double2(v[2], v[3]));
 }
 
 struct BandRows {          // what a lane knows about its four rows in this window
-  uint32_t begin[kBandRowsPerLane + 1];  // tile-relative entry offsets: row r owns [begin[r], begin[r + 1])
+  uint32_t counts;         // one byte per row
+  uint32_t begin;          // tile-relative offset of the first entry of the first row
   uint32_t base, total;    // first entry of the tile (into idx / val), entries of the tile
 };
 
 __device__ __forceinline__ BandRows band_rows(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
                                               int64_t tile, int lane) {
   BandRows R;
-  const uint32_t c4 = __ldcs(reinterpret_cast<const uint32_t *>(cnt + tile * kBandTile) + lane);
-  const uint32_t mine = sum_bytes(c4);
+  R.counts = __ldcs(reinterpret_cast<const uint32_t *>(cnt + tile * kBandTile) + lane);
+  R.base = __ldg(tile_base + tile);
+  R.total = __ldg(tile_base + tile + 1) - R.base;  // (tile_base holds one more element than there are tiles x windows)
+  const uint32_t mine = sum_bytes(R.counts);
   uint32_t incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += up;
   }
-  R.total = __shfl_sync(0xffffffffu, incl, 31);
-  R.base = __ldg(tile_base + tile);
-  R.begin[0] = incl - mine;
-#pragma unroll
-  for (int r = 0; r < kBandRowsPerLane; ++r) R.begin[r + 1] = R.begin[r] + ((c4 >> (8 * r)) & 0xffu);
+  R.begin = incl - mine;
   return R;
 }
 
 // acc[r] += products of row r, for the four rows of this lane
+template <int kChunk>
 __device__ __forceinline__ void band_accumulate(const BandRows &R, const int32_t *__restrict__ idx,
                                                 const double *__restrict__ val, const double *__restrict__ vec,
                                                 double *__restrict__ prod, int lane, double (&acc)[kBandRowsPerLane]) {
+  constexpr int kBandSpan = 32 * kChunk;
   const int32_t *ip = idx + R.base;
   const double *vp = val + R.base;
 #pragma unroll 1
   for (uint32_t q = 0; q < R.total; q += kBandSpan) {
-    int32_t j[kBandChunk];
-    double a[kBandChunk], g[kBandChunk];
+    int32_t j[kChunk];
+    double a[kChunk], g[kChunk];
 #pragma unroll
-    for (int u = 0; u < kBandChunk; ++u) {
+    for (int u = 0; u < kChunk; ++u) {
       const uint32_t e = q + u * 32 + lane;
       const bool ok = e < R.total;
       j[u] = ok ? __ldcs(ip + e) : 0;
       a[u] = ok ? __ldcs(vp + e) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < kBandChunk; ++u) g[u] = q + u * 32 + lane < R.total ? __ldg(vec + j[u]) : 0.0;
+    for (int u = 0; u < kChunk; ++u) g[u] = q + u * 32 + lane < R.total ? __ldg(vec + j[u]) : 0.0;
 #pragma unroll
-    for (int u = 0; u < kBandChunk; ++u) prod[u * 32 + lane] = __dmul_rn(a[u], g[u]);
+    for (int u = 0; u < kChunk; ++u) prod[u * 32 + lane] = __dmul_rn(a[u], g[u]);
     __syncwarp();
+    uint32_t first = R.begin;
 #pragma unroll
     for (int r = 0; r < kBandRowsPerLane; ++r) {
-      const uint32_t lo = R.begin[r] > q ? R.begin[r] : q;
-      const uint32_t hi = R.begin[r + 1] < q + kBandSpan ? R.begin[r + 1] : q + kBandSpan;
+      const uint32_t last = first + ((R.counts >> (8 * r)) & 0xffu);
+      const uint32_t lo = first > q ? first : q, hi = last < q + kBandSpan ? last : q + kBandSpan;
       for (uint32_t e = lo; e < hi; ++e) acc[r] = __dadd_rn(acc[r], prod[e - q]);
+      first = last;
     }
     __syncwarp();
   }
@@ -251,52 +242,50 @@ __device__ __forceinline__ void band_accumulate(const BandRows &R, const int32_t
 // One window of the dual half-iteration (:231-240, :333-341).
 // kFirst: the sums start from 0.0 (csr_matvec), otherwise from the carries of the previous window.
 // kLast : fused dual step + projection, otherwise the partial sums go to the carry.
-template <bool kFirst, bool kLast>
-__global__ void __launch_bounds__(kBlock, 4)
+template <bool kFirst, bool kLast, int kChunk, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB)
 k_dual_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base, const int32_t *__restrict__ idx,
             const double *__restrict__ val, const double *__restrict__ xbar, double *__restrict__ carry, Vec b, Vec sigma,
             double *__restrict__ y, int64_t m, int64_t ntiles, int64_t m_eq) {
-  __shared__ double prod_all[kBandWarps][kBandSpan];
+  __shared__ double prod_all[kBandWarps][32 * kChunk];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
   if (tile >= ntiles) return;  // (whole warps)
   const int64_t i0 = tile * kBandTile + lane * kBandRowsPerLane;
   const BandRows R = band_rows(cnt, tile_base, tile, lane);
-  double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0}, bi[kBandRowsPerLane], si[kBandRowsPerLane], yi[kBandRowsPerLane];
+  double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0};
   if (!kFirst) band_load4(carry, i0, m, acc);
-  if (kLast) {
-    band_load4(b, i0, m, bi);
-    band_load4(sigma, i0, m, si);
-    band_load4(y, i0, m, yi);
-  }
-  band_accumulate(R, idx, val, xbar, prod_all[wib], lane, acc);
+  band_accumulate<kChunk>(R, idx, val, xbar, prod_all[wib], lane, acc);
   if (!kLast) {
-    band_store4<true>(carry, i0, m, acc);
+    band_store4(carry, i0, m, acc);
     return;
   }
-  double yn[kBandRowsPerLane];
 #pragma unroll
-  for (int r = 0; r < kBandRowsPerLane; ++r) {
-    const double res = __dsub_rn(acc[r], bi[r]);
-    yn[r] = __dadd_rn(yi[r], __dmul_rn(si[r], res));
-    if (i0 + r >= m_eq) yn[r] = (yn[r] < 0.0) ? 0.0 : yn[r];
+  for (int h2 = 0; h2 < 2; ++h2) {  // two rows at a time
+    const int64_t i = i0 + 2 * h2;
+    const double2 bi = band_load2(b, i, m), si = band_load2(sigma, i, m), yi = band_load2(y, i, m);
+    double2 yn;
+    yn.x = __dadd_rn(yi.x, __dmul_rn(si.x, __dsub_rn(acc[2 * h2], bi.x)));
+    yn.y = __dadd_rn(yi.y, __dmul_rn(si.y, __dsub_rn(acc[2 * h2 + 1], bi.y)));
+    if (i >= m_eq) yn.x = (yn.x < 0.0) ? 0.0 : yn.x;
+    if (i + 1 >= m_eq) yn.y = (yn.y < 0.0) ? 0.0 : yn.y;
+    band_store2<false>(y, i, m, yn);
   }
-  band_store4<false>(y, i0, m, yn);
 }
 
 // One window of the primal half-iteration (:198-228).
 // mode bit 0: the sums of this window's kind (equality / inequality rows) start from 0.0
-//      bit 1: last window — fused primal step, clip, extrapolation
 //      bit 2: the window gathers equality duals (its sums are s_eq, kept apart from s_ineq as in :206, :216)
-constexpr int kBandStart = 1, kBandLast = 2, kBandEq = 4;
-template <bool kWriteD>
-__global__ void __launch_bounds__(kBlock, 4)
+// kLast     : last window — fused primal step, clip, extrapolation (kWriteD: d is kept for the stats block)
+constexpr int kBandStart = 1, kBandEq = 4;
+template <bool kLast, bool kWriteD, int kChunk, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB)
 k_primal_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base, const int32_t *__restrict__ idx,
               const double *__restrict__ val, const double *__restrict__ y, double *__restrict__ carry_eq,
               double *__restrict__ carry_in, int mode, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
               double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int64_t ntiles, int has_eq, int has_ineq,
               double theta, double one_plus_theta) {
-  __shared__ double prod_all[kBandWarps][kBandSpan];
+  __shared__ double prod_all[kBandWarps][32 * kChunk];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
   if (tile >= ntiles) return;  // (whole warps)
@@ -305,35 +294,86 @@ k_primal_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict_
   double *carry = (mode & kBandEq) ? carry_eq : carry_in;
   double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0};
   if (!(mode & kBandStart)) band_load4(carry, j0, n, acc);
-  band_accumulate(R, idx, val, y, prod_all[wib], lane, acc);
-  if (!(mode & kBandLast)) {
-    band_store4<true>(carry, j0, n, acc);
+  band_accumulate<kChunk>(R, idx, val, y, prod_all[wib], lane, acc);
+  if (!kLast) {
+    band_store4(carry, j0, n, acc);
     return;
   }
-  double other[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0}, xo[kBandRowsPerLane], cj[kBandRowsPerLane], tj[kBandRowsPerLane],
-         lo[kBandRowsPerLane], up[kBandRowsPerLane], x2[kBandRowsPerLane], xb[kBandRowsPerLane], dd[kBandRowsPerLane];
-  if (!(mode & kBandEq) && has_eq) band_load4(carry_eq, j0, n, other);
-  band_load4(x, j0, n, xo);
-  band_load4(c, j0, n, cj);
-  band_load4(T, j0, n, tj);
-  band_load4(lb, j0, n, lo);
-  band_load4(ub, j0, n, up);
 #pragma unroll
-  for (int r = 0; r < kBandRowsPerLane; ++r) {
-    const double s_eq = (mode & kBandEq) ? acc[r] : other[r], s_in = (mode & kBandEq) ? 0.0 : acc[r];
-    double d = cj[r];
-    if (has_eq) d = __dadd_rn(d, s_eq);
-    if (has_ineq) d = __dadd_rn(d, s_in);
-    double v = __dsub_rn(xo[r], __dmul_rn(tj[r], d));
-    v = (lo[r] > v) ? lo[r] : v;
-    v = (up[r] < v) ? up[r] : v;
-    x2[r] = v;
-    xb[r] = __dsub_rn(__dmul_rn(one_plus_theta, v), __dmul_rn(theta, xo[r]));
-    dd[r] = d;
+  for (int h2 = 0; h2 < 2; ++h2) {  // two columns at a time
+    const int64_t j = j0 + 2 * h2;
+    double2 other = make_double2(0.0, 0.0);
+    if (!(mode & kBandEq) && has_eq) other = band_load2(carry_eq, j, n);
+    const double2 xo = band_load2(x, j, n), cj = band_load2(c, j, n), tj = band_load2(T, j, n);
+    const double2 lo = band_load2(lb, j, n), up = band_load2(ub, j, n);
+    double2 x2, xb, dd;
+    {
+      const double s = acc[2 * h2];
+      double d = cj.x;
+      if (has_eq) d = __dadd_rn(d, (mode & kBandEq) ? s : other.x);
+      if (has_ineq) d = __dadd_rn(d, (mode & kBandEq) ? 0.0 : s);
+      double v = __dsub_rn(xo.x, __dmul_rn(tj.x, d));
+      v = (lo.x > v) ? lo.x : v;
+      v = (up.x < v) ? up.x : v;
+      x2.x = v;
+      xb.x = __dsub_rn(__dmul_rn(one_plus_theta, v), __dmul_rn(theta, xo.x));
+      dd.x = d;
+    }
+    {
+      const double s = acc[2 * h2 + 1];
+      double d = cj.y;
+      if (has_eq) d = __dadd_rn(d, (mode & kBandEq) ? s : other.y);
+      if (has_ineq) d = __dadd_rn(d, (mode & kBandEq) ? 0.0 : s);
+      double v = __dsub_rn(xo.y, __dmul_rn(tj.y, d));
+      v = (lo.y > v) ? lo.y : v;
+      v = (up.y < v) ? up.y : v;
+      x2.y = v;
+      xb.y = __dsub_rn(__dmul_rn(one_plus_theta, v), __dmul_rn(theta, xo.y));
+      dd.y = d;
+    }
+    band_store2<false>(xbar, j, n, xb);
+    band_store2<false>(x, j, n, x2);
+    if (kWriteD) band_store2<false>(d_out, j, n, dd);
   }
-  band_store4<false>(xbar, j0, n, xb);
-  band_store4<false>(x, j0, n, x2);
-  if (kWriteD) band_store4<false>(d_out, j0, n, dd);
+}
+
+// ---- compiled shapes of the window kernels ----------------------------------------------------------------------
+// The windows before the last one only stream entries, counts and carries: lean kernels, many warps per SM.  The last
+// window also runs the fused epilogue (up to eight more vectors): it keeps the 64-register shape.
+struct BandShape {
+  int chunk, min_blocks;
+  const char *name;
+};
+constexpr int kNumBandShapes = 4;
+constexpr BandShape kBandShapes[kNumBandShapes] = {{4, 4, "flat4/4cta"}, {3, 6, "flat3/6cta"}, {2, 6, "flat2/6cta"}, {2, 8, "flat2/8cta"}};
+
+using DualBandFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *, double *,
+                            Vec, Vec, double *, int64_t, int64_t, int64_t);
+using PrimalBandFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *,
+                              double *, double *, int, Vec, Vec, Vec, Vec, double *, double *, double *, int64_t, int64_t, int,
+                              int, double, double);
+
+template <bool kFirst, bool kLast>
+DualBandFn dual_band_shape(int shape) {
+  switch (shape) {
+    case 1: return k_dual_band<kFirst, kLast, 3, 6>;
+    case 2: return k_dual_band<kFirst, kLast, 2, 6>;
+    case 3: return k_dual_band<kFirst, kLast, 2, 8>;
+    default: return k_dual_band<kFirst, kLast, 4, 4>;
+  }
+}
+inline DualBandFn dual_band_kernel(bool first, bool last, int shape) {
+  if (last) return first ? k_dual_band<true, true, 4, 4> : k_dual_band<false, true, 4, 4>;
+  return first ? dual_band_shape<true, false>(shape) : dual_band_shape<false, false>(shape);
+}
+inline PrimalBandFn primal_band_kernel(bool last, bool write_d, int shape) {
+  if (last) return write_d ? k_primal_band<true, true, 4, 4> : k_primal_band<true, false, 4, 4>;
+  switch (shape) {
+    case 1: return k_primal_band<false, false, 3, 6>;
+    case 2: return k_primal_band<false, false, 2, 6>;
+    case 3: return k_primal_band<false, false, 2, 8>;
+    default: return k_primal_band<false, false, 4, 4>;
+  }
 }
 
 }  // namespace

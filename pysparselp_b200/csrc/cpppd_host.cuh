@@ -1065,19 +1065,15 @@ int launch_primal_band(cpppd_solver *h, bool write_d) {
   const int grid = (int)((ntiles + kBandWarps - 1) / kBandWarps);  // a warp per tile of 128 rows
   for (int w = 0; w < B.geo.windows; ++w) {
     const bool eq = w < B.geo.eq_windows;
-    const int mode = ((w == 0 || w == B.geo.eq_windows) ? kBandStart : 0) | (w == B.geo.windows - 1 ? kBandLast : 0) |
-                     (eq ? kBandEq : 0);
+    const int mode = ((w == 0 || w == B.geo.eq_windows) ? kBandStart : 0) | (eq ? kBandEq : 0);
     const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     double *ceq = B.carry_eq ? B.carry_eq : B.carry;  // one kind of rows only: a single carry serves it
-    if (write_d)
-      k_primal_band<true><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT,
-                                                         h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles, has_eq,
-                                                         has_ineq, h->theta, h->one_plus_theta);
-    else
-      k_primal_band<false><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT,
-                                                          h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles, has_eq,
-                                                          has_ineq, h->theta, h->one_plus_theta);
+    const bool last = w == B.geo.windows - 1;
+    PrimalBandFn fn = primal_band_kernel(last, write_d, B.shape);
+    fn<<<grid, kBlock, 0, h->stream>>>(
+        cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles,
+        has_eq, has_ineq, h->theta, h->one_plus_theta);
   }
   return 0;
 }
@@ -1091,14 +1087,8 @@ int launch_dual_band(cpppd_solver *h) {
     const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     const bool first = w == 0, last = w == W - 1;
-#define CPPPD_DUAL_BAND(F, L)                                                                                          \
-  k_dual_band<F, L><<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, \
-                                                    h->m, ntiles, h->m_eq)
-    if (first && last) CPPPD_DUAL_BAND(true, true);
-    else if (first) CPPPD_DUAL_BAND(true, false);
-    else if (last) CPPPD_DUAL_BAND(false, true);
-    else CPPPD_DUAL_BAND(false, false);
-#undef CPPPD_DUAL_BAND
+    DualBandFn fn = dual_band_kernel(first, last, B.shape);
+    fn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, h->m, ntiles, h->m_eq);
   }
   return 0;
 }
@@ -1145,6 +1135,8 @@ struct TuneChoice {
   float ms[2][CPPPD_KERNEL_VARIANTS] = {};
   bool band_primal = false, band_dual = false;
   float band_ms[2] = {0.f, 0.f};
+  int band_shape[2] = {0, 0};
+  float band_shape_ms[2][4] = {};
 };
 std::map<TuneKey, TuneChoice> g_tune_cache;
 std::mutex g_tune_mutex;
@@ -1168,6 +1160,8 @@ int tune_kernels(cpppd_solver *h) {
   // a banded operand is used unless the timing below finds the SELL kernel faster
   h->bandA.in_use = h->bandA.built;
   h->bandAT.in_use = h->bandAT.built;
+  if (const char *env = getenv("CPPPD_BAND_SHAPE"))  // (all shapes give the same bits; the timing below picks one otherwise)
+    if (atoi(env) >= 0 && atoi(env) < kNumBandShapes) h->bandA.shape = h->bandAT.shape = atoi(env);
   int request = h->variant_request;
   if (request == 0)
     if (const char *env = getenv("CPPPD_KERNEL_VARIANT")) request = atoi(env);
@@ -1201,6 +1195,10 @@ int tune_kernels(cpppd_solver *h) {
       }
       h->bandAT.ms = hit->second.band_ms[0];
       h->bandA.ms = hit->second.band_ms[1];
+      h->bandAT.shape = hit->second.band_shape[0];
+      h->bandA.shape = hit->second.band_shape[1];
+      memcpy(h->bandAT.shape_ms, hit->second.band_shape_ms[0], sizeof h->bandAT.shape_ms);
+      memcpy(h->bandA.shape_ms, hit->second.band_shape_ms[1], sizeof h->bandA.shape_ms);
       h->autotuned = true;
       return 0;
     }
@@ -1241,18 +1239,28 @@ int tune_kernels(cpppd_solver *h) {
     // the banded copy of the operand, when it was built: same protocol, against the best SELL variant
     Band &band = kind == 0 ? h->bandAT : h->bandA;
     if (band.built) {
+      int forced_shape = -1;
+      if (const char *env = getenv("CPPPD_BAND_SHAPE")) forced_shape = atoi(env);
       for (int pass = 0; pass < 3 && !rc; ++pass) {
-        float ms = 0.f;
-        if (pass > 0) CK(cudaEventRecord(e0, st));
-        for (int rep = 0; rep < (pass > 0 ? 2 : 1) && !rc; ++rep)
-          rc = kind == 0 ? launch_primal(h, false, kBandVariant) : launch_dual(h, kBandVariant);
-        if (rc || pass == 0) continue;
-        CK(cudaEventRecord(e1, st));
-        CK(cudaEventSynchronize(e1));
-        CK(cudaEventElapsedTime(&ms, e0, e1));
-        ms /= 2;
-        if (pass == 1 || ms < band.ms) band.ms = ms;
+        for (int shape = 0; shape < kNumBandShapes && !rc; ++shape) {
+          if (forced_shape >= 0 && forced_shape < kNumBandShapes && shape != forced_shape) continue;
+          band.shape = shape;
+          float ms = 0.f;
+          if (pass > 0) CK(cudaEventRecord(e0, st));
+          for (int rep = 0; rep < (pass > 0 ? 2 : 1) && !rc; ++rep)
+            rc = kind == 0 ? launch_primal(h, false, kBandVariant) : launch_dual(h, kBandVariant);
+          if (rc || pass == 0) continue;
+          CK(cudaEventRecord(e1, st));
+          CK(cudaEventSynchronize(e1));
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          ms /= 2;
+          if (pass == 1 || ms < band.shape_ms[shape]) band.shape_ms[shape] = ms;
+        }
       }
+      band.shape = forced_shape >= 0 && forced_shape < kNumBandShapes ? forced_shape : 0;
+      for (int shape = 0; shape < kNumBandShapes; ++shape)
+        if (band.shape_ms[shape] > 0.f && band.shape_ms[shape] < band.shape_ms[band.shape]) band.shape = shape;
+      band.ms = band.shape_ms[band.shape];
       band.in_use = (h->flags & CPPPD_FLAG_BANDED) || (!rc && band.ms < 0.98f * h->variant_ms[kind][best]);
     }
   }
@@ -1269,6 +1277,10 @@ int tune_kernels(cpppd_solver *h) {
     choice.band_dual = h->bandA.built && h->bandA.ms > 0.f && h->bandA.ms < 0.98f * h->variant_ms[1][h->dual_variant];
     choice.band_ms[0] = h->bandAT.ms;
     choice.band_ms[1] = h->bandA.ms;
+    choice.band_shape[0] = h->bandAT.shape;
+    choice.band_shape[1] = h->bandA.shape;
+    memcpy(choice.band_shape_ms[0], h->bandAT.shape_ms, sizeof h->bandAT.shape_ms);
+    memcpy(choice.band_shape_ms[1], h->bandA.shape_ms, sizeof h->bandA.shape_ms);
     std::lock_guard<std::mutex> lock(g_tune_mutex);
     g_tune_cache[key] = choice;
   }

@@ -17,7 +17,7 @@ def test_algorithmic_bytes_match_survey_numbers():
     assert round((p + d) / 1e9, 2) == 11.20
     p, d = bench.algorithmic_bytes(20_000_000, 40_000_000, 320_000_000)
     assert round((p + d) / 1e9, 2) == 10.80
-    assert bench._potts_nnz(4096) == 201277440
+    assert bench.workload_nnz("potts", 4096) == 201277440 and bench.workload_nnz("random", 20_000_000) == 320_000_000
 
 
 def test_reference_arm_prints_one_json_line():
@@ -103,9 +103,11 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     monkeypatch.setattr(bench, "pinned_empty", lambda: (lambda count, dtype=np.float64: np.empty(int(count), dtype=dtype), []))
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
-    a = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="b200", size=24, iters_per_step=3, ref_iters_per_step=1,
-                           ref_numpy_iters=1, e2e_iters=7, e2e_steps=2, no_cpu_baseline=False, variants=1, flags=0,
-                           stats_interval=5, small_configs=2, small_iters=30)
+    torch.cuda.empty_cache()  # (a no-op without a device; the script calls it between the workloads)
+    a = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="b200", workload="potts", size=24, iters_per_step=3,
+                           ref_iters_per_step=1, ref_numpy_iters=1, e2e_iters=7, e2e_steps=2, no_cpu_baseline=False,
+                           variants=1, flags=0, stats_interval=5, small_configs=2, small_iters=30, secondary="random",
+                           secondary_size=2000)
     bench.run_b200(a)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -116,7 +118,12 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["dtype"] == "f64" and d["value"] > 0
     assert d["config"]["workload"] == "potts_segmentation_lp_24x24" and "l2" in d["config"]
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"] in ("k_primal", "k_dual")
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"].startswith(("k_primal[", "k_dual["))
+    # the timed configuration reproduces the digest the C port minted for this workload (tests/golden/bench_digests.json)
+    assert d["parity"]["status"] == "ok", d["parity"]
+    sec = d["secondary_workloads"]["random_sparse_lp_2000x4000_8_per_row"]
+    assert sec["value"] > 0 and sec["parity"]["status"] == "ok" and sec["roofline"]["frac"] > 0
+    assert sec["e2e"]["value"] > 0 and sec["e2e"]["finite"] and "error" not in sec["sell_kernels"]
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["achieved"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     e = d["e2e"]
@@ -146,3 +153,22 @@ def test_smoke_dry_run_on_the_emulated_library(monkeypatch, capsys):
     monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
     entry.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def test_committed_bench_digests_are_reproducible():
+    """tests/golden/bench_digests.json (bench.py's `parity` key): the small entries are re-minted here from the C
+    port and must equal the committed ones — the generators and the port are deterministic across machines and
+    thread counts; the full-size entries were minted by the same script (tools/mint_bench_digests.py)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle.c_port import COracle
+    from pysparselp_b200 import generators
+
+    table = json.load(open(bench.DIGESTS))
+    for name in (bench.workload_name("potts", 4096), bench.workload_name("random", 20_000_000)):
+        assert name in table and len(table[name]["sha256"]) == 64 and table[name]["iterations"] == bench.DIGEST_ITERS
+    for kind, size in (("potts", 256), ("random", 200000)):
+        lp, _ = bench.build_workload(kind, size, pinned=False)
+        co = COracle(*generators.lp_args(lp))
+        co.iterate(bench.DIGEST_ITERS)
+        assert bench.iterate_digest(co.x, co.y) == table[bench.workload_name(kind, size)]["sha256"]

@@ -422,3 +422,20 @@ def test_emulated_banded_operands_give_the_same_bits(name, window, monkeypatch):
         curves_close(np.array(trace), g["trace_10"])
     finally:
         solver.close()
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3])
+def test_emulated_banded_kernel_shapes_give_the_same_bits(shape, monkeypatch):
+    """The window kernels are compiled in four (entries per lane and trip, CTAs per SM) shapes; cpppd_create times them
+    on large operands.  Every shape must produce the golden bits (shape 0 is what the other banded tests run)."""
+    monkeypatch.setenv("CPPPD_BAND_WINDOW", "11")
+    monkeypatch.setenv("CPPPD_BAND_SHAPE", str(shape))
+    args, g = case_args("random_small")
+    x, best, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=100, nb_iter_plot=10, flags=_cabi.FLAG_BANDED)
+    try:
+        info = solver.info()
+        assert info["band_in_use"] == [1, 1] and info["band_shape"] == [shape, shape]
+        assert np.array_equal(x, g["x_100"])
+        assert np.array_equal(solver.get_y(), np.concatenate([g["y_eq"], g["y_ineq"]]))
+    finally:
+        solver.close()

@@ -22,7 +22,8 @@ from pysparselp_b200 import generators  # noqa: E402
 
 
 def main():
-    jobs = sys.argv[1:] or ["potts:4096", "random:20000000", "potts:1024", "potts:256", "random:2000000", "random:200000"]
+    jobs = sys.argv[1:] or ["potts:4096", "random:20000000", "potts:1024", "potts:256", "random:2000000", "random:200000",
+                            "potts:24", "random:2000"]  # (the last two: the CPU dry run of bench.py)
     path = bench.DIGESTS
     table = json.load(open(path)) if os.path.isfile(path) else {}
     threads = c_port.set_threads()

@@ -35,6 +35,6 @@ out = dict(kind=a.kind, size=a.size, variant=a.variant, chosen=(info["primal_var
            actual_GBs=info["bytes_per_iteration_actual"] / ms / 1e6, times=times,
            pad_A=info["a_padded_entries"] / max(info["nnz"], 1), pad_AT=info["at_padded_entries"] / max(info["nnz"], 1),
            device_GB=info["device_bytes"] / 1e9, band_windows=info["band_windows"], band_in_use=info["band_in_use"],
-           band_ms=info["band_ms"], band_spg=info["band_sectors_per_gather"], band_window_mb=info["band_window_bytes"] / 2**20,
+           band_ms=info["band_ms"], band_shape=info["band_shape"], band_shape_ms=info["band_shape_ms"], band_spg=info["band_sectors_per_gather"], band_window_mb=info["band_window_bytes"] / 2**20,
            variant_ms=info["variant_ms"], band_env=os.environ.get("CPPPD_BAND_WINDOW_MB"))
 print(json.dumps(out))
