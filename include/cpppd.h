@@ -27,7 +27,7 @@
  *   CPPPD_AUTOTUNE_MIN_NNZ  smallest operand (entries) whose kernel variants are timed at creation (default 2^22)
  *   CPPPD_AUTOTUNE_CACHE    0: time the variants at every creation instead of once per operand shape and process
  *   CPPPD_BAND_WINDOW_MB    megabytes of the gathered vector per window of a banded operand (default 48)
- *   CPPPD_BAND_SHAPE        0..3: compiled shape of the banded window kernels (cpppd_info.band_shape_ms) instead of the timed choice
+ *   CPPPD_BAND_SHAPE        0..7: compiled shape of the banded window kernels (cpppd_info.band_shape_ms) instead of the timed choice
  *   CPPPD_BAND_WINDOW       the same in elements (tests: windows of a few dozen elements on small LPs); both are
  *                           only read when cpppd_problem.band_window is 0
  *
@@ -215,8 +215,10 @@ typedef struct {
   float band_sectors_per_gather[2]; /* sampled locality of the operand: distinct 32-byte sectors per gather of a warp */
   int64_t band_window_bytes;    /* bytes of the gathered vector per window (largest window) */
   int32_t band_shape[2];        /* compiled shape of the window kernels in use (0-based, see band_shape_ms) */
-  float band_shape_ms[2][4];    /* ms per half-iteration measured at creation for the shapes flat4/4cta, flat3/6cta,
-                                   flat2/6cta, flat2/8cta (flat entries per lane and trip / CTAs per SM); 0 = not timed */
+  float band_shape_ms[2][8];    /* ms per half-iteration measured at creation for the shapes flat4/4cta, flat3/6cta,
+                                   flat2/6cta, flat2/8cta (entries through registers: flat entries per lane and trip /
+                                   CTAs per SM) and bulk-g8/5cta, bulk-g10/5cta, bulk-g12/4cta, bulk-g6/5cta (entries
+                                   staged in shared memory by cp.async.bulk: gathers in flight per lane); 0 = not timed */
 } cpppd_info;
 
 typedef enum {

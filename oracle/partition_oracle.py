@@ -23,7 +23,8 @@ Rank r keeps its rows in the order
 (equalities first, then inequalities; inside each, by bucket, then by min(length, 4095), then by
 original index) and its columns in the order (bucket, min(length, 4095), original index) — grouping
 equal lengths inside a bucket is the sigma-sorting of SELL-C-sigma: slices of 32 neighbours get
-nearly equal widths.
+nearly equal widths.  With banded operands (CPPPD_FLAG_BANDED, or chosen automatically for patterns without
+locality) and the balanced split, rows and columns instead keep their ORIGINAL order inside (rank, kind).
 Ghost columns of rank r: columns owned by another rank that appear in r's rows; ghost rows:
 rows owned by another rank that hit r's columns.  Both are listed by (owner, local position).
 """
@@ -51,7 +52,7 @@ def locality_keys(indptr, indices, n):
     return row_key, col_key
 
 
-def partition(indptr, indices, n, m_eq, world, granule=None, reorder=True):
+def partition(indptr, indices, n, m_eq, world, granule=None, reorder=True, keep_order=False):
     """Returns dict(row_order, row_start, col_order, col_start, m_eq_local).
 
     ``row_order[row_start[r]:row_start[r+1]]`` are the original row ids owned by rank r in local
@@ -85,8 +86,14 @@ def partition(indptr, indices, n, m_eq, world, granule=None, reorder=True):
         row_owner = np.minimum(world - 1, indptr[:-1] * world // nnz)
         col_owner = np.minimum(world - 1, (np.cumsum(col_lens) - col_lens) * world // nnz)
     is_ineq = (np.arange(m) >= m_eq).astype(np.int64)
-    row_order = np.lexsort((np.arange(m), np.minimum(lens, 4095), rq, is_ineq, row_owner))
-    col_order = np.lexsort((np.arange(n), np.minimum(col_lens, 4095), cq, col_owner))
+    if balanced and keep_order:
+        # banded operands (csrc/cpppd_banded.cuh) on several GPUs: original order inside (owner, kind), so that a
+        # range of original ids stays a few contiguous pieces of the local layout
+        row_order = np.lexsort((np.arange(m), is_ineq, row_owner))
+        col_order = np.lexsort((np.arange(n), col_owner))
+    else:
+        row_order = np.lexsort((np.arange(m), np.minimum(lens, 4095), rq, is_ineq, row_owner))
+        col_order = np.lexsort((np.arange(n), np.minimum(col_lens, 4095), cq, col_owner))
     row_start = np.concatenate(([0], np.cumsum(np.bincount(row_owner, minlength=world))))
     col_start = np.concatenate(([0], np.cumsum(np.bincount(col_owner, minlength=world))))
     m_eq_local = np.bincount(row_owner[:m_eq], minlength=world)

@@ -80,7 +80,7 @@ class Info(C.Structure):
         ("balanced_split", C.c_int32), ("tiny_persistent", C.c_int32),
         ("band_windows", C.c_int32 * 2), ("band_in_use", C.c_int32 * 2), ("band_ms", C.c_float * 2),
         ("band_sectors_per_gather", C.c_float * 2), ("band_window_bytes", C.c_int64),
-        ("band_shape", C.c_int32 * 2), ("band_shape_ms", (C.c_float * 4) * 2),
+        ("band_shape", C.c_int32 * 2), ("band_shape_ms", (C.c_float * 8) * 2),
     ]
 
     def as_dict(self):

@@ -45,15 +45,20 @@ constexpr int kBandRowsPerLane = kBandTile / 32;
 // thread per row: entries per (window, row) into cnt[w * rows_pad + row]; flag[0] |= 1 when some row visits its
 // windows out of order (the operand then cannot be banded without changing the summation order), |= 2 when a
 // count does not fit a byte
+// `orig` (may be nullptr): original id of a local element of the gathered vector — with more than one GPU the windows
+// are ranges of ORIGINAL ids (the order the caller's rows are sorted in), which the local layout keeps in a few
+// contiguous pieces (own range, then the ghosts of every peer in original order; see setup()).
 __global__ void k_band_count(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indices, int64_t nrows,
-                             int64_t rows_pad, BandGeometry geo, unsigned char *__restrict__ cnt, int *__restrict__ flag) {
+                             int64_t rows_pad, BandGeometry geo, const int32_t *__restrict__ orig,
+                             unsigned char *__restrict__ cnt, int *__restrict__ flag) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nrows) return;
   const int64_t e0 = rowptr[row], e1 = rowptr[row + 1];
   int cur = -1, bad = 0;
   uint32_t run = 0;
   for (int64_t e = e0; e < e1; ++e) {
-    const int w = geo.window_of(indices[e] & kIdxMask);
+    const int32_t loc = indices[e] & kIdxMask;
+    const int w = geo.window_of(orig ? orig[loc] : loc);
     if (w != cur) {
       if (cur >= 0) cnt[(int64_t)cur * rows_pad + row] = (unsigned char)run;
       if (w < cur) bad |= 1;
@@ -337,21 +342,166 @@ k_primal_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict_
   }
 }
 
+// ---- bulk-async staged variant (TMA 1-D bulk copy + mbarrier) ------------------------------------------------------
+// The register-path kernels above pay two dependent memory round trips per 64-128 entries of a tile (index / value
+// loads, then the gathers) and walk a tile's ~300 entries in three or four such trips: ncu shows them bound by
+// latency, not by any unit (profiles/r02_random_lp.md).  Here one elected lane asks the copy engine for the tile's
+// whole run of indices and values (two cp.async.bulk of up to kBandPiece entries into shared memory, completion on
+// an mbarrier); no registers hold entries in flight, so the lanes can then keep kG gathers each (up to 384 per warp)
+// in flight at once, multiply in place in shared memory and finish with the same sequential per-row sums.
+constexpr int kBandPiece = 384;  // entries staged per bulk copy pair (a tile holds ~256-340 with the default windows)
+
+struct alignas(16) BandStage {
+  double val[kBandPiece + 2];    // (+ alignment slack: bulk copies move whole 16-byte units)
+  int32_t idx[kBandPiece + 4];
+  unsigned long long bar;        // mbarrier
+  unsigned long long pad;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t band_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void band_bar_init(unsigned long long *bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(band_smem_addr(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders the lanes' generic-proxy accesses to the stage before the copy engine's next writes to it
+__device__ __forceinline__ void band_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void band_bar_expect(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(band_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void band_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(band_smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(band_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void band_bar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(band_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+#else  // CPU emulation (tests/emul): the copy is synchronous, the wait is the warp rendezvous that makes it visible
+inline void band_bar_init(unsigned long long *) {}
+inline void band_fence_async() {}
+inline void band_bar_expect(unsigned long long *, uint32_t) {}
+inline void band_bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+inline void band_bar_wait(unsigned long long *, uint32_t) { __syncwarp(); }
+#endif
+
+// acc[r] += products of row r for the four rows of this lane, entries staged through `st` by bulk copies
+template <int kG>
+__device__ __forceinline__ void band_accumulate_staged(const BandRows &R, const int32_t *__restrict__ idx,
+                                                       const double *__restrict__ val, const double *__restrict__ vec,
+                                                       BandStage *st, int lane, double (&acc)[kBandRowsPerLane]) {
+  uint32_t parity = 0;
+#pragma unroll 1
+  for (uint32_t p0 = 0; p0 < R.total; p0 += kBandPiece) {
+    const uint32_t count = R.total - p0 < (uint32_t)kBandPiece ? R.total - p0 : (uint32_t)kBandPiece;
+    const uint32_t first = R.base + p0;
+    // whole 16-byte units around [first, first + count): 4 indices / 2 values per unit
+    const uint32_t i_lo = first & ~3u, i_hi = (first + count + 3u) & ~3u, v_lo = first & ~1u, v_hi = (first + count + 1u) & ~1u;
+    const uint32_t i_off = first - i_lo, v_off = first - v_lo;
+    if (lane == 0) {
+      band_fence_async();
+      band_bar_expect(&st->bar, (i_hi - i_lo) * 4u + (v_hi - v_lo) * 8u);
+      band_bulk_load(st->idx, idx + i_lo, (i_hi - i_lo) * 4u, &st->bar);
+      band_bulk_load(st->val, val + v_lo, (v_hi - v_lo) * 8u, &st->bar);
+    }
+    band_bar_wait(&st->bar, parity);
+    parity ^= 1u;
+#pragma unroll 1
+    for (uint32_t q = 0; q < count; q += 32 * kG) {
+      double g[kG];
+#pragma unroll
+      for (int u = 0; u < kG; ++u) {
+        const uint32_t e = q + u * 32 + lane;
+        g[u] = e < count ? __ldg(vec + st->idx[i_off + e]) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kG; ++u) {
+        const uint32_t e = q + u * 32 + lane;
+        if (e < count) st->val[v_off + e] = __dmul_rn(st->val[v_off + e], g[u]);
+      }
+    }
+    __syncwarp();
+    uint32_t begin = R.begin;
+#pragma unroll
+    for (int r = 0; r < kBandRowsPerLane; ++r) {
+      const uint32_t end = begin + ((R.counts >> (8 * r)) & 0xffu);
+      const uint32_t lo = begin > p0 ? begin : p0, hi = end < p0 + count ? end : p0 + count;
+      for (uint32_t e = lo; e < hi; ++e) acc[r] = __dadd_rn(acc[r], st->val[v_off + e - p0]);
+      begin = end;
+    }
+    __syncwarp();
+  }
+}
+
+template <bool kFirst, int kG, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB)
+k_dual_band_staged(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
+                   const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ xbar,
+                   double *__restrict__ carry, int64_t m, int64_t ntiles) {
+  __shared__ BandStage stage[kBandWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
+  if (tile >= ntiles) return;  // (whole warps)
+  if (lane == 0) band_bar_init(&stage[wib].bar);
+  __syncwarp();
+  const int64_t i0 = tile * kBandTile + lane * kBandRowsPerLane;
+  const BandRows R = band_rows(cnt, tile_base, tile, lane);
+  double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0};
+  if (!kFirst) band_load4(carry, i0, m, acc);
+  band_accumulate_staged<kG>(R, idx, val, xbar, &stage[wib], lane, acc);
+  band_store4(carry, i0, m, acc);
+}
+
+template <int kG, int kMinB>
+__global__ void __launch_bounds__(kBlock, kMinB)
+k_primal_band_staged(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
+                     const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ y,
+                     double *__restrict__ carry, int start, int64_t n, int64_t ntiles) {
+  __shared__ BandStage stage[kBandWarps];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
+  if (tile >= ntiles) return;  // (whole warps)
+  if (lane == 0) band_bar_init(&stage[wib].bar);
+  __syncwarp();
+  const int64_t j0 = tile * kBandTile + lane * kBandRowsPerLane;
+  const BandRows R = band_rows(cnt, tile_base, tile, lane);
+  double acc[kBandRowsPerLane] = {0.0, 0.0, 0.0, 0.0};
+  if (!start) band_load4(carry, j0, n, acc);
+  band_accumulate_staged<kG>(R, idx, val, y, &stage[wib], lane, acc);
+  band_store4(carry, j0, n, acc);
+}
+
 // ---- compiled shapes of the window kernels ----------------------------------------------------------------------
 // The windows before the last one only stream entries, counts and carries: lean kernels, many warps per SM.  The last
 // window also runs the fused epilogue (up to eight more vectors): it keeps the 64-register shape.
 struct BandShape {
-  int chunk, min_blocks;
+  int chunk, min_blocks, staged;
   const char *name;
 };
-constexpr int kNumBandShapes = 4;
-constexpr BandShape kBandShapes[kNumBandShapes] = {{4, 4, "flat4/4cta"}, {3, 6, "flat3/6cta"}, {2, 6, "flat2/6cta"}, {2, 8, "flat2/8cta"}};
+constexpr int kNumBandShapes = 8;
+constexpr BandShape kBandShapes[kNumBandShapes] = {
+    {4, 4, 0, "flat4/4cta"},    {3, 6, 0, "flat3/6cta"},     {2, 6, 0, "flat2/6cta"},     {2, 8, 0, "flat2/8cta"},
+    {8, 5, 1, "bulk-g8/5cta"}, {10, 5, 1, "bulk-g10/5cta"}, {12, 4, 1, "bulk-g12/4cta"}, {6, 5, 1, "bulk-g6/5cta"}};
 
 using DualBandFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *, double *,
                             Vec, Vec, double *, int64_t, int64_t, int64_t);
 using PrimalBandFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *,
                               double *, double *, int, Vec, Vec, Vec, Vec, double *, double *, double *, int64_t, int64_t, int,
                               int, double, double);
+using DualStagedFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *, double *,
+                              int64_t, int64_t);
+using PrimalStagedFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *,
+                                double *, int, int64_t, int64_t);
 
 template <bool kFirst, bool kLast>
 DualBandFn dual_band_shape(int shape) {
@@ -362,6 +512,7 @@ DualBandFn dual_band_shape(int shape) {
     default: return k_dual_band<kFirst, kLast, 4, 4>;
   }
 }
+// kernels of the windows before the last one; the last window always runs the register path with the fused epilogue
 inline DualBandFn dual_band_kernel(bool first, bool last, int shape) {
   if (last) return first ? k_dual_band<true, true, 4, 4> : k_dual_band<false, true, 4, 4>;
   return first ? dual_band_shape<true, false>(shape) : dual_band_shape<false, false>(shape);
@@ -373,6 +524,26 @@ inline PrimalBandFn primal_band_kernel(bool last, bool write_d, int shape) {
     case 2: return k_primal_band<false, false, 2, 6>;
     case 3: return k_primal_band<false, false, 2, 8>;
     default: return k_primal_band<false, false, 4, 4>;
+  }
+}
+template <bool kFirst>
+DualStagedFn dual_staged_shape(int shape) {
+  switch (shape) {
+    case 5: return k_dual_band_staged<kFirst, 10, 5>;
+    case 6: return k_dual_band_staged<kFirst, 12, 4>;
+    case 7: return k_dual_band_staged<kFirst, 6, 5>;
+    default: return k_dual_band_staged<kFirst, 8, 5>;
+  }
+}
+inline DualStagedFn dual_staged_kernel(bool first, int shape) {
+  return first ? dual_staged_shape<true>(shape) : dual_staged_shape<false>(shape);
+}
+inline PrimalStagedFn primal_staged_kernel(int shape) {
+  switch (shape) {
+    case 5: return k_primal_band_staged<10, 5>;
+    case 6: return k_primal_band_staged<12, 4>;
+    case 7: return k_primal_band_staged<6, 5>;
+    default: return k_primal_band_staged<8, 5>;
   }
 }
 

@@ -116,8 +116,10 @@ int band_locality(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices
 // CSR (device, int64 rowptr; A^T entries may carry kEqBit) -> window-major copy (cpppd_banded.cuh).
 // vec_len: length of the gathered vector; split: its first element that belongs to an inequality row (A^T) or 0.
 // Leaves out->built false (and frees nothing it did not allocate persistently) when the operand does not qualify.
+// orig: local -> original ids of the gathered vector (nullptr on one GPU: identity); vec_len and split then count
+// ORIGINAL ids (the whole LP), because that is the order in which the caller's rows are sorted.
 int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, const double *values, int64_t nrows,
-               int64_t nnz, int64_t vec_len, int64_t split, bool forced, Band *out) {
+               int64_t nnz, int64_t vec_len, int64_t split, bool forced, const int32_t *orig, Band *out) {
   if (nrows == 0 || nnz == 0 || vec_len == 0) return 0;
   cudaStream_t st = h->stream;
   const int64_t target = band_window_elems(h);
@@ -149,7 +151,7 @@ int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   CK(cudaMemsetAsync(cnt, 0, (size_t)geo.windows * rows_pad, st));
   CK(cudaMemsetAsync(flag, 0, sizeof(int), st));
   CK(cudaMemsetAsync(total + cells, 0, sizeof(uint32_t), st));
-  k_band_count<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, nrows, rows_pad, geo, cnt, flag);
+  k_band_count<<<grid_for(nrows), kBlock, 0, st>>>(rowptr, indices, nrows, rows_pad, geo, orig, cnt, flag);
   int bad = 0;
   CK(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -164,8 +166,10 @@ int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   if (int rc = alloc_array(h, &out->tile_base, cells + 1)) return rc;
   if (int rc = exclusive_scan(h, total, out->tile_base, cells + 1)) return rc;
   tmp.release(total);
-  if (int rc = alloc_array(h, &out->idx, nnz)) return rc;
-  if (int rc = alloc_array(h, &out->val, nnz)) return rc;
+  if (int rc = alloc_array(h, &out->idx, nnz + 4)) return rc;  // (+ slack: the bulk copies move whole 16-byte units)
+  if (int rc = alloc_array(h, &out->val, nnz + 2)) return rc;
+  CK(cudaMemsetAsync(out->idx + nnz, 0, 4 * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(out->val + nnz, 0, 2 * sizeof(double), st));
   if (int rc = alloc_array(h, &out->carry, nrows)) return rc;
   if (geo.eq_windows && in_windows)
     if (int rc = alloc_array(h, &out->carry_eq, nrows)) return rc;
@@ -493,7 +497,7 @@ int setup_p2p(cpppd_solver *h) {
     }
   }
   // (the fused kernels wait for the halo themselves; the long-row pre-passes would read the ghosts too early)
-  if ((h->flags & CPPPD_FLAG_FUSED_HALO) && h->longA.count == 0 && h->longAT.count == 0)
+  if ((h->flags & CPPPD_FLAG_FUSED_HALO) && h->longA.count == 0 && h->longAT.count == 0 && !h->bandA.built && !h->bandAT.built)
     if (int rc = setup_fused(h, dst_base[0], dst_base[1])) return rc;
   // nobody may push before every rank has initialised its vectors and flags
   NK(g_nccl.AllReduce(send, send, 1, ncclInt8, ncclSum, h->comm, st));
@@ -611,7 +615,9 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
   // Banded operands (cpppd_banded.cuh) keep the caller's numbering: the window order along a row is what keeps
   // the sums bit-exact.  Candidates: forced by flag, or a pattern without locality over vectors of several windows.
-  const bool band_ok = !reorder && nnz > 0 && !(h->flags & (CPPPD_FLAG_NO_BANDED | CPPPD_FLAG_VALUE_DICT));
+  // With more than one GPU they need the balanced split in original order (decided below): windows are ranges of
+  // original ids, and the local layout must keep such a range in a few contiguous pieces.
+  const bool band_ok = (N > 1 || !reorder) && nnz > 0 && !(h->flags & (CPPPD_FLAG_NO_BANDED | CPPPD_FLAG_VALUE_DICT));
   const bool band_forced = band_ok && (h->flags & CPPPD_FLAG_BANDED);
   bool band_candidate = band_forced;
   if (band_ok && !band_forced && std::max(n, m) > 2 * band_window_elems(h)) {
@@ -692,6 +698,10 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     unsigned long long worst = 0;
     for (int r = 0; r < N; ++r) worst = std::max(worst, std::max(row_share[r], col_share[r]));
     h->balanced_split = nnz > 0 && (unsigned __int128)2 * N * worst > (unsigned __int128)3 * (unsigned long long)nnz;
+    // banded operands on several GPUs: only with the balanced split, whose rows / columns then keep their original
+    // order inside a rank (no locality buckets, no length sorting: the banded kernels do not pad)
+    if (N > 1 && !h->balanced_split) band_candidate = false;
+    const int keep_order = N > 1 && band_candidate ? 1 : 0;
     int64_t *col_prefix = nullptr;
     if (h->balanced_split) {
       int64_t *col_len64 = nullptr;
@@ -715,9 +725,9 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = tmp.get(&co_b, n)) return rc;
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 3 * N, st));
     if (m) k_sort_keys<<<grid_for(m), kBlock, 0, st>>>(row_key, m, (int32_t)G, owner_dev, m_eq, 1, rowptr, nullptr,
-                                                       h->balanced_split ? rowptr : nullptr, nnz, N, rk_a, ro_a, counts, counts + N);
+                                                       h->balanced_split ? rowptr : nullptr, nnz, N, keep_order, rk_a, ro_a, counts, counts + N);
     if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, nullptr, col_len,
-                                                       col_prefix, nnz, N, ck_a, co_a, counts + 2 * N, nullptr);
+                                                       col_prefix, nnz, N, keep_order, ck_a, co_a, counts + 2 * N, nullptr);
     const int end_bit = 44 + bits_for((uint64_t)2 * N + 1);
     cub::DoubleBuffer<uint64_t> rk(rk_a, rk_b), ck(ck_a, ck_b);
     cub::DoubleBuffer<uint32_t> rov(ro_a, ro_b), cov(co_a, co_b);
@@ -867,7 +877,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     } else {
       if (int rc = build_sell(h, rowptr, indices, values, m, &h->A)) return rc;
       if (band_candidate)
-        if (int rc = build_band(h, rowptr, indices, values, m, nnz, n, 0, band_forced, &h->bandA)) return rc;
+        if (int rc = build_band(h, rowptr, indices, values, m, nnz, n, 0, band_forced, nullptr, &h->bandA)) return rc;
     }
   } else {
     int64_t *len = nullptr, *lrowptr = nullptr;
@@ -892,6 +902,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
     } else {
       if (int rc = build_sell(h, lrowptr, lidx, lval, mloc, &h->A)) return rc;
+      if (band_candidate)
+        if (int rc = build_band(h, lrowptr, lidx, lval, mloc, lnnz, n, 0, band_forced, h->col_old, &h->bandA)) return rc;
     }
     tmp.release(len); tmp.release(lrowptr); tmp.release(lidx); tmp.release(lval);
   }
@@ -945,8 +957,10 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       tmp.release(s_rowptr); tmp.release(s_idx); tmp.release(s_val);
     } else {
       if (int rc = build_sell(h, lcolptr, t_idx, t_val, nloc, &h->AT)) return rc;
-      if (band_candidate && !reorder)
-        if (int rc = build_band(h, lcolptr, t_idx, t_val, nloc, lnnz, mloc, m_eq, band_forced, &h->bandAT)) return rc;
+      if (band_candidate)
+        if (int rc = build_band(h, lcolptr, t_idx, t_val, nloc, lnnz, m, m_eq, band_forced, reorder ? h->row_old : nullptr,
+                                &h->bandAT))
+          return rc;
     }
     tmp.release(lcolptr); tmp.release(t_idx); tmp.release(t_val);
   }
@@ -1070,6 +1084,11 @@ int launch_primal_band(cpppd_solver *h, bool write_d) {
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     double *ceq = B.carry_eq ? B.carry_eq : B.carry;  // one kind of rows only: a single carry serves it
     const bool last = w == B.geo.windows - 1;
+    if (!last && kBandShapes[B.shape].staged) {
+      PrimalStagedFn sfn = primal_staged_kernel(B.shape);
+      sfn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, eq ? ceq : B.carry, mode & kBandStart, h->n, ntiles);
+      continue;
+    }
     PrimalBandFn fn = primal_band_kernel(last, write_d, B.shape);
     fn<<<grid, kBlock, 0, h->stream>>>(
         cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles,
@@ -1087,6 +1106,11 @@ int launch_dual_band(cpppd_solver *h) {
     const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     const bool first = w == 0, last = w == W - 1;
+    if (!last && kBandShapes[B.shape].staged) {
+      DualStagedFn sfn = dual_staged_kernel(first, B.shape);
+      sfn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->m, ntiles);
+      continue;
+    }
     DualBandFn fn = dual_band_kernel(first, last, B.shape);
     fn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, h->m, ntiles, h->m_eq);
   }
@@ -1094,8 +1118,12 @@ int launch_dual_band(cpppd_solver *h) {
 }
 
 int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
-  if (variant == kBandVariant || (variant == -1 && h->bandAT.in_use)) return launch_primal_band(h, write_d);
   P2P &pp = h->p2p;
+  if (variant == kBandVariant || (variant == -1 && h->bandAT.in_use)) {
+    if (int rc = launch_primal_band(h, write_d)) return rc;
+    if (variant != -1) return 0;
+    return pp.active ? exchange_p2p(h, 0) : exchange(h, h->xbar, h->hx);
+  }
   const FusedComm *cm = pp.use_fused ? pp.fused[0] : nullptr;
   if (int rc = long_pass(h, h->longAT, h->y, h->y)) return rc;  // long columns: their A^T y into the tail of y
   if (h->AT.nslices) {
@@ -1112,8 +1140,12 @@ int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
 }
 
 int launch_dual(cpppd_solver *h, int variant = -1) {
-  if (variant == kBandVariant || (variant == -1 && h->bandA.in_use)) return launch_dual_band(h);
   P2P &pp = h->p2p;
+  if (variant == kBandVariant || (variant == -1 && h->bandA.in_use)) {
+    if (int rc = launch_dual_band(h)) return rc;
+    if (variant != -1) return 0;
+    return pp.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);
+  }
   const FusedComm *cm = pp.use_fused ? pp.fused[1] : nullptr;
   if (int rc = long_pass(h, h->longA, h->xbar, h->xbar)) return rc;  // long rows: their A xbar into the tail of xbar
   if (h->A.nslices) {
@@ -1136,7 +1168,7 @@ struct TuneChoice {
   bool band_primal = false, band_dual = false;
   float band_ms[2] = {0.f, 0.f};
   int band_shape[2] = {0, 0};
-  float band_shape_ms[2][4] = {};
+  float band_shape_ms[2][8] = {};
 };
 std::map<TuneKey, TuneChoice> g_tune_cache;
 std::mutex g_tune_mutex;

@@ -81,7 +81,7 @@ __global__ void k_bucket_work(const int32_t *__restrict__ key, const int64_t *__
 __global__ void k_sort_keys(const int32_t *__restrict__ key, int64_t count, int32_t granule,
                             const int32_t *__restrict__ owner_of_bucket, int64_t m_eq, int is_rows,
                             const int64_t *__restrict__ rowptr, const int32_t *__restrict__ len32,
-                            const int64_t *__restrict__ prefix, int64_t total, int world,
+                            const int64_t *__restrict__ prefix, int64_t total, int world, int keep_order,
                             uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_id,
                             int32_t *__restrict__ count_per_owner, int32_t *__restrict__ eq_per_owner) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +94,8 @@ __global__ void k_sort_keys(const int32_t *__restrict__ key, int64_t count, int3
   int64_t len = rowptr ? rowptr[i + 1] - rowptr[i] : (int64_t)len32[i];
   uint64_t len12 = (uint64_t)(len > 4095 ? 4095 : len);
   uint64_t major = is_rows ? (uint64_t)o * 2 + (i >= m_eq ? 1 : 0) : (uint64_t)o;
-  out_key[i] = (major << 44) | ((uint64_t)(uint32_t)q << 12) | len12;
+  // keep_order (banded operands on several GPUs): original order inside (owner, kind) — the sort is stable
+  out_key[i] = keep_order ? (major << 44) : ((major << 44) | ((uint64_t)(uint32_t)q << 12) | len12);
   out_id[i] = (uint32_t)i;
   atomicAdd(count_per_owner + o, 1);
   if (is_rows && i < m_eq) atomicAdd(eq_per_owner + o, 1);

@@ -60,7 +60,7 @@ struct Band {
   double sectors_per_gather = 0;                  // sampled locality of the operand (k_band_locality)
   float ms = 0.f;                                 // per half-iteration, measured by tune_kernels()
   int shape = 0;                                  // kBandShapes index of the windows before the last one
-  float shape_ms[4] = {0.f, 0.f, 0.f, 0.f};
+  float shape_ms[8] = {};
 };
 
 struct StatsDev {  // device-resident, copied verbatim into cpppd_stats

@@ -90,3 +90,25 @@ def test_random_lp_takes_the_banded_path_and_matches_the_c_port(monkeypatch):
     assert min(auto["band_sectors_per_gather"]) > 0.6
     for label in results:
         assert results[label][0] == want, label
+
+
+@pytest.mark.parametrize("name,window", [("random_small", 11), ("l1svm", 251)])
+@pytest.mark.parametrize("shape", range(8))
+def test_banded_kernel_shapes_give_the_same_bits(shape, name, window, monkeypatch):
+    """Every compiled shape of the window kernels — entries through registers (0-3) or staged in shared memory by
+    cp.async.bulk + mbarrier (4-7; the L1-SVM tiles take dozens of 384-entry pieces) — produces the golden bits."""
+    from pysparselp_b200 import _cabi
+    from pysparselp_b200.ChambollePockPPD import chambolle_pock_ppd
+
+    monkeypatch.setenv("CPPPD_BAND_WINDOW", str(window))
+    monkeypatch.setenv("CPPPD_BAND_SHAPE", str(shape))
+    args, g = case_args(name)
+    x, best, solver = chambolle_pock_ppd(*args, nb_max_iter=100, nb_iter_plot=10, flags=_cabi.FLAG_BANDED, return_solver=True)
+    try:
+        info = solver.info()
+        y = solver.get_y()
+    finally:
+        solver.close()
+    assert info["band_in_use"][1] == 1 and info["band_shape"][1] == shape
+    assert np.array_equal(x, g["x_100"])
+    assert np.array_equal(y, np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g]))

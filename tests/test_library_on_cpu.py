@@ -424,18 +424,23 @@ def test_emulated_banded_operands_give_the_same_bits(name, window, monkeypatch):
         solver.close()
 
 
-@pytest.mark.parametrize("shape", [1, 2, 3])
-def test_emulated_banded_kernel_shapes_give_the_same_bits(shape, monkeypatch):
-    """The window kernels are compiled in four (entries per lane and trip, CTAs per SM) shapes; cpppd_create times them
-    on large operands.  Every shape must produce the golden bits (shape 0 is what the other banded tests run)."""
-    monkeypatch.setenv("CPPPD_BAND_WINDOW", "11")
+@pytest.mark.parametrize("name,window", [("random_small", 11), ("l1svm", 251)])
+@pytest.mark.parametrize("shape", [1, 2, 3, 4, 5, 6, 7])
+def test_emulated_banded_kernel_shapes_give_the_same_bits(shape, name, window, monkeypatch):
+    """The window kernels are compiled in eight shapes — entries through registers (flat entries per lane and trip /
+    CTAs per SM) or staged in shared memory by bulk copies (gathers in flight per lane) — and cpppd_create times
+    them on large operands.  Every shape must produce the golden bits (shape 0 is what the other banded tests run).
+    The L1-SVM case has tiles of ~32 000 entries per window: dozens of staged pieces of 384 entries per tile."""
+    monkeypatch.setenv("CPPPD_BAND_WINDOW", str(window))
     monkeypatch.setenv("CPPPD_BAND_SHAPE", str(shape))
-    args, g = case_args("random_small")
+    args, g = case_args(name)
     x, best, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=100, nb_iter_plot=10, flags=_cabi.FLAG_BANDED)
     try:
         info = solver.info()
-        assert info["band_in_use"] == [1, 1] and info["band_shape"] == [shape, shape]
+        assert info["band_in_use"][1] == 1 and info["band_shape"][1] == shape
+        if name == "random_small":
+            assert info["band_in_use"] == [1, 1]
         assert np.array_equal(x, g["x_100"])
-        assert np.array_equal(solver.get_y(), np.concatenate([g["y_eq"], g["y_ineq"]]))
+        assert np.array_equal(solver.get_y(), np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g]))
     finally:
         solver.close()

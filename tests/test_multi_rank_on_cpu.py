@@ -182,3 +182,39 @@ def test_multi_rank_balanced_split_for_patterns_without_locality(world):
         assert np.array_equal(ghost_c, gc) and np.array_equal(ghost_r, gr)
         # nobody holds more than 1.5x its share of the entries, rows and columns alike
         assert r["info"]["nnz_local_rows"] * world * 2 <= 3 * A.nnz and r["info"]["nnz_local_cols"] * world * 2 <= 3 * A.nnz
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("transport", ["push_wait_kernels", "nccl"])
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("name", ["random_small", "sc105", "kb2"])
+def test_multi_rank_banded_operands(name, world, transport, monkeypatch):
+    """Banded operands (csrc/cpppd_banded.cuh) on several ranks: patterns without locality take the balanced split, rows
+    and columns keep their original order inside a rank, the windows are ranges of ORIGINAL ids (looked up through
+    the local -> original maps), and the halo exchange follows the last window of every half-iteration.  Same bits
+    as one GPU; the layout is the Python restatement's (keep_order)."""
+    monkeypatch.setenv("CPPPD_BAND_WINDOW", "9")
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    res = solve_on_ranks(args, world, TRANSPORTS[transport] | _cabi.FLAG_BANDED, 100, 10, **kw)
+    y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+    c, a_eq, beq, a_in, b_lo, b_up, lb, ub = args
+    a_in1, b_in1 = one_sided_rows(a_in, b_lo, b_up)
+    A, b, m_eq = stack_operator(a_eq if a_eq is not None and a_eq.shape[0] else None, beq, a_in1, b_in1, c.size)
+    part = po.partition(A.indptr, A.indices, A.shape[1], m_eq, world, granule=32, keep_order=True)
+    banded = 0
+    for rank, r in enumerate(res):
+        assert np.array_equal(r["x"], g["x_100"]) and np.array_equal(r["y"], y_gold) and np.array_equal(r["T"], g["diag_t"])
+        assert np.allclose(r["trace"], g["trace_10"], rtol=1e-6, atol=1e-9, equal_nan=True)
+        own_c, ghost_c = r["cols"]
+        own_r, ghost_r = r["rows"]
+        assert np.array_equal(own_c, part["col_order"][part["col_start"][rank]: part["col_start"][rank + 1]])
+        assert np.array_equal(own_r, part["row_order"][part["row_start"][rank]: part["row_start"][rank + 1]])
+        if part["balanced_split"]:
+            assert r["info"]["balanced_split"] == 1 and r["info"]["band_in_use"] == [1, 1]
+            assert np.all(np.diff(own_c) > 0)  # original order inside the rank
+            banded += 1
+        else:  # locality buckets: the banded form is not built
+            assert r["info"]["band_in_use"] == [0, 0]
+    if name == "random_small":
+        assert banded == world
