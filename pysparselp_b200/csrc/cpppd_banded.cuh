@@ -148,6 +148,25 @@ __global__ void k_band_locality(const int64_t *__restrict__ rowptr, const int32_
   }
 }
 
+// The window a launch gathers from starts cold: until its sectors have been touched once, the gathers miss L2 and
+// run at DRAM random-access speed.  The first CTAs of every launch therefore ask the L2 for the whole window up front
+// (one bulk prefetch of 32 KB per CTA: a 48 MB window is requested by the first 1536 CTAs, within the first waves).
+struct BandPrefetch {
+  const char *base;  // first byte of the window in the gathered vector (nullptr: no prefetch)
+  int64_t bytes;
+};
+constexpr int64_t kBandPrefetchSlice = 32768;
+__device__ __forceinline__ void band_prefetch(const BandPrefetch &pf) {
+#ifdef __CUDACC__
+  const int64_t off = (int64_t)blockIdx.x * kBandPrefetchSlice;
+  if (pf.base && threadIdx.x == 0 && off < pf.bytes) {
+    const int64_t left = pf.bytes - off;
+    const uint32_t size = (uint32_t)((left < kBandPrefetchSlice ? left : kBandPrefetchSlice) & ~(int64_t)15);
+    if (size) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.base + off), "r"(size) : "memory");
+  }
+#endif
+}
+
 // ---- the hot kernels ----------------------------------------------------------------------------------------
 // A warp owns a tile of 128 rows, lane l the rows 4 l .. 4 l + 3.  The entries of the tile in this window are one
 // contiguous run: the warp reads them FLAT, 128 at a time (lane l takes entries q + l, q + 32 + l, ...: every load
@@ -251,7 +270,8 @@ template <bool kFirst, bool kLast, int kChunk, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_dual_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base, const int32_t *__restrict__ idx,
             const double *__restrict__ val, const double *__restrict__ xbar, double *__restrict__ carry, Vec b, Vec sigma,
-            double *__restrict__ y, int64_t m, int64_t ntiles, int64_t m_eq) {
+            double *__restrict__ y, int64_t m, int64_t ntiles, int64_t m_eq, BandPrefetch pf) {
+  band_prefetch(pf);
   __shared__ double prod_all[kBandWarps][32 * kChunk];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
@@ -289,7 +309,8 @@ k_primal_band(const unsigned char *__restrict__ cnt, const uint32_t *__restrict_
               const double *__restrict__ val, const double *__restrict__ y, double *__restrict__ carry_eq,
               double *__restrict__ carry_in, int mode, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
               double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int64_t ntiles, int has_eq, int has_ineq,
-              double theta, double one_plus_theta) {
+              double theta, double one_plus_theta, BandPrefetch pf) {
+  band_prefetch(pf);
   __shared__ double prod_all[kBandWarps][32 * kChunk];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
@@ -447,7 +468,8 @@ template <bool kFirst, int kG, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_dual_band_staged(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
                    const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ xbar,
-                   double *__restrict__ carry, int64_t m, int64_t ntiles) {
+                   double *__restrict__ carry, int64_t m, int64_t ntiles, BandPrefetch pf) {
+  band_prefetch(pf);
   __shared__ BandStage stage[kBandWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
@@ -466,7 +488,8 @@ template <int kG, int kMinB>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_primal_band_staged(const unsigned char *__restrict__ cnt, const uint32_t *__restrict__ tile_base,
                      const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ y,
-                     double *__restrict__ carry, int start, int64_t n, int64_t ntiles) {
+                     double *__restrict__ carry, int start, int64_t n, int64_t ntiles, BandPrefetch pf) {
+  band_prefetch(pf);
   __shared__ BandStage stage[kBandWarps];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t tile = (int64_t)blockIdx.x * kBandWarps + wib;
@@ -494,14 +517,14 @@ constexpr BandShape kBandShapes[kNumBandShapes] = {
     {8, 5, 1, "bulk-g8/5cta"}, {10, 5, 1, "bulk-g10/5cta"}, {12, 4, 1, "bulk-g12/4cta"}, {6, 5, 1, "bulk-g6/5cta"}};
 
 using DualBandFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *, double *,
-                            Vec, Vec, double *, int64_t, int64_t, int64_t);
+                            Vec, Vec, double *, int64_t, int64_t, int64_t, BandPrefetch);
 using PrimalBandFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *,
                               double *, double *, int, Vec, Vec, Vec, Vec, double *, double *, double *, int64_t, int64_t, int,
-                              int, double, double);
+                              int, double, double, BandPrefetch);
 using DualStagedFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *, double *,
-                              int64_t, int64_t);
+                              int64_t, int64_t, BandPrefetch);
 using PrimalStagedFn = void (*)(const unsigned char *, const uint32_t *, const int32_t *, const double *, const double *,
-                                double *, int, int64_t, int64_t);
+                                double *, int, int64_t, int64_t, BandPrefetch);
 
 template <bool kFirst, bool kLast>
 DualBandFn dual_band_shape(int shape) {
@@ -514,7 +537,7 @@ DualBandFn dual_band_shape(int shape) {
 }
 // kernels of the windows before the last one; the last window always runs the register path with the fused epilogue
 inline DualBandFn dual_band_kernel(bool first, bool last, int shape) {
-  if (last) return first ? k_dual_band<true, true, 4, 4> : k_dual_band<false, true, 4, 4>;
+  if (last) return first ? k_dual_band<true, true, 3, 5> : k_dual_band<false, true, 3, 5>;
   return first ? dual_band_shape<true, false>(shape) : dual_band_shape<false, false>(shape);
 }
 inline PrimalBandFn primal_band_kernel(bool last, bool write_d, int shape) {

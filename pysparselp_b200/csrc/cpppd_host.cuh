@@ -567,10 +567,28 @@ int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const s
   return 0;
 }
 
+// CPPPD_SETUP_TIMING=1: wall-clock of the phases of setup() on stderr (after a stream synchronisation each)
+struct PhaseTimer {
+  cudaStream_t st;
+  int rank;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTimer(cudaStream_t s, int r) : st(s), rank(r), on(getenv("CPPPD_SETUP_TIMING") && atoi(getenv("CPPPD_SETUP_TIMING"))),
+                                      t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[cpppd setup rank %d] %-28s %8.1f ms\n", rank, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 int setup(cpppd_solver *h, const cpppd_problem *P) {
   const int64_t n = h->n_glob, m = h->m_glob, nnz = h->nnz_glob, m_eq = h->m_eq_glob;
   const int N = h->world, me = h->rank;
   cudaStream_t st = h->stream;
+  PhaseTimer phase(st, me);
   Scratch tmp(h);
   // ---- CSR of the whole A on the device (temporary; every rank analyses the same pattern)
   int64_t *rowptr = nullptr;
@@ -659,6 +677,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   }
 
   if (reorder) {
+    phase.mark("upload + validation");
     // ---- locality keys -> buckets -> owners (oracle/partition_oracle.py restates this block)
     const int64_t G = h->granule > 0 ? h->granule : default_granule(n);
     h->granule = G;
@@ -751,6 +770,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (row_order == ro_a) tmp.release(ro_b); else tmp.release(ro_a);
     if (col_order == co_a) tmp.release(co_b); else tmp.release(co_a);
     tmp.release(row_key); tmp.release(col_key); tmp.release(col_len); tmp.release(work); tmp.release(col_prefix);
+    phase.mark("partition + local orders");
     // ---- ghosts of this rank
     int32_t *gcol_flag = nullptr, *grow_flag = nullptr;
     if (int rc = tmp.get(&gcol_flag, n + 1)) return rc;
@@ -786,6 +806,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     CK(cudaStreamSynchronize(st));
     tmp.release(gcol_flag);
     tmp.release(grow_flag);
+    phase.mark("ghosts + id maps");
     // ---- what to send to every peer
     if (N > 1) {
       int32_t *sx_flag = nullptr, *sy_flag = nullptr, *sx_scan = nullptr, *sy_scan = nullptr;
@@ -796,13 +817,26 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       std::vector<std::vector<int32_t>> sx_lists(N), sy_lists(N);
       int32_t *list_dev = nullptr;
       if (int rc = tmp.get(&list_dev, std::max(nloc, mloc) + 1)) return rc;
+      // one pass over the entries marks, per owned column / row, the set of peers that need it
+      unsigned long long *sx_mask = nullptr, *sy_mask = nullptr;
+      if (int rc = tmp.get(&sx_mask, nloc + 1)) return rc;
+      if (int rc = tmp.get(&sy_mask, mloc + 1)) return rc;
+      CK(cudaMemsetAsync(sx_mask, 0, sizeof(unsigned long long) * (nloc + 1), st));
+      CK(cudaMemsetAsync(sy_mask, 0, sizeof(unsigned long long) * (mloc + 1), st));
+      RankStarts starts;
+      memset(&starts, 0, sizeof starts);
+      for (int r = 0; r <= N; ++r) {
+        starts.row[r] = row_start[r];
+        starts.col[r] = col_start[r];
+      }
+      if (nnz) k_mark_send_masks<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, starts, N,
+                                                                 sx_mask, sy_mask);
       for (int t = 0; t < N; ++t) {
         if (t == me) continue;
-        CK(cudaMemsetAsync(sx_flag, 0, sizeof(int32_t) * (nloc + 1), st));
-        CK(cudaMemsetAsync(sy_flag, 0, sizeof(int32_t) * (mloc + 1), st));
-        if (nnz) k_mark_sends<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce,
-                                                              row_start[t], row_start[t + 1], col_start[t], col_start[t + 1],
-                                                              sx_flag, sy_flag);
+        CK(cudaMemsetAsync(sx_flag + nloc, 0, sizeof(int32_t), st));
+        CK(cudaMemsetAsync(sy_flag + mloc, 0, sizeof(int32_t), st));
+        if (nloc) k_flag_from_mask<<<grid_for(nloc), kBlock, 0, st>>>(sx_mask, nloc, t, sx_flag);
+        if (mloc) k_flag_from_mask<<<grid_for(mloc), kBlock, 0, st>>>(sy_mask, mloc, t, sy_flag);
         if (int rc = exclusive_scan(h, sx_flag, sx_scan, nloc + 1)) return rc;
         if (int rc = exclusive_scan(h, sy_flag, sy_scan, mloc + 1)) return rc;
         int32_t cx = 0, cy = 0;
@@ -834,6 +868,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
         if (H.send_total) CK(cudaMemcpy(H.send_idx, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice));
       }
       tmp.release(sx_flag); tmp.release(sy_flag); tmp.release(sx_scan); tmp.release(sy_scan); tmp.release(list_dev);
+      tmp.release(sx_mask); tmp.release(sy_mask);
     }
   }
   const int64_t nloc = ce - cs, mloc = re - rs;
@@ -863,6 +898,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       h->ndict = 0;
     }
   }
+  phase.mark("send lists");
   // ---- this rank's rows of A -> SELL-32
   int64_t *s_rowptr = nullptr;  // CSR without the long rows (see split_long_rows), when there are any
   int32_t *s_idx = nullptr;
@@ -907,6 +943,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     }
     tmp.release(len); tmp.release(lrowptr); tmp.release(lidx); tmp.release(lval);
   }
+  phase.mark("rows of A -> SELL (+ band)");
   // ---- this rank's columns of A as rows of A^T.  A stable radix sort of the entries (taken in CSR
   //      order) by column keeps, inside each column, the original row order — exactly the
   //      accumulation order of scipy's csc_matvec.
@@ -964,6 +1001,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     }
     tmp.release(lcolptr); tmp.release(t_idx); tmp.release(t_val);
   }
+  phase.mark("columns of A -> SELL (+ band)");
   // ---- vectors in local layout
   for (double **v : {&h->c, &h->T, &h->lb, &h->ub, &h->best})
     if (int rc = alloc_array(h, v, nloc)) return rc;
@@ -1031,6 +1069,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       }
     }
   }
+  phase.mark("vectors + preconditioners");
   // ---- stats plumbing
   h->stat_blocks_c = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(nloc), (int64_t)h->sm_count * 8));
   h->stat_blocks_r = (int)std::max<int64_t>(1, std::min<int64_t>(grid_for(h->A.nslices * 32), (int64_t)h->sm_count * 8));
@@ -1048,9 +1087,12 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   h->tiny = (h->flags & CPPPD_FLAG_TINY_PERSISTENT) && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
             !h->bandA.built && !h->bandAT.built &&
             std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
+  phase.mark("stats plumbing");
   if (int rc = tune_kernels(h)) return rc;
+  phase.mark("kernel timing");
   if (want_p2p)
     if (int rc = setup_p2p(h)) return rc;
+  phase.mark("peer-memory mapping");
   return 0;
 }
 
@@ -1072,6 +1114,19 @@ int exchange(cpppd_solver *h, double *vec, Halo &H) {
 // waits, pushes and signals (CPPPD_FLAG_FUSED_HALO), or NCCL send/recv (CPPPD_FLAG_NO_P2P).
 // one launch per window of the gathered vector (cpppd_banded.cuh)
 constexpr int kBandVariant = -2;  // `variant` argument of launch_primal / launch_dual: time the banded kernels
+// the piece of the gathered vector that window w of B covers (one GPU: local ids are original ids); CPPPD_BAND_PREFETCH=0
+// switches the L2 prefetch off
+BandPrefetch band_window_range(const cpppd_solver *h, const Band &B, const double *vec, int64_t vec_len, int w) {
+  static const bool enabled = [] { const char *e = getenv("CPPPD_BAND_PREFETCH"); return !e || atoi(e) != 0; }();
+  if (!enabled || h->world > 1) return BandPrefetch{nullptr, 0};
+  const BandGeometry &g = B.geo;
+  const int64_t lo = w < g.eq_windows ? (int64_t)w * g.eq_elems : g.split + (int64_t)(w - g.eq_windows) * g.in_elems;
+  const int64_t end = w < g.eq_windows ? g.split : vec_len;
+  const int64_t hi = std::min(end, lo + (w < g.eq_windows ? g.eq_elems : g.in_elems));
+  const int64_t first = lo & ~(int64_t)1;  // 16-byte aligned start
+  return BandPrefetch{reinterpret_cast<const char *>(vec + first), std::max<int64_t>(0, (hi - first) * 8)};
+}
+
 int launch_primal_band(cpppd_solver *h, bool write_d) {
   const Band &B = h->bandAT;
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
@@ -1083,16 +1138,17 @@ int launch_primal_band(cpppd_solver *h, bool write_d) {
     const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     double *ceq = B.carry_eq ? B.carry_eq : B.carry;  // one kind of rows only: a single carry serves it
+    const BandPrefetch pf = band_window_range(h, B, h->y, h->m, w);
     const bool last = w == B.geo.windows - 1;
     if (!last && kBandShapes[B.shape].staged) {
       PrimalStagedFn sfn = primal_staged_kernel(B.shape);
-      sfn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, eq ? ceq : B.carry, mode & kBandStart, h->n, ntiles);
+      sfn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->y, eq ? ceq : B.carry, mode & kBandStart, h->n, ntiles, pf);
       continue;
     }
     PrimalBandFn fn = primal_band_kernel(last, write_d, B.shape);
     fn<<<grid, kBlock, 0, h->stream>>>(
         cnt, base, B.idx, B.val, h->y, ceq, B.carry, mode, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar, h->dbuf, h->n, ntiles,
-        has_eq, has_ineq, h->theta, h->one_plus_theta);
+        has_eq, has_ineq, h->theta, h->one_plus_theta, pf);
   }
   return 0;
 }
@@ -1106,13 +1162,14 @@ int launch_dual_band(cpppd_solver *h) {
     const unsigned char *cnt = B.cnt + (int64_t)w * B.rows_pad;
     const uint32_t *base = B.tile_base + (int64_t)w * ntiles;
     const bool first = w == 0, last = w == W - 1;
+    const BandPrefetch pf = band_window_range(h, B, h->xbar, h->n, w);
     if (!last && kBandShapes[B.shape].staged) {
       DualStagedFn sfn = dual_staged_kernel(first, B.shape);
-      sfn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->m, ntiles);
+      sfn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->m, ntiles, pf);
       continue;
     }
     DualBandFn fn = dual_band_kernel(first, last, B.shape);
-    fn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, h->m, ntiles, h->m_eq);
+    fn<<<grid, kBlock, 0, h->stream>>>(cnt, base, B.idx, B.val, h->xbar, B.carry, h->vb, h->vsigma, h->y, h->m, ntiles, h->m_eq, pf);
   }
   return 0;
 }

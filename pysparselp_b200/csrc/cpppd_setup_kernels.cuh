@@ -138,16 +138,40 @@ __global__ void k_mark_ghosts(const int32_t *__restrict__ indices, const uint32_
   if (col_mine && !row_mine) grow_flag[rp] = 1;
 }
 
-// what this rank must send to peer t: its columns hit by t's rows, its rows hitting t's columns
-__global__ void k_mark_sends(const int32_t *__restrict__ indices, const uint32_t *__restrict__ row_of, int64_t nnz,
-                             const int32_t *__restrict__ row_pos, const int32_t *__restrict__ col_pos, int32_t rs,
-                             int32_t re, int32_t cs, int32_t ce, int32_t trs, int32_t tre, int32_t tcs, int32_t tce,
-                             int32_t *__restrict__ sendx_flag, int32_t *__restrict__ sendy_flag) {
+// What this rank must send to its peers: its columns hit by their rows, its rows hitting their columns — for all
+// peers in ONE pass over the entries: bit t of sendx_mask[j] / sendy_mask[i] is set when peer t needs
+// this rank's column j / row i (world <= 64).  The owner of a position is found in the rank boundaries (N + 1 each).
+struct RankStarts {
+  int32_t row[kMaxWorld + 1], col[kMaxWorld + 1];
+};
+__device__ __forceinline__ int owner_of(const int32_t *start, int world, int32_t pos) {
+  int lo = 0, hi = world - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (start[mid] <= pos) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+__global__ void k_mark_send_masks(const int32_t *__restrict__ indices, const uint32_t *__restrict__ row_of, int64_t nnz,
+                                  const int32_t *__restrict__ row_pos, const int32_t *__restrict__ col_pos, int32_t rs,
+                                  int32_t re, int32_t cs, int32_t ce, RankStarts starts, int world,
+                                  unsigned long long *__restrict__ sendx_mask, unsigned long long *__restrict__ sendy_mask) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nnz) return;
-  int32_t rp = row_pos[row_of[e]], cp = col_pos[indices[e]];
-  if (cp >= cs && cp < ce && rp >= trs && rp < tre) sendx_flag[cp - cs] = 1;
-  if (rp >= rs && rp < re && cp >= tcs && cp < tce) sendy_flag[rp - rs] = 1;
+  const int32_t rp = row_pos[row_of[e]], cp = col_pos[indices[e]];
+  const bool row_mine = rp >= rs && rp < re, col_mine = cp >= cs && cp < ce;
+  if (col_mine && !row_mine) {
+    const unsigned long long bit = 1ull << owner_of(starts.row, world, rp);
+    if (!(sendx_mask[cp - cs] & bit)) atomicOr(sendx_mask + (cp - cs), bit);
+  }
+  if (row_mine && !col_mine) {
+    const unsigned long long bit = 1ull << owner_of(starts.col, world, cp);
+    if (!(sendy_mask[rp - rs] & bit)) atomicOr(sendy_mask + (rp - rs), bit);
+  }
+}
+__global__ void k_flag_from_mask(const unsigned long long *__restrict__ mask, int64_t count, int peer, int32_t *__restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) flag[i] = (int32_t)((mask[i] >> peer) & 1ull);
 }
 
 // out[base + scan[i]] = value(i) for flagged i

@@ -101,6 +101,30 @@ def main():
         xo, _ = chambolle_pock_ppd_oracle(*args, x0=x0, nb_max_iter=64, nb_iter_plot=1000)
     x, _ = chambolle_pock_ppd(*args, x0=x0, nb_max_iter=64, nb_iter_plot=1000)
     assert np.array_equal(x, xo)
+    # banded operands across ranks (csrc/cpppd_banded.cuh): a random LP without locality takes the balanced split in
+    # original order; x, y after 6 iterations must hash to the digest the C port minted (tests/golden/bench_digests.json)
+    import json
+
+    import bench
+
+    os.environ["CPPPD_BAND_WINDOW_MB"] = "0.25"
+    table = json.load(open(bench.DIGESTS))
+    for size in (200000, 2000000):
+        lp, _ = bench.build_workload("random", size, pinned=False)
+        largs = generators.lp_args(lp)
+        for flags in (_cabi.FLAG_BANDED, 0, _cabi.FLAG_BANDED | _cabi.FLAG_NO_P2P):
+            x, _, solver = chambolle_pock_ppd(*largs, nb_max_iter=bench.DIGEST_ITERS, nb_iter_plot=1000, return_solver=True,
+                                              flags=flags)
+            y = solver.get_y()
+            info = solver.info()
+            solver.close()
+            assert bench.iterate_digest(x, y) == table[bench.workload_name("random", size)]["sha256"], (size, flags)
+            if flags & _cabi.FLAG_BANDED:
+                assert info["balanced_split"] == 1 and info["band_in_use"] == [1, 1], info
+        if rank == 0:
+            print("random LP %d x %d banded on %d GPUs: digest ok (windows %r)" % (size, 2 * size, world, info["band_windows"]),
+                  flush=True)
+    os.environ.pop("CPPPD_BAND_WINDOW_MB")
     dist.barrier()
     if rank == 0:
         print("DIST_WORKER_OK world=%d" % world, flush=True)

@@ -280,6 +280,7 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
 inline int atomicMin(int *p, int v) { int o = *p; if (v < o) *p = v; return o; }
 inline int atomicOr(int *p, int v) { int o = *p; *p = o | v; return o; }
 inline unsigned atomicOr(unsigned *p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o | v; return o; }
 using std::max;
 using std::min;
 inline long long max(long long a, long b) { return a > b ? a : (long long)b; }
