@@ -26,7 +26,7 @@
  *   CPPPD_KERNEL_VARIANT    like cpppd_problem.kernel_variant when that field is 0
  *   CPPPD_AUTOTUNE_MIN_NNZ  smallest operand (entries) whose kernel variants are timed at creation (default 2^22)
  *   CPPPD_AUTOTUNE_CACHE    0: time the variants at every creation instead of once per operand shape and process
- *   CPPPD_BAND_WINDOW_MB    megabytes of the gathered vector per window of a banded operand (default 48)
+ *   CPPPD_BAND_WINDOW_MB    megabytes of the gathered vector per window of a banded operand (default 56)
  *   CPPPD_BAND_SHAPE        0..7: compiled shape of the banded window kernels (cpppd_info.band_shape_ms) instead of the timed choice
  *   CPPPD_BAND_WINDOW       the same in elements (tests: windows of a few dozen elements on small LPs); both are
  *                           only read when cpppd_problem.band_window is 0
@@ -154,7 +154,7 @@ typedef struct {
                            budget rows).  0: default (2048); < 0: never.  LPs with such rows agree with the reference
                            to rounding (fixed summation tree) instead of bit for bit; others are unaffected. */
   int64_t band_window;  /* banded operands: elements of the gathered vector per window.  0: CPPPD_BAND_WINDOW_MB
-                           megabytes (default 48 MB = 6 291 456 elements, the L2-resident plateau measured by
+                           megabytes (default 56 MB = 7 340 032 elements: the L2-resident plateau measured by
                            tools/probe/gather_probe.cu) */
 } cpppd_problem;
 

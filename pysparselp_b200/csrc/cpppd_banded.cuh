@@ -9,7 +9,7 @@
 // whole vector); what helps is making the gathers hit L2: tools/probe/gather_probe.cu measured 4.7 ns per 1000 random
 // gathers while the gathered window is <= 48-64 MB, 2.2x / 3.7x / 4.2x that at 128 / 320 / 512 MB.
 //
-// What.  The gathered vector is cut into windows of <= 48 MB; the entries of the operand are stored window-major
+// What.  The gathered vector is cut into windows of <= 56 MB; the entries of the operand are stored window-major
 // (all entries that gather from window 0, then window 1, ...), in CSR order inside a window, with one count byte per
 // row and window and one offset per tile of 128 rows and window.  A half-iteration is one launch PER WINDOW: thread i continues
 // the sum of row i where the previous window left it (an fp64 carry in HBM, 16 bytes per row and window), so the
@@ -150,7 +150,7 @@ __global__ void k_band_locality(const int64_t *__restrict__ rowptr, const int32_
 
 // The window a launch gathers from starts cold: until its sectors have been touched once, the gathers miss L2 and
 // run at DRAM random-access speed.  The first CTAs of every launch therefore ask the L2 for the whole window up front
-// (one bulk prefetch of 32 KB per CTA: a 48 MB window is requested by the first 1536 CTAs, within the first waves).
+// (one bulk prefetch of 32 KB per CTA: a 56 MB window is requested by the first 1792 CTAs, within the first waves).
 struct BandPrefetch {
   const char *base;  // first byte of the window in the gathered vector (nullptr: no prefetch)
   int64_t bytes;

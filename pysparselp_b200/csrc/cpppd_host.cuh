@@ -86,13 +86,14 @@ int build_sell(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   return 0;
 }
 
-// elements of the gathered vector per window: cpppd_problem.band_window, CPPPD_BAND_WINDOW_MB, or 48 MB — the
-// largest window tools/probe/gather_probe.cu still found at the L2-hit plateau with the matrix streaming past it
+// elements of the gathered vector per window: cpppd_problem.band_window, CPPPD_BAND_WINDOW_MB, or 56 MB — inside the
+// L2-hit plateau tools/probe/gather_probe.cu found (<= 64 MB with the matrix streaming past it) and the best of the
+// 24 .. 80 MB sweep on the 20M x 40M random LP (profiles/r02_random_lp.md)
 int64_t band_window_elems(const cpppd_solver *h) {
   if (h->band_window > 0) return h->band_window;
   if (const char *env = getenv("CPPPD_BAND_WINDOW"))
     if (atoll(env) > 0) return atoll(env);
-  double mb = 48.0;
+  double mb = 56.0;
   if (const char *env = getenv("CPPPD_BAND_WINDOW_MB")) mb = atof(env);
   return std::max<int64_t>(32, (int64_t)(mb * 1048576.0 / 8.0));
 }

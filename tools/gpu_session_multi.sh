@@ -11,7 +11,7 @@ n=${2:-2}
 what=${3:-all}
 out=gpurun_out
 mkdir -p $out
-export PYTHONUNBUFFERED=1 CPPPD_HALO_TIMEOUT_S=20
+export PYTHONUNBUFFERED=1 CPPPD_HALO_TIMEOUT_S=20 CPPPD_SETUP_TIMING=1
 run() { timeout "$1" python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
 
 if [ "$what" = all ] || [ "$what" = parity ]; then
