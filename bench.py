@@ -681,7 +681,7 @@ def small_configs(a, generators, make_solver):
             small["netlib_sc105"] = {"error": repr(e)}
         for name, sargs in small_lps.items():
             small[name] = {}
-            for label, sflags in (("cuda_graphs", 0), ("persistent_cta", 512)):
+            for label, sflags in (("cuda_graphs", 4096), ("persistent_cta", 0)):  # (4096: CPPPD_FLAG_NO_TINY_PERSISTENT)
                 try:
                     ss = make_solver(*sargs, flags=sflags)
                     try:

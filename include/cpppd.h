@@ -94,10 +94,7 @@ enum {
   CPPPD_FLAG_FUSED_HALO = 1u << 7,
   /* never time the kernel variants at creation: use variant 1 (see cpppd_problem.kernel_variant) */
   CPPPD_FLAG_NO_AUTOTUNE = 1u << 8,
-  /* one GPU, LPs whose operands fit the L1 of one SM (n, m <= 4096 and <= 16384 stored entries in A and A^T
-   * together, e.g. netlib SC105): cpppd_iterate(k) runs all k iterations in ONE launch of one CTA instead of 2k
-   * graph nodes — such LPs are bound by launch latency, not bandwidth.  Same per-row code, same bits.
-   * (Opt-in until it has been measured on hardware.) */
+  /* (accepted for compatibility: this is the default now, see CPPPD_FLAG_NO_TINY_PERSISTENT) */
   CPPPD_FLAG_TINY_PERSISTENT = 1u << 9,
   /* one GPU, caller's numbering: store A and A^T window-major ("banded") and run one launch per window of the
    * gathered vector, so that the gathers of a launch stay inside a window that fits the L2 (cpppd_banded.cuh).
@@ -107,7 +104,13 @@ enum {
    * otherwise the operand silently stays with the SELL kernels; see cpppd_info.band_in_use).  Same bits. */
   CPPPD_FLAG_BANDED = 1u << 10,
   /* never build the banded copies */
-  CPPPD_FLAG_NO_BANDED = 1u << 11
+  CPPPD_FLAG_NO_BANDED = 1u << 11,
+  /* One GPU, LPs whose operands fit the L1 of one SM (n, m <= 4096 and <= 16384 stored entries in A and A^T together,
+   * e.g. netlib SC105) and no forced kernel variant: cpppd_iterate(k) runs all k iterations in ONE launch of one CTA
+   * (k_tiny_iterate) instead of 2k graph nodes — such LPs are bound by launch latency, not bandwidth (SC105 on a B200:
+   * 800 000 iterations/s against 189 000 through CUDA graphs).  Same per-row code, same bits.  This flag keeps the
+   * graph path. */
+  CPPPD_FLAG_NO_TINY_PERSISTENT = 1u << 12
 };
 
 typedef struct {

@@ -28,6 +28,7 @@ FLAG_NO_AUTOTUNE = 1 << 8
 FLAG_TINY_PERSISTENT = 1 << 9
 FLAG_BANDED = 1 << 10
 FLAG_NO_BANDED = 1 << 11
+FLAG_NO_TINY_PERSISTENT = 1 << 12
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 

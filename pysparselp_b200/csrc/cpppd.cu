@@ -54,8 +54,9 @@ int fetch_vector(cpppd_solver *h, const double *local, bool is_col, double *host
   if (int rc = tmp.get(&buf, full)) return rc;
   CK(cudaMemsetAsync(buf, 0, sizeof(double) * std::max<int64_t>(full, 1), h->stream));
   if (owned) k_scatter_f64<<<grid_for(owned), kBlock, 0, h->stream>>>(local, is_col ? h->col_old : h->row_old, owned, buf);
-  // every entry is owned by exactly one rank, the others contribute +0.0: the sum is exact
-  if (h->world > 1 && full) NK(g_nccl.AllReduce(buf, buf, (size_t)full, ncclFloat64, ncclSum, h->comm, h->stream));
+  // every entry is owned by exactly one rank and the others contribute all-zero bits: summing the BIT PATTERNS as
+  // 64-bit integers reproduces the owner's double exactly (an fp64 sum would turn -0.0 into +0.0 and quiet NaNs)
+  if (h->world > 1 && full) NK(g_nccl.AllReduce(buf, buf, (size_t)full, ncclUint64, ncclSum, h->comm, h->stream));
   if (full) CK(cudaMemcpyAsync(host_dst, buf, sizeof(double) * full, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;

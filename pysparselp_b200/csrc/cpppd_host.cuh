@@ -1085,7 +1085,8 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(st));
   // a single CTA can carry a whole iteration when both operands fit the L1 of one SM (see k_tiny_iterate)
-  h->tiny = (h->flags & CPPPD_FLAG_TINY_PERSISTENT) && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
+  const bool variant_forced = h->variant_request != 0 || (getenv("CPPPD_KERNEL_VARIANT") && atoi(getenv("CPPPD_KERNEL_VARIANT")));
+  h->tiny = !(h->flags & CPPPD_FLAG_NO_TINY_PERSISTENT) && !variant_forced && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
             !h->bandA.built && !h->bandAT.built &&
             std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
   phase.mark("stats plumbing");

@@ -80,7 +80,7 @@ thread_local std::vector<Pending> g_group;
 thread_local int g_group_depth = 0;
 thread_local struct ncclComm *g_current_comm = nullptr;  // the rank thread's communicator (one at a time)
 
-size_t type_bytes(ncclDataType_t t) { return t == ncclFloat64 ? 8 : 1; }
+size_t type_bytes(ncclDataType_t t) { return (t == ncclFloat64 || t == ncclUint64) ? 8 : 1; }
 
 }  // namespace
 
@@ -147,6 +147,13 @@ ncclResult_t ncclAllReduce(const void *send, void *recv, size_t count, ncclDataT
     for (size_t i = 0; i < count; ++i) {
       double acc = static_cast<const double *>(w->pub[0])[i];
       for (int r = 1; r < w->n; ++r) acc += static_cast<const double *>(w->pub[r])[i];
+      out[i] = acc;
+    }
+  } else if (t == ncclUint64) {
+    unsigned long long *out = reinterpret_cast<unsigned long long *>(tmp.data());
+    for (size_t i = 0; i < count; ++i) {
+      unsigned long long acc = 0;
+      for (int r = 0; r < w->n; ++r) acc += static_cast<const unsigned long long *>(w->pub[r])[i];
       out[i] = acc;
     }
   } else {

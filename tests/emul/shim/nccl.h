@@ -6,5 +6,5 @@
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef struct ncclComm *ncclComm_t;
 typedef enum { ncclSuccess = 0, ncclInvalidArgument = 4 } ncclResult_t;
-typedef enum { ncclInt8 = 0, ncclFloat64 = 8 } ncclDataType_t;
+typedef enum { ncclInt8 = 0, ncclUint64 = 5, ncclFloat64 = 8 } ncclDataType_t;
 typedef enum { ncclSum = 0, ncclMax = 2 } ncclRedOp_t;

@@ -10,11 +10,15 @@ from conftest import CASE_PARAMS, GOLDEN_CASES, case_args
 from emul.cabi_driver import emulated_chambolle_pock_ppd, make_emulated_solver
 from pysparselp_b200 import _cabi
 
+# (the small goldens would otherwise all run in the persistent CTA, which has its own tests below: keep the
+#  thread-per-row kernels + CUDA graphs under test here, and the library default as one more set)
+GRAPHS = _cabi.FLAG_NO_TINY_PERSISTENT
 FLAG_SETS = {
-    "plain": 0,
-    "renumbered": _cabi.FLAG_REORDER,
-    "compressed": _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS,
-    "all": _cabi.FLAG_REORDER | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS,
+    "plain": GRAPHS,
+    "renumbered": GRAPHS | _cabi.FLAG_REORDER,
+    "compressed": GRAPHS | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS,
+    "all": GRAPHS | _cabi.FLAG_REORDER | _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS,
+    "default": 0,
 }
 
 

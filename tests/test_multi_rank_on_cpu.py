@@ -218,3 +218,29 @@ def test_multi_rank_banded_operands(name, world, transport, monkeypatch):
             assert r["info"]["band_in_use"] == [0, 0]
     if name == "random_small":
         assert banded == world
+
+
+@pytest.mark.timeout(300)
+def test_distributed_vector_assembly_keeps_the_sign_of_zero():
+    """cpppd_get_vector on several ranks assembles a vector by summing, over the ranks, a buffer that holds the owner's
+    value and zero bits elsewhere.  The sum runs on the 64-bit patterns: a floating point sum would return +0.0 for an
+    entry whose owner holds -0.0 (seen on hardware: the digest of a 2 M-variable random LP differed from the C port's
+    while every element compared equal)."""
+    args, g = case_args("random_small")
+    n, m = args[0].size, g["y_eq"].size + g["y_ineq"].size
+    xs = np.linspace(-1.0, 1.0, n)
+    xs[::3] = -0.0
+    ys = np.linspace(-2.0, 2.0, m)
+    ys[1::4] = -0.0
+
+    def body(rank, world, comm_id):
+        solver = make_emulated_solver(*args, partition_granule=32, rank=rank, world=world, comm_id=comm_id)
+        solver.set_x(xs)
+        solver.set_y(ys)
+        out = solver.get_x(), solver.get_y()
+        solver.close()
+        return out
+
+    for x, y in run_ranks(3, body):
+        assert np.array_equal(x, xs) and np.array_equal(np.signbit(x), np.signbit(xs))
+        assert np.array_equal(y, ys) and np.array_equal(np.signbit(y), np.signbit(ys))

@@ -22,7 +22,7 @@ if [ "$what" = all ] || [ "$what" = parity ]; then
 fi
 port=29621
 if [ "$what" = all ] || [ "$what" = potts ]; then
-  for flags in 0 128; do
+  for flags in 0 ${POTTS_EXTRA_FLAGS:-}; do
     echo "== bench potts --gpus $n --flags $flags" | tee -a $out/${tag}_multi_n$n.log
     run 600 $port bench.py --gpus $n --steps 10 --warmup 3 --e2e-steps 1 --flags $flags \
       > $out/${tag}_bench_potts_n${n}_f$flags.json 2> $out/${tag}_bench_potts_n${n}_f$flags.err

@@ -18,6 +18,8 @@ if a.kind == "potts":
     lp = generators.potts_lp(a.size)
 elif a.kind == "random":
     lp, _ = generators.random_sparse_lp_chunked(a.size, 2 * a.size, nnz_per_row=8)
+elif a.kind == "l1svm":  # --size samples x 1000 features (BASELINE configs[2] family)
+    lp, _ = generators.l1svm_lp(a.size, 1000)
 t1 = time.time()
 a_in, b_in = one_sided_rows(lp.a_ineq, lp.b_lower, lp.b_upper)
 A, b, m_eq = stack_operator(lp.a_eq, lp.b_eq, a_in, b_in, lp.c.size)
@@ -34,7 +36,8 @@ out = dict(kind=a.kind, size=a.size, variant=a.variant, chosen=(info["primal_var
            algo_GBs=info["bytes_per_iteration_algorithmic"] / ms / 1e6,
            actual_GBs=info["bytes_per_iteration_actual"] / ms / 1e6, times=times,
            pad_A=info["a_padded_entries"] / max(info["nnz"], 1), pad_AT=info["at_padded_entries"] / max(info["nnz"], 1),
-           device_GB=info["device_bytes"] / 1e9, band_windows=info["band_windows"], band_in_use=info["band_in_use"],
+           device_GB=info["device_bytes"] / 1e9, long_rows=info["long_rows"], long_cols=info["long_cols"],
+           long_entries=info["long_entries"], band_windows=info["band_windows"], band_in_use=info["band_in_use"],
            band_ms=info["band_ms"], band_shape=info["band_shape"], band_shape_ms=info["band_shape_ms"], band_spg=info["band_sectors_per_gather"], band_window_mb=info["band_window_bytes"] / 2**20,
            variant_ms=info["variant_ms"], band_env=os.environ.get("CPPPD_BAND_WINDOW_MB"))
 print(json.dumps(out))
