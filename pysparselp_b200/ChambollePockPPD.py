@@ -17,7 +17,9 @@ automatically; see ``cpppd_problem.kernel_variant`` — the iterates do not depe
 ``long_row_threshold`` (rows / columns with more entries are summed by many threads, see
 ``cpppd_problem.long_row_threshold``), ``distributed`` (None: use the initialised torch.distributed
 world when it has more than one rank — one process per GPU, every rank passes the same LP and
-gets the same result; False: this GPU only; or an explicit ProcessGroup).
+gets the same result; False: this GPU only; or an explicit ProcessGroup), ``n_gpus`` (N > 1: this ONE process
+drives N GPUs of the node — helper processes are spawned for the other devices for the duration of the call, see
+``pysparselp_b200/multi_gpu.py``; ``device`` may then list the N ordinals).
 """
 import atexit
 import ctypes as C
@@ -551,6 +553,7 @@ def chambolle_pock_ppd(
     partition_granule=0,
     kernel_variant=0,
     long_row_threshold=0,
+    n_gpus=None,
 ):
     """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
 
@@ -574,6 +577,18 @@ def chambolle_pock_ppd(
     n = c.size
     lb = _as_f64(lb, n, "lb")  # the reference asserts these sizes (:95-96)
     ub = _as_f64(ub, n, "ub")
+    if n_gpus is not None and int(n_gpus) > 1:
+        # one call, one process, several GPUs: helper processes for the other devices (pysparselp_b200/multi_gpu.py)
+        from .multi_gpu import solve_on_gpus
+
+        if return_solver:
+            raise ValueError("return_solver is not available with n_gpus > 1 (the solver state lives in several processes)")
+        kw = dict(alpha=alpha, theta=theta, nb_max_iter=nb_max_iter, max_time=max_time, save_problem=save_problem,
+                  force_integer=force_integer, nb_iter_plot=nb_iter_plot, verbose=verbose, flags=flags,
+                  partition_granule=partition_granule, kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
+        return solve_on_gpus(n_gpus, dict(c=c, a_eq=a_eq, beq=beq, a_ineq=a_ineq, b_lower=b_lower, b_upper=b_upper, lb=lb,
+                                          ub=ub, x0=x0), kw, callback_func=callback_func,
+                             devices=device if isinstance(device, (list, tuple)) else None)
     if save_problem:  # :99-112
         import pickle
 

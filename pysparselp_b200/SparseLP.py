@@ -505,6 +505,10 @@ class SparseLP:
                        reduced.b_lower, reduced.b_upper, reduced.lower_bounds, reduced.upper_bounds)
         want_device_curves = solver_options.pop("device_curves", True)
         device_curves = want_device_curves and plot_solution is None and reduced.nb_variables == self.nb_variables
+        if int(solver_options.get("n_gpus") or 1) > 1:
+            # several GPUs from this one process (pysparselp_b200/multi_gpu.py): the solver state lives in helper
+            # processes too, so the curves come through the callback, evaluated on the host like the reference does
+            device_curves = False
         if device_curves:
             # No variable was eliminated (x_full == x) and nobody asked to see x: every per-callback curve
             # of the reference (:1074-1091) is evaluated on the device inside the stats block and x never

@@ -267,3 +267,36 @@ def test_random_lp_generator_is_feasible_and_regular():
     assert np.all(lp.lb <= xf) and np.all(xf <= lp.ub)
     lp2, _ = generators.random_sparse_lp(500, 900, n_eq=60, nnz_per_row=8, seed=3)
     assert np.array_equal(lp.a_ineq.data, lp2.a_ineq.data)
+
+
+def test_multi_gpu_front_ships_the_lp_through_shared_memory():
+    """pysparselp_b200/multi_gpu.py (``n_gpus=``): the LP reaches the helper processes as POSIX shared memory blocks
+    described by a small picklable spec; what a helper unpacks is array-identical, CSR matrices included."""
+    import pickle
+
+    import numpy as np
+
+    from pysparselp_b200 import generators
+    from pysparselp_b200.multi_gpu import pack_lp, unpack_lp
+
+    lp, _ = generators.random_sparse_lp(300, 500, n_eq=40, seed=5)
+    args = dict(c=lp.c, a_eq=lp.a_eq, beq=lp.b_eq, a_ineq=lp.a_ineq, b_lower=lp.b_lower, b_upper=lp.b_upper, lb=lp.lb,
+                ub=lp.ub, x0=None)
+    spec, blocks = pack_lp(args)
+    try:
+        assert len(pickle.dumps(spec)) < 4096
+        got, keep = unpack_lp(pickle.loads(pickle.dumps(spec)))
+        for name in ("c", "beq", "b_upper", "lb", "ub"):
+            assert np.array_equal(got[name], np.ravel(args[name]))
+        assert got["b_lower"] is None and got["x0"] is None
+        for name in ("a_eq", "a_ineq"):
+            a, b = got[name], args[name]
+            assert a.shape == b.shape and np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices)
+            assert np.array_equal(a.data, b.data) and np.array_equal((a @ np.ones(a.shape[1])), (b @ np.ones(b.shape[1])))
+        del got, a, b
+        for shm in keep:
+            shm.close()
+    finally:
+        for shm in blocks:
+            shm.close()
+            shm.unlink()

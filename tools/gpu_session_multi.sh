@@ -36,4 +36,10 @@ if [ "$what" = all ] || [ "$what" = random ]; then
     > $out/${tag}_bench_random_n${n}.json 2> $out/${tag}_bench_random_n${n}.err
   echo "exit $?" | tee -a $out/${tag}_multi_n$n.log
 fi
+if [ "$what" = all ] || [ "$what" = ngpus ]; then
+  echo "== one process, $n GPUs (no torchrun): chambolle_pock_ppd(..., n_gpus=$n)" | tee -a $out/${tag}_multi_n$n.log
+  timeout 600 python tools/n_gpus_check.py $n > $out/${tag}_n_gpus_check_n$n.log 2>&1
+  echo "exit $?" | tee -a $out/${tag}_multi_n$n.log
+  grep "from one process\|regression\|N_GPUS_CHECK_OK" $out/${tag}_n_gpus_check_n$n.log | tee -a $out/${tag}_multi_n$n.log
+fi
 echo "== done" | tee -a $out/${tag}_multi_n$n.log

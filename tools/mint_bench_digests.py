@@ -37,6 +37,8 @@ def main():
         co.iterate(bench.DIGEST_ITERS)
         table[name] = {"sha256": bench.iterate_digest(co.x, co.y), "iterations": bench.DIGEST_ITERS, "n": int(co.n), "m": int(co.m),
                        "minted_by": "tools/mint_bench_digests.py: oracle/cpppd_oracle.c (OpenMP, %d threads)" % threads}
+        if kind == "l1svm":  # long weight columns: compared within 1e-9, not bit for bit
+            table[name]["fingerprint"] = bench.iterate_fingerprint(co.x, co.y)
         print(name, table[name]["sha256"], "%.1f s" % (time.time() - t0), flush=True)
         del co, lp
         with open(path, "w") as f:
