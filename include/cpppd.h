@@ -110,7 +110,11 @@ enum {
    * (k_tiny_iterate) instead of 2k graph nodes — such LPs are bound by launch latency, not bandwidth (SC105 on a B200:
    * 800 000 iterations/s against 189 000 through CUDA graphs).  Same per-row code, same bits.  This flag keeps the
    * graph path. */
-  CPPPD_FLAG_NO_TINY_PERSISTENT = 1u << 12
+  CPPPD_FLAG_NO_TINY_PERSISTENT = 1u << 12,
+  /* world_size > 1, patterns without locality (balanced split + banded operands): keep only the ghosts the pattern
+   * really touches and push them through index lists, instead of the dense halo (every foreign column / row is a
+   * ghost; one contiguous copy per peer).  For comparison runs. */
+  CPPPD_FLAG_NO_DENSE_HALO = 1u << 13
 };
 
 typedef struct {
@@ -217,6 +221,8 @@ typedef struct {
   float band_ms[2];             /* milliseconds per half-iteration measured at creation; 0 = not timed */
   float band_sectors_per_gather[2]; /* sampled locality of the operand: distinct 32-byte sectors per gather of a warp */
   int64_t band_window_bytes;    /* bytes of the gathered vector per window (largest window) */
+  int32_t dense_halo;           /* world_size > 1: ghosts = all foreign columns / rows, contiguous per-peer pushes */
+  int32_t reserved2;
   int32_t band_shape[2];        /* compiled shape of the window kernels in use (0-based, see band_shape_ms) */
   float band_shape_ms[2][8];    /* ms per half-iteration measured at creation for the shapes flat4/4cta, flat3/6cta,
                                    flat2/6cta, flat2/8cta (entries through registers: flat entries per lane and trip /

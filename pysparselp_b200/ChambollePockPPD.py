@@ -19,7 +19,8 @@ automatically; see ``cpppd_problem.kernel_variant`` — the iterates do not depe
 world when it has more than one rank — one process per GPU, every rank passes the same LP and
 gets the same result; False: this GPU only; or an explicit ProcessGroup), ``n_gpus`` (N > 1: this ONE process
 drives N GPUs of the node — helper processes are spawned for the other devices for the duration of the call, see
-``pysparselp_b200/multi_gpu.py``; ``device`` may then list the N ordinals).
+``pysparselp_b200/multi_gpu.py``; ``device`` may then list the N ordinals), ``y0`` (dual warm start
+``[y_eq; y_ineq]`` in the row order of the one-sided system; the reference always starts from zero).
 """
 import atexit
 import ctypes as C
@@ -554,6 +555,7 @@ def chambolle_pock_ppd(
     kernel_variant=0,
     long_row_threshold=0,
     n_gpus=None,
+    y0=None,
 ):
     """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
 
@@ -599,6 +601,14 @@ def chambolle_pock_ppd(
     solver = make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
                          device=device, flags=flags, distributed=distributed, partition_granule=partition_granule,
                          kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
+    if solver is not None and y0 is not None:
+        # dual warm start (extension: the reference always starts from y = 0, :166,:177).  y0 = [y_eq; y_ineq] in the
+        # row order of the ONE-SIDED system (finite uppers, then negated finite lowers, :74-88)
+        try:
+            solver.set_y(y0)
+        except BaseException:
+            solver.close()
+            raise
     if solver is None:  # no constraint row: closed form, bare vector (:147-151)
         x = np.zeros_like(lb)
         x[c > 0] = lb[c > 0]

@@ -29,6 +29,7 @@ FLAG_TINY_PERSISTENT = 1 << 9
 FLAG_BANDED = 1 << 10
 FLAG_NO_BANDED = 1 << 11
 FLAG_NO_TINY_PERSISTENT = 1 << 12
+FLAG_NO_DENSE_HALO = 1 << 13
 
 VEC_X, VEC_XBAR, VEC_Y, VEC_T, VEC_SIGMA, VEC_BEST_INTEGER, VEC_D = range(7)
 
@@ -81,13 +82,14 @@ class Info(C.Structure):
         ("balanced_split", C.c_int32), ("tiny_persistent", C.c_int32),
         ("band_windows", C.c_int32 * 2), ("band_in_use", C.c_int32 * 2), ("band_ms", C.c_float * 2),
         ("band_sectors_per_gather", C.c_float * 2), ("band_window_bytes", C.c_int64),
+        ("dense_halo", C.c_int32), ("reserved2", C.c_int32),
         ("band_shape", C.c_int32 * 2), ("band_shape_ms", (C.c_float * 8) * 2),
     ]
 
     def as_dict(self):
         arrays = ("band_windows", "band_in_use", "band_ms", "band_sectors_per_gather", "band_shape")
         out = {name: getattr(self, name) for name, _ in self._fields_
-               if name not in ("variant_ms", "band_shape_ms", "reserved") + arrays}
+               if name not in ("variant_ms", "band_shape_ms", "reserved", "reserved2") + arrays}
         out["band_shape_ms"] = [list(self.band_shape_ms[0]), list(self.band_shape_ms[1])]
         for name in arrays:  # [A (dual half), A^T (primal half)]
             out[name] = list(getattr(self, name))

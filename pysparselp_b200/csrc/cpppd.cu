@@ -482,6 +482,7 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
   for (int bit = 0; bit < 6; ++bit)
     if (!((h->const_mask >> bit) & 1)) vec_bytes += 8 * per_elem[bit];
   out->balanced_split = h->balanced_split ? 1 : 0;
+  out->dense_halo = h->dense_halo && h->world > 1 ? 1 : 0;
   out->tiny_persistent = h->tiny ? 1 : 0;
   out->long_rows = h->longA.count;
   out->long_cols = h->longAT.count;

@@ -490,6 +490,11 @@ int setup_p2p(cpppd_solver *h) {
         dst[H.send_off[t] + k] = base + k;
       }
     }
+    pp.dense[kind] = h->dense_halo && H.owned > 0;
+    for (int t = 0; t < N; ++t) {
+      pp.dense_dst[kind][t] = dst_base[kind][t];
+      if (t != me && H.send_count[t] != H.owned) pp.dense[kind] = false;
+    }
     if (int rc = alloc_array(h, &pp.push_peer[kind], H.send_total)) return rc;
     if (int rc = alloc_array(h, &pp.push_dst[kind], H.send_total)) return rc;
     if (H.send_total) {
@@ -512,7 +517,14 @@ int exchange_p2p(cpppd_solver *h, int kind) {
   P2P &pp = h->p2p;
   Halo &H = kind ? h->hy : h->hx;
   const double *vec = kind ? h->y : h->xbar;
-  if (H.send_total)
+  if (pp.dense[kind]) {
+    DenseDst D;
+    memcpy(D.base, pp.dense_dst[kind], sizeof D.base);
+    // (a few CTAs per SM: every thread streams its share of the owned entries to all peers)
+    const int grid = (int)std::min<int64_t>(grid_for(H.owned), (int64_t)h->sm_count * 16);
+    k_push_dense<<<grid, kBlock, 0, h->stream>>>(vec, H.owned, pp.ptrs[kind], D, kind, h->world, h->rank, pp.send_mask[kind],
+                                                 pp.state);
+  } else if (H.send_total)
     k_push<<<grid_for(H.send_total), kBlock, 0, h->stream>>>(vec, H.send_idx, pp.push_dst[kind], pp.push_peer[kind],
                                                             H.send_total, pp.ptrs[kind], kind, h->world, h->rank,
                                                             pp.send_mask[kind], pp.state);
@@ -780,7 +792,17 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = tmp.get(&grow_scan, m + 1)) return rc;
     CK(cudaMemsetAsync(gcol_flag, 0, sizeof(int32_t) * (n + 1), st));
     CK(cudaMemsetAsync(grow_flag, 0, sizeof(int32_t) * (m + 1), st));
-    if (nnz && N > 1) k_mark_ghosts<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, gcol_flag, grow_flag);
+    // Patterns without locality on several GPUs (balanced split in original order): a rank's rows touch nearly every
+    // column and its columns nearly every row (random LP, 8 GPUs: 86 % / 63 %).  Every foreign column / row is then
+    // kept as a ghost: the halo of a peer is the peer's whole slice in its own order — one contiguous, index-free
+    // copy per peer (k_push_dense) instead of an indexed push of almost the same bytes.
+    h->dense_halo = keep_order && !(h->flags & CPPPD_FLAG_NO_DENSE_HALO);
+    if (N > 1 && h->dense_halo) {
+      if (n) k_flag_outside<<<grid_for(n), kBlock, 0, st>>>(gcol_flag, n, cs, ce);
+      if (m) k_flag_outside<<<grid_for(m), kBlock, 0, st>>>(grow_flag, m, rs, re);
+    } else if (nnz && N > 1) {
+      k_mark_ghosts<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, gcol_flag, grow_flag);
+    }
     if (int rc = exclusive_scan(h, gcol_flag, gcol_scan, n + 1)) return rc;
     if (int rc = exclusive_scan(h, grow_flag, grow_scan, m + 1)) return rc;
     std::vector<int32_t> cb(N + 1), rb(N + 1);
@@ -830,8 +852,14 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
         starts.row[r] = row_start[r];
         starts.col[r] = col_start[r];
       }
-      if (nnz) k_mark_send_masks<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, starts, N,
-                                                                 sx_mask, sy_mask);
+      if (h->dense_halo) {
+        const unsigned long long peers = (N >= 64 ? ~0ull : ((1ull << N) - 1ull)) & ~(1ull << me);
+        if (nloc) k_fill_u64<<<grid_for(nloc), kBlock, 0, st>>>(sx_mask, nloc, peers);
+        if (mloc) k_fill_u64<<<grid_for(mloc), kBlock, 0, st>>>(sy_mask, mloc, peers);
+      } else if (nnz) {
+        k_mark_send_masks<<<grid_for(nnz), kBlock, 0, st>>>(indices, row_of, nnz, row_pos, col_pos, rs, re, cs, ce, starts, N,
+                                                           sx_mask, sy_mask);
+      }
       for (int t = 0; t < N; ++t) {
         if (t == me) continue;
         CK(cudaMemsetAsync(sx_flag + nloc, 0, sizeof(int32_t), st));

@@ -169,6 +169,15 @@ __global__ void k_mark_send_masks(const int32_t *__restrict__ indices, const uin
     if (!(sendy_mask[rp - rs] & bit)) atomicOr(sendy_mask + (rp - rs), bit);
   }
 }
+// dense halo: every position outside [lo, hi) is a ghost / every owned entry goes to every peer
+__global__ void k_flag_outside(int32_t *__restrict__ flag, int64_t count, int32_t lo, int32_t hi) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) flag[i] = (i < lo || i >= hi) ? 1 : 0;
+}
+__global__ void k_fill_u64(unsigned long long *__restrict__ p, int64_t count, unsigned long long v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) p[i] = v;
+}
 __global__ void k_flag_from_mask(const unsigned long long *__restrict__ mask, int64_t count, int peer, int32_t *__restrict__ flag) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) flag[i] = (int32_t)((mask[i] >> peer) & 1ull);

@@ -203,6 +203,33 @@ k_push(const double *__restrict__ vec, const int32_t *__restrict__ src, const in
     if ((send_mask >> t) & 1ull) st_release_sys(P.flags[t] + kind * world + me, stamp);
 }
 
+// Dense halo (patterns without locality: every peer needs every owned entry, and its ghost slots for this rank are
+// one contiguous run in this rank's order): no index lists, the owned part of the vector is streamed once and
+// stored to every peer, coalesced.  Same stamp protocol as k_push.
+struct DenseDst {
+  int64_t base[kMaxWorld];  // first ghost slot of this rank's entries in peer t's vector
+};
+__global__ void __launch_bounds__(kBlock)
+k_push_dense(const double *__restrict__ vec, int64_t owned, PeerPtrs P, DenseDst D, int kind, int world, int me,
+             unsigned long long send_mask, SyncState *st) {
+  for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < owned; k += (int64_t)gridDim.x * kBlock) {
+    const double v = vec[k];
+    for (int t = 0; t < world; ++t)
+      if ((send_mask >> t) & 1ull) P.vec[t][D.base[t] + k] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const unsigned int ticket = atomicAdd(&st->ticket[kind], 1u);
+  if (ticket != gridDim.x - 1) return;
+  __threadfence_system();
+  st->ticket[kind] = 0;
+  const unsigned long long stamp = st->push_stamp[kind] + 1;
+  st->push_stamp[kind] = stamp;
+  for (int t = 0; t < world; ++t)
+    if ((send_mask >> t) & 1ull) st_release_sys(P.flags[t] + kind * world + me, stamp);
+}
+
 // Wait until every neighbour this rank receives from has pushed its halo for this exchange.
 __global__ void k_wait(const unsigned long long *__restrict__ flags, int kind, int world,
                        unsigned long long recv_mask, SyncState *st) {

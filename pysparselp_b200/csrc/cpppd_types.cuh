@@ -93,6 +93,8 @@ struct P2P {
   int32_t *push_peer[2] = {nullptr, nullptr};
   int64_t *push_dst[2] = {nullptr, nullptr};
   unsigned long long send_mask[2] = {0, 0}, recv_mask[2] = {0, 0};
+  bool dense[2] = {false, false};        // every peer takes all owned entries, contiguously (k_push_dense)
+  int64_t dense_dst[2][kMaxWorld] = {};  // first ghost slot of this rank's entries in every peer's vector
   // halo exchange fused into k_primal ([0], produces xbar) and k_dual ([1], produces y)
   FusedComm *fused[2] = {nullptr, nullptr};
   bool use_fused = false;
@@ -160,6 +162,7 @@ struct cpppd_solver {
   bool identity_layout = true;  // local index == original index (one GPU, no reordering)
   bool tiny = false;            // iterations run in k_tiny_iterate (one persistent CTA)
   bool balanced_split = false;  // ownership by prefix sums instead of locality buckets (see setup())
+  bool dense_halo = false;      // patterns without locality: every rank keeps ghosts of ALL foreign columns / rows
   int32_t *col_old = nullptr;   // n + ghosts : original column id of a local column
   int32_t *row_old = nullptr;   // m + ghosts : original row id of a local row
   Halo hx, hy;                  // xbar-like vectors (columns) / y-like vectors (rows)

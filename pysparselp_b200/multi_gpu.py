@@ -57,13 +57,22 @@ def pack_lp(lp_args):
     return spec, blocks
 
 
-def unpack_lp(spec):
-    """Inverse of pack_lp in another process: arrays are views of the shared blocks (kept alive in the second result)."""
+def unpack_lp(spec, foreign=False):
+    """Inverse of pack_lp: arrays are views of the shared blocks (kept alive in the second result).  `foreign`: this
+    process did not create the blocks (a helper)."""
     keep = []
 
     def get(item):
         _, name, dtype, shape = item
         shm = shared_memory.SharedMemory(name=name)
+        if foreign:  # attaching registers the block with this process's resource tracker, which would unlink it (and
+            # warn about a leak) when this process exits; the block belongs to the process that created it
+            try:
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(shm._name, "shared_memory")
+            except Exception:
+                pass
         keep.append(shm)
         return np.ndarray(shape, dtype=np.dtype(dtype), buffer=shm.buf)
 
@@ -92,17 +101,31 @@ def _helper(rank, world, port, spec, solve_kw, devices):
     torch.cuda.set_device(devices[rank])
     dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
                             device_id=torch.device("cuda", devices[rank]))
-    lp, keep = unpack_lp(spec)
+    lp, keep = unpack_lp(spec, foreign=True)
     solve_kw = dict(solve_kw, save_problem=False, verbose=False)
     try:
         chambolle_pock_ppd(lp["c"], lp["a_eq"], lp["beq"], lp["a_ineq"], lp["b_lower"], lp["b_upper"], lp["lb"], lp["ub"],
                            x0=lp["x0"], callback_func=None, distributed=True, device=devices[rank], **solve_kw)
     finally:
-        dist.barrier()
-        dist.destroy_process_group()
+        _leave_group(dist)
         del lp
         for shm in keep:
             shm.close()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)  # (no interpreter teardown: nothing of this process is needed any more, and a communicator left to an
+    #               atexit hook would wait for peers that are not exiting)
+
+
+def _leave_group(dist):
+    """Every rank of the call destroys its NCCL communicator of libcpppd at the same point (ncclCommDestroy waits for
+    the peers), then the torch process group."""
+    from pysparselp_b200.ChambollePockPPD import _destroy_cached_comms
+
+    dist.barrier()
+    _destroy_cached_comms()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def solve_on_gpus(n_gpus, lp_args, solve_kw, callback_func=None, devices=None):
@@ -145,8 +168,7 @@ def solve_on_gpus(n_gpus, lp_args, solve_kw, callback_func=None, devices=None):
                                      x0=a.get("x0"), callback_func=callback_func, distributed=True, device=devices[0],
                                      **solve_kw)
         finally:
-            dist.barrier()
-            dist.destroy_process_group()
+            _leave_group(dist)
         for p in helpers:
             code = p.wait(timeout=120)
             if code != 0:

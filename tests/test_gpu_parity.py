@@ -362,3 +362,29 @@ def test_solve_curves_on_device_equal_host_curves():
             assert np.allclose(cd[k], ch[k], rtol=1e-13, atol=1e-15), k
         else:
             assert np.array_equal(cd[k], ch[k], equal_nan=True), k
+
+
+def test_dual_warm_start_y0():
+    """``y0=`` (extension; the reference always starts from y = 0, :166,:177): the solve continues from the given duals.
+    Checked against the numpy oracle stepped from the same state: x0, y0 given, xbar = x0 as the reference sets it."""
+    from oracle.cpppd_oracle import CpPpdOracle
+    from pysparselp_b200.ChambollePockPPD import chambolle_pock_ppd
+
+    args, g = case_args("random_small")
+    rng = np.random.default_rng(11)
+    m_eq, m_in = g["y_eq"].size, g["y_ineq"].size
+    x0 = rng.standard_normal(args[0].size)
+    y0 = np.concatenate((rng.standard_normal(m_eq), np.abs(rng.standard_normal(m_in))))
+    o = CpPpdOracle(*args, x0=x0)
+    o.y_eq, o.y_ineq = y0[:m_eq].copy(), y0[m_eq:].copy()
+    for _ in range(40):
+        o.primal_step()
+        o.dual_step()
+    x, best, solver = chambolle_pock_ppd(*args, x0=x0, y0=y0, nb_max_iter=40, nb_iter_plot=1000, return_solver=True)
+    try:
+        y = solver.get_y()
+    finally:
+        solver.close()
+    assert np.array_equal(x, o.x) and np.array_equal(y, np.concatenate((o.y_eq, o.y_ineq)))
+    with pytest.raises(ValueError):
+        chambolle_pock_ppd(*args, y0=y0[:-1], nb_max_iter=1)

@@ -186,7 +186,7 @@ def test_multi_rank_balanced_split_for_patterns_without_locality(world):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("transport", ["push_wait_kernels", "nccl"])
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("name", ["random_small", "sc105", "kb2"])
 def test_multi_rank_banded_operands(name, world, transport, monkeypatch):
     """Banded operands (csrc/cpppd_banded.cuh) on several ranks: patterns without locality take the balanced split, rows
@@ -213,6 +213,13 @@ def test_multi_rank_banded_operands(name, world, transport, monkeypatch):
         if part["balanced_split"]:
             assert r["info"]["balanced_split"] == 1 and r["info"]["band_in_use"] == [1, 1]
             assert np.all(np.diff(own_c) > 0)  # original order inside the rank
+            # dense halo: every foreign column / row is a ghost, peer by peer, each peer's slice in its own order
+            assert r["info"]["dense_halo"] == 1
+            others = [q for q in range(world) if q != rank]
+            assert np.array_equal(ghost_c, np.concatenate(
+                [part["col_order"][part["col_start"][q]: part["col_start"][q + 1]] for q in others]))
+            assert np.array_equal(ghost_r, np.concatenate(
+                [part["row_order"][part["row_start"][q]: part["row_start"][q + 1]] for q in others]))
             banded += 1
         else:  # locality buckets: the banded form is not built
             assert r["info"]["band_in_use"] == [0, 0]
@@ -244,3 +251,15 @@ def test_distributed_vector_assembly_keeps_the_sign_of_zero():
     for x, y in run_ranks(3, body):
         assert np.array_equal(x, xs) and np.array_equal(np.signbit(x), np.signbit(xs))
         assert np.array_equal(y, ys) and np.array_equal(np.signbit(y), np.signbit(ys))
+
+
+@pytest.mark.timeout(900)
+def test_multi_rank_sparse_halo_of_banded_operands(monkeypatch):
+    """CPPPD_FLAG_NO_DENSE_HALO: banded operands with the index-list halo (only the ghosts the pattern touches)."""
+    monkeypatch.setenv("CPPPD_BAND_WINDOW", "9")
+    args, g = case_args("random_small")
+    res = solve_on_ranks(args, 3, _cabi.FLAG_BANDED | _cabi.FLAG_NO_DENSE_HALO, 100, 10)
+    y_gold = np.concatenate([g["y_eq"], g["y_ineq"]])
+    for r in res:
+        assert r["info"]["dense_halo"] == 0 and r["info"]["band_in_use"] == [1, 1]
+        assert np.array_equal(r["x"], g["x_100"]) and np.array_equal(r["y"], y_gold)
