@@ -23,6 +23,10 @@ done
 timeout 900 python bench.py --workload l1svm --size 100000 --steps 4 --iters-per-step 10 --e2e-steps 1 --e2e-iters 50 --no-cpu-baseline --small-configs 0 \
   > $out/${tag}_bench_l1svm.json 2> $out/${tag}_bench_l1svm.err
 echo "bench l1svm exit $?" | tee -a $log
+echo "== 3b. compressed storage (flags 3 / 11) on the Potts LP: every kernel variant" | tee -a $log
+for f in 3 11; do for v in 1 2 3 4 5 6 7; do
+  timeout 300 python tools/quick_bench.py --size 4096 --iters 100 --reps 3 --variant $v --flags $f >> $out/${tag}_variants.jsonl 2>> $out/${tag}_variants.err
+done; done
 echo "== 4. ncu launch list of the default bench command (headline only)" | tee -a $log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
   python bench.py --steps 1 --warmup 3 --iters-per-step 10 --e2e-steps 0 --variants 0 --no-cpu-baseline --small-configs 0 --secondary '' > $out/${tag}_ncu_bench.log 2>&1
