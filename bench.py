@@ -731,7 +731,7 @@ def small_configs(a, generators, make_solver):
 
 
 VARIANT_NAMES = ("loop-unroll4/8cta", "chunk2/8cta", "chunk4/6cta", "chunk4/4cta", "chunk8/4cta", "rows2-chunk4/3cta",
-                 "rows2-chunk2/4cta")
+                 "rows2-chunk2/4cta", "stride-chunk2/8cta", "stride-chunk4/6cta")
 
 
 def kernel_variants(info):

@@ -49,7 +49,7 @@ extern "C" {
 
 #define CPPPD_ABI_VERSION 7
 
-#define CPPPD_KERNEL_VARIANTS 7
+#define CPPPD_KERNEL_VARIANTS 9
 
 typedef struct cpppd_solver *cpppd_handle;
 

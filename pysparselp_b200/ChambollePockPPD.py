@@ -33,6 +33,8 @@ from . import _cabi
 
 # (process group, device) -> cpppd_comm, kept for the life of the process
 _COMM_CACHE = {}
+# device ordinal -> the torch stream solvers use when the caller is on the legacy default stream
+_SOLVER_STREAMS = {}
 
 
 def _destroy_cached_comms():
@@ -311,7 +313,11 @@ class CpPpdSolver(SolverHandle):
         # for the work already queued on the default stream.
         current = torch.cuda.current_stream(dev)
         if current.cuda_stream == 0:
-            self._stream = torch.cuda.Stream(dev)
+            # one such stream per device and process: torch's caching allocator pools blocks per stream, so a fresh
+            # stream per solve could not reuse what the previous solve freed (gigabytes of cudaMalloc per call)
+            if dev.index not in _SOLVER_STREAMS:
+                _SOLVER_STREAMS[dev.index] = torch.cuda.Stream(dev)
+            self._stream = _SOLVER_STREAMS[dev.index]
             self._stream.wait_stream(current)
         else:
             self._stream = current

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcpppd.so")
 
 ABI_VERSION = 7
-KERNEL_VARIANTS = 7
+KERNEL_VARIANTS = 9
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 FREE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)

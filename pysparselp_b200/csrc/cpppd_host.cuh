@@ -1219,7 +1219,9 @@ int launch_primal(cpppd_solver *h, bool write_d, int variant = -1) {
     const int v = cm ? 0 : (variant >= 0 ? variant : h->primal_variant);
     PrimalFn fn = cm ? primal_kernel_fused(write_d, dict) : primal_kernel(write_d, dict, v);
     const int64_t warps = (h->AT.nslices + kVariants[v].rows - 1) / kVariants[v].rows;  // a warp walks `rows` slices
-    fn<<<grid_for(warps * 32), kBlock, 0, h->stream>>>(view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar,
+    int grid = grid_for(warps * 32);
+    if (!cm && kVariants[v].persist) grid = std::min(grid, h->sm_count * kVariants[v].persist);
+    fn<<<grid, kBlock, 0, h->stream>>>(view(h->AT), h->y, h->vc, h->vT, h->vlb, h->vub, h->x, h->xbar,
                                                               h->dbuf, h->n, has_eq, has_ineq, h->theta, h->one_plus_theta, cm);
   }
   if (cm || variant >= 0) return 0;
@@ -1240,7 +1242,9 @@ int launch_dual(cpppd_solver *h, int variant = -1) {
     const int v = cm ? 0 : (variant >= 0 ? variant : h->dual_variant);
     DualFn fn = cm ? dual_kernel_fused(dict) : dual_kernel(dict, v);
     const int64_t warps = (h->A.nslices + kVariants[v].rows - 1) / kVariants[v].rows;
-    fn<<<grid_for(warps * 32), kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
+    int grid = grid_for(warps * 32);
+    if (!cm && kVariants[v].persist) grid = std::min(grid, h->sm_count * kVariants[v].persist);
+    fn<<<grid, kBlock, 0, h->stream>>>(view(h->A), h->xbar, h->vb, h->vsigma, h->y, h->m, h->m_eq, cm);
   }
   if (cm || variant >= 0) return 0;
   return pp.active ? exchange_p2p(h, 1) : exchange(h, h->y, h->hy);

@@ -436,7 +436,9 @@ __device__ __forceinline__ void primal_rows(const SellView &AT, const double *__
 // kDict: entries are single 32-bit words [pad][eq][code][index]; values come from a <= 256 entry
 // dictionary staged in shared memory.
 // kComm: the halo exchange is done by the kernel itself (see FusedComm); cm is not touched otherwise.
-template <bool kWriteD, bool kDict, int kChunk, int kMinB, bool kComm, int kRows = 1>
+// kPersist: the grid is a few CTAs per SM and every warp strides over the slices (no CTA churn: with two or three
+// entries per row a CTA of the one-slice-per-warp grid lives for a microsecond or two)
+template <bool kWriteD, bool kDict, int kChunk, int kMinB, bool kComm, int kRows = 1, bool kPersist = false>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub, double *__restrict__ x,
          double *__restrict__ xbar, double *__restrict__ d_out, int64_t n, int has_eq, int has_ineq,
@@ -451,6 +453,10 @@ k_primal(SellView AT, const double *__restrict__ y, Vec c, Vec T, Vec lb, Vec ub
   if constexpr (kRows == 2) {  // warp s takes slices 2s and 2s + 1 (the grid covers half as many warps)
     primal_rows2<kWriteD, kDict, kChunk>(AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta, one_plus_theta,
                                          sdict, s);
+  } else if constexpr (kPersist) {
+    for (int64_t jj = j; (jj >> 5) < AT.nslices; jj += (int64_t)gridDim.x * kBlock)
+      primal_rows<kWriteD, kDict, kChunk, false, false, LoadStream>(AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta,
+                                                                    one_plus_theta, cm, sdict, jj, jj >> 5);
   } else if (s < AT.nslices)
     primal_rows<kWriteD, kDict, kChunk, (kChunk > 0 && kMinB <= 6), kComm, typename std::conditional<kComm, LoadPeer, LoadStream>::type>(
         AT, y, c, T, lb, ub, x, xbar, d_out, n, has_eq, has_ineq, theta, one_plus_theta, cm, sdict, j, s);
@@ -487,7 +493,7 @@ __device__ __forceinline__ void dual_rows(const SellView &A, const double *__res
 }
 
 // Dual half-iteration (:231-240, :333-341).  Thread i owns row i of A.
-template <bool kDict, int kChunk, int kMinB, bool kComm, int kRows = 1>
+template <bool kDict, int kChunk, int kMinB, bool kComm, int kRows = 1, bool kPersist = false>
 __global__ void __launch_bounds__(kBlock, kMinB)
 k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__restrict__ y, int64_t m,
        int64_t m_eq, const FusedComm *__restrict__ cm) {
@@ -500,6 +506,9 @@ k_dual(SellView A, const double *__restrict__ xbar, Vec b, Vec sigma, double *__
   const int64_t s = i >> 5;
   if constexpr (kRows == 2) {
     dual_rows2<kDict, kChunk>(A, xbar, b, sigma, y, m, m_eq, sdict, s);
+  } else if constexpr (kPersist) {
+    for (int64_t ii = i; (ii >> 5) < A.nslices; ii += (int64_t)gridDim.x * kBlock)
+      dual_rows<kDict, kChunk, false, LoadStream>(A, xbar, b, sigma, y, m, m_eq, cm, sdict, ii, ii >> 5);
   } else if (s < A.nslices)
     dual_rows<kDict, kChunk, kComm, typename std::conditional<kComm, LoadPeer, LoadStream>::type>(A, xbar, b, sigma, y, m, m_eq, cm,
                                                                                                sdict, i, s);
@@ -540,12 +549,14 @@ k_tiny_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, Vec
 struct HotVariant {
   int chunk, min_blocks, rows;  // rows: slices (rows per lane) a warp walks in lock step; the grid shrinks accordingly
   const char *name;
+  int persist;                  // > 0: grid of sm_count * persist CTAs, warps stride over the slices
 };
 // index 0 is the variant every other one is measured against (and the one used without tuning)
-constexpr int kNumVariants = 7;
+constexpr int kNumVariants = 9;
 constexpr HotVariant kVariants[kNumVariants] = {
-    {0, 8, 1, "loop-unroll4/8cta"}, {2, 8, 1, "chunk2/8cta"},        {4, 6, 1, "chunk4/6cta"},       {4, 4, 1, "chunk4/4cta"},
-    {8, 4, 1, "chunk8/4cta"},       {4, 3, 2, "rows2-chunk4/3cta"}, {2, 4, 2, "rows2-chunk2/4cta"}};
+    {0, 8, 1, "loop-unroll4/8cta", 0}, {2, 8, 1, "chunk2/8cta", 0},        {4, 6, 1, "chunk4/6cta", 0},
+    {4, 4, 1, "chunk4/4cta", 0},       {8, 4, 1, "chunk8/4cta", 0},        {4, 3, 2, "rows2-chunk4/3cta", 0},
+    {2, 4, 2, "rows2-chunk2/4cta", 0}, {2, 8, 1, "stride-chunk2/8cta", 8}, {4, 6, 1, "stride-chunk4/6cta", 6}};
 
 using PrimalFn = void (*)(SellView, const double *, Vec, Vec, Vec, Vec, double *, double *, double *, int64_t, int, int,
                           double, double, const FusedComm *);
@@ -560,6 +571,8 @@ PrimalFn primal_variant(int v) {
     case 4: return k_primal<kWriteD, kDict, 8, 4, false>;
     case 5: return k_primal<kWriteD, kDict, 4, 3, false, 2>;
     case 6: return k_primal<kWriteD, kDict, 2, 4, false, 2>;
+    case 7: return k_primal<kWriteD, kDict, 2, 8, false, 1, true>;
+    case 8: return k_primal<kWriteD, kDict, 4, 6, false, 1, true>;
     default: return k_primal<kWriteD, kDict, 0, 8, false>;
   }
 }
@@ -572,6 +585,8 @@ DualFn dual_variant(int v) {
     case 4: return k_dual<kDict, 8, 4, false>;
     case 5: return k_dual<kDict, 4, 3, false, 2>;
     case 6: return k_dual<kDict, 2, 4, false, 2>;
+    case 7: return k_dual<kDict, 2, 8, false, 1, true>;
+    case 8: return k_dual<kDict, 4, 6, false, 1, true>;
     default: return k_dual<kDict, 0, 8, false>;
   }
 }

@@ -104,7 +104,7 @@ k_long_copy(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indi
 
 // One CTA per segment: partial[2 s] / partial[2 s + 1] = equality / other part of sum_k a_k * vec[idx_k] over the
 // segment (vec == nullptr: sum_k |a_k|^power, the preconditioner sums).  Thread t takes entries t, t + 256, ...
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 k_long_partial(const int64_t *__restrict__ ptr, const int64_t *__restrict__ seg_ptr, const int32_t *__restrict__ seg_row,
                const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ vec,
                double power, double *__restrict__ partial) {
@@ -113,11 +113,28 @@ k_long_partial(const int64_t *__restrict__ ptr, const int64_t *__restrict__ seg_
   const int64_t e0 = ptr[r] + (s - seg_ptr[r]) * kLongSeg;
   const int64_t e1 = min(e0 + (int64_t)kLongSeg, ptr[r + 1]);
   double v[2] = {0.0, 0.0};
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += kBlock) {
-    const int32_t w = __ldcs(idx + e);
-    const double a = __ldcs(val + e);
-    const double t = vec ? __dmul_rn(a, __ldg(vec + (w & kIdxMask))) : abs_pow(a, power);
-    if (w & kEqBit) v[0] = __dadd_rn(v[0], t); else v[1] = __dadd_rn(v[1], t);
+  // kLongUnroll entries of the thread at a time: all index / value loads, then all gathers, then the additions in
+  // the thread's entry order (the same fixed tree as a one-at-a-time loop, with six loads in flight instead of one:
+  // ncu had this kernel at 39 % of the DRAM bandwidth on the L1-SVM weight columns, bound by load latency)
+  constexpr int kLongUnroll = 6;
+#pragma unroll 1
+  for (int64_t base = e0 + threadIdx.x; base < e1; base += (int64_t)kBlock * kLongUnroll) {
+    int32_t w[kLongUnroll];
+    double a[kLongUnroll], g[kLongUnroll];
+#pragma unroll
+    for (int u = 0; u < kLongUnroll; ++u) {
+      const int64_t e = base + (int64_t)u * kBlock;
+      w[u] = e < e1 ? __ldcs(idx + e) : 0;
+      a[u] = e < e1 ? __ldcs(val + e) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kLongUnroll; ++u) g[u] = (vec && base + (int64_t)u * kBlock < e1) ? __ldg(vec + (w[u] & kIdxMask)) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kLongUnroll; ++u) {
+      if (base + (int64_t)u * kBlock >= e1) break;
+      const double t = vec ? __dmul_rn(a[u], g[u]) : abs_pow(a[u], power);
+      if (w[u] & kEqBit) v[0] = __dadd_rn(v[0], t); else v[1] = __dadd_rn(v[1], t);
+    }
   }
   block_reduce_write<2>(v, 0u, partial + 2 * s);
 }

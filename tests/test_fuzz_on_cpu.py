@@ -116,7 +116,7 @@ def assert_traces(got, want, rel):
 def test_random_lp_one_rank(seed):
     args, x0, theta, rng = random_lp(seed)
     flags = int(rng.choice(FLAG_CHOICES))
-    variant = int(rng.choice([0, 0, 1, 2, 3, 4, 5, 6, 7, 6, 7, 2 | (5 << 8), 7 | (6 << 8)]))
+    variant = int(rng.choice([0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 6, 7, 2 | (5 << 8), 7 | (6 << 8), 9 | (8 << 8)]))
     threshold = int(rng.choice([0, 0, 0, 2, 5, -1]))
     force_integer = bool(rng.random() < 0.4)
     plot = int(rng.choice([1, 4, 10, 1000]))
@@ -162,7 +162,7 @@ def test_random_lp_on_two_or_three_ranks(seed):
     plot = int(rng.choice([1, 7, 1000]))
     iters = int(rng.integers(1, 40))
     granule = int(rng.choice([0, 32, 64]))
-    variant = int(rng.choice([0, 0, 3, 6, 7]))
+    variant = int(rng.choice([0, 0, 3, 6, 7, 8]))
     xo, best_o, trace_o = run_oracle(args, x0=x0, theta=theta, nb_max_iter=iters, nb_iter_plot=plot,
                                      force_integer=force_integer)
 

@@ -13,7 +13,7 @@ def gold_y(g):
     return np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
 
 
-@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 6, 7, 2 | (4 << 8), 6 | (3 << 8)])
+@pytest.mark.parametrize("kernel_variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 2 | (4 << 8), 6 | (3 << 8), 8 | (9 << 8)])
 @pytest.mark.parametrize("compressed", [False, True])
 def test_every_kernel_variant_gives_the_same_bits(kernel_variant, compressed):
     from pysparselp_b200 import _cabi
@@ -46,7 +46,7 @@ def test_variants_on_a_mid_size_lp_with_ragged_rows():
     for args in cases:
         with np.errstate(invalid="ignore"):
             xo, _ = chambolle_pock_ppd_oracle(*args, nb_max_iter=30, nb_iter_plot=1000)
-        for v in range(1, 8):
+        for v in range(1, 10):
             x, _ = chambolle_pock_ppd(*args, nb_max_iter=30, nb_iter_plot=1000, kernel_variant=v)
             assert np.array_equal(x, xo), v
 

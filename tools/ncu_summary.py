@@ -23,6 +23,9 @@ VARIANTS = {(0, 8, 1): "loop-unroll4/8cta", (2, 8, 1): "chunk2/8cta", (4, 6, 1):
             (8, 4, 1): "chunk8/4cta", (4, 3, 2): "rows2-chunk4/3cta", (2, 4, 2): "rows2-chunk2/4cta"}
 
 
+STRIDE = {(2, 8, 1): "stride-chunk2/8cta", (4, 6, 1): "stride-chunk4/6cta"}
+
+
 def short(name):
     """k_primal<kWriteD, kDict, kChunk, kMinB, kComm, kRows> / k_dual<kDict, kChunk, kMinB, kComm, kRows> ->
     'k_primal[chunk2/8cta]' (+ ',dict' / ',write_d' / ',fused-halo'): the key bench.py looks its traffic up with."""
@@ -32,11 +35,12 @@ def short(name):
     if m:
         t = [int(v.replace("(bool)", "").replace("(int)", "")) for v in m.group(2).split(",")]
         if m.group(1) == "k_primal":
-            write_d, dict_, chunk, minb, comm, rows = (t + [1])[:6]
+            write_d, dict_, chunk, minb, comm, rows, persist = (t + [1, 0])[:7] if len(t) >= 6 else (t + [1, 0])[:7]
         else:
             write_d = 0
-            dict_, chunk, minb, comm, rows = (t + [1])[:5]
-        tags = [VARIANTS.get((chunk, minb, rows), "chunk%d/%dcta/rows%d" % (chunk, minb, rows))]
+            dict_, chunk, minb, comm, rows, persist = (t + [1, 0])[:6] if len(t) >= 5 else (t + [1, 0])[:6]
+        table = STRIDE if persist else VARIANTS
+        tags = [table.get((chunk, minb, rows), "chunk%d/%dcta/rows%d" % (chunk, minb, rows))]
         tags += ["dict"] * bool(dict_) + ["write_d"] * bool(write_d) + ["fused-halo"] * bool(comm)
         return "%s[%s]" % (m.group(1), ",".join(tags))
     m = re.search(r"(k_primal_band|k_dual_band)<([^>]*)>", name)
