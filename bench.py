@@ -574,7 +574,7 @@ def run_b200(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         with_stats = {"iterations_per_s": blocks * interval / dt, "nb_iter_plot": interval, "iterations": blocks * interval,
-                      "note": "device-resident, wall clock around %d stats intervals (stats block + 96-byte read-back each)" % blocks}
+                      "note": "device-resident, wall clock around %d stats intervals (stats block + 128-byte read-back each)" % blocks}
     except Exception as e:
         if world > 1:
             raise

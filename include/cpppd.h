@@ -181,6 +181,11 @@ typedef struct {
   double max_bound_violation;          /* max(max(lb - x), max(x - ub))                       */
   double distance_to_ground_truth;     /* mean |gt - x[idx]|        (cpppd_set_ground_truth)  */
   double distance_to_ground_truth_rounded; /* mean |gt - round(x[idx])|                       */
+  /* the two row maxima of max_constraint_violation for the caller's FULL LP when variables were eliminated
+   * before the solve (cpppd_set_row_offsets); equal to max_violated_equality_rounded / max_violated_inequality
+   * without offsets */
+  double max_violated_equality_full;   /* max |A_eq xr - b_eq - off|                          */
+  double max_violated_inequality_full; /* max (A_ineq xr - b_ineq - off)                      */
   int32_t feasible;                    /* exact test of :284                                   */
   int32_t improved;                    /* xr became the best integer solution at this block   */
   int32_t have_best_integer;           /* a best integer solution exists                       */
@@ -292,6 +297,11 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out);
 /* Ground truth for the distance curves of the stats block: values[k] is compared with x[indices[k]]
  * (original column ids).  count = 0 removes it.  With world_size > 1 every rank passes the full list. */
 int cpppd_set_ground_truth(cpppd_handle h, const int32_t *indices, const double *values, int64_t count);
+/* Per-row constants subtracted from the residuals A xr - b in the two *_full maxima of the stats block (m values,
+ * original row order; NULL removes them).  SparseLP.solve() eliminates fixed variables before the solve (reference
+ * SparseLP.py:632-674) and evaluates max_constraint_violation on the FULL LP at the mapped-back point (:1064-1093,
+ * :186-204): the full residual of a row is the reduced one minus a constant, so x can stay on the device. */
+int cpppd_set_row_offsets(cpppd_handle h, const double *offsets);
 /* Partition of this rank: number of owned and ghost columns (columns != 0) or rows (columns == 0)
  * and, when ids is not NULL, their original indices in local order (owned first, then ghosts in
  * exchange order).  A pure function of (indptr, indices, m_eq, world_size, granule):

@@ -247,6 +247,14 @@ class SolverHandle:
             raise ValueError("ground truth indices and values differ in size")
         self._call(self.lib.cpppd_set_ground_truth, idx.ctypes.data, val.ctypes.data, idx.size)
 
+    def set_row_offsets(self, offsets):
+        """Per-row constants of the full-LP residuals (see ``cpppd_set_row_offsets``); None removes them."""
+        if offsets is None:
+            self._call(self.lib.cpppd_set_row_offsets, None)
+            return
+        v = _as_f64(offsets, self.m, "row offsets")
+        self._call(self.lib.cpppd_set_row_offsets, v.ctypes.data)
+
     def set_x(self, v):
         self._set(_cabi.VEC_X, v, self.n)
 

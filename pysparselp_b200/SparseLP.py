@@ -426,6 +426,46 @@ class SparseLP:
         self.lower_bounds.fill(-np.inf)
         self.upper_bounds.fill(np.inf)
 
+    def _fixed_variable_curve_terms(self, reduced, shift, ground_truth, ground_truth_indices):
+        """What the eliminated variables contribute to the per-callback curves of ``solve`` (reference :1064-1093)
+        when x stays on the device.  The curves are evaluated on the FULL LP at ``x_full = m_change x - shift``
+        (the reference's sign, :1259): an eliminated entry of ``x_full`` is the constant ``-shift``.
+
+        * bounds (:188-189): ``max(lb - x_full, x_full - ub)`` over the eliminated entries — a constant;
+        * rows (:190-197): with ``A_full x_full = A_free x - A shift`` and the reduced right-hand sides
+          ``b' = b - A shift`` (:646-656), the full residual of a row is the reduced one minus ``2 (A shift)_i`` —
+          a per-row constant, in the row order of the one-sided system the solver builds
+          (finite uppers, then negated finite lowers: ``+2 (A shift)`` / ``-2 (A shift)``);
+        * ground truth (:1074-1082): eliminated entries contribute constant terms to the two sums.
+        """
+        free = self.upper_bounds > self.lower_bounds
+        x_fixed = -shift[~free]
+        out = {"bound_violation": max(float(np.max(self.lower_bounds[~free] - x_fixed)),
+                                      float(np.max(x_fixed - self.upper_bounds[~free])))}
+        offs = []
+        if self.nb_equality_constraints() > 0:
+            offs.append(2.0 * (self.a_equalities * shift))
+        if self.nb_inequality_constraints() > 0:
+            moved = 2.0 * (self.a_inequalities * shift)
+            if reduced.b_lower is None:
+                offs.append(moved)
+            else:
+                up = np.flatnonzero(np.asarray(reduced.b_upper) != np.inf)
+                lo = np.flatnonzero(np.asarray(reduced.b_lower) != -np.inf)
+                offs.append(np.concatenate((moved[up], -moved[lo])))
+        out["row_offsets"] = np.concatenate(offs) if offs else np.zeros(0)
+        if ground_truth is not None:
+            gt = np.asarray(ground_truth, dtype=np.float64).ravel()
+            idx = np.asarray(ground_truth_indices).ravel()
+            reduced_id = np.cumsum(free) - 1
+            is_free = free[idx]
+            out["gt_free_reduced_ids"] = reduced_id[idx[is_free]].astype(np.int32)
+            out["gt_free_values"] = gt[is_free]
+            xf = -shift[idx[~is_free]]
+            out["gt_fixed_sum"] = float(np.sum(np.abs(gt[~is_free] - xf)))
+            out["gt_fixed_sum_rounded"] = float(np.sum(np.abs(gt[~is_free] - np.round(xf))))
+        return out
+
     # -- solve ------------------------------------------------------------------------------------
     def solve(
         self,
@@ -504,16 +544,20 @@ class SparseLP:
         solver_args = (reduced.costsvector, reduced.a_equalities, reduced.b_equalities, reduced.a_inequalities,
                        reduced.b_lower, reduced.b_upper, reduced.lower_bounds, reduced.upper_bounds)
         want_device_curves = solver_options.pop("device_curves", True)
-        device_curves = want_device_curves and plot_solution is None and reduced.nb_variables == self.nb_variables
+        device_curves = want_device_curves and plot_solution is None
         if int(solver_options.get("n_gpus") or 1) > 1:
             # several GPUs from this one process (pysparselp_b200/multi_gpu.py): the solver state lives in helper
             # processes too, so the curves come through the callback, evaluated on the host like the reference does
             device_curves = False
+        fixed = None
+        if device_curves and reduced.nb_variables != self.nb_variables:
+            fixed = self._fixed_variable_curve_terms(reduced, shift, ground_truth, ground_truth_indices)
         if device_curves:
-            # No variable was eliminated (x_full == x) and nobody asked to see x: every per-callback curve
-            # of the reference (:1074-1091) is evaluated on the device inside the stats block and x never
-            # leaves the GPU before the end.  Values equal the host path up to the summation order of the
-            # two distance means.
+            # Nobody asked to see x: every per-callback curve of the reference (:1074-1091) is evaluated on the
+            # device inside the stats block and x never leaves the GPU before the end.  Values equal the host path
+            # up to the summation order of the two distance means.  When variables were eliminated (:632-674) the
+            # curves are those of the FULL LP at the mapped-back point m_change * x - shift: the eliminated entries
+            # contribute constants (bounds, ground truth) and shift every row residual by a constant (`fixed`).
             solve_kw = {k: solver_options[k] for k in ("device", "flags", "distributed", "partition_granule", "kernel_variant",
                                                           "long_row_threshold")
                         if k in solver_options}
@@ -523,13 +567,25 @@ class SparseLP:
                 device_curves = False
             else:
                 try:
-                    if ground_truth is not None:
+                    gt_total = 0 if ground_truth is None else np.size(ground_truth)
+                    if ground_truth is not None and fixed is None:
                         solver.set_ground_truth(ground_truth_indices, ground_truth)
+                    elif ground_truth is not None and fixed["gt_free_values"].size:
+                        solver.set_ground_truth(fixed["gt_free_reduced_ids"], fixed["gt_free_values"])
+                    if fixed is not None:
+                        solver.set_row_offsets(fixed["row_offsets"])
 
                     def record_stats(niter, st, duration):
-                        if ground_truth is not None:
+                        if ground_truth is not None and fixed is None:
                             self.distance_to_ground_truth.append(st["distance_to_ground_truth"])
                             self.distanceToGroundTruthAfterRounding.append(st["distance_to_ground_truth_rounded"])
+                        elif ground_truth is not None:
+                            # the device means run over the free entries only: back to sums, add the constants
+                            nfree = fixed["gt_free_values"].size
+                            self.distance_to_ground_truth.append(
+                                (st["distance_to_ground_truth"] * nfree + fixed["gt_fixed_sum"]) / gt_total)
+                            self.distanceToGroundTruthAfterRounding.append(
+                                (st["distance_to_ground_truth_rounded"] * nfree + fixed["gt_fixed_sum_rounded"]) / gt_total)
                         self.itrn_curve.append(niter)
                         self.opttime_curve.append(duration)
                         self.dopttime_curve.append(duration)
@@ -537,10 +593,12 @@ class SparseLP:
                         self.pobj_curve.append(st["energy1"])
                         # max_constraint_violation (:186-204) from the device maxima, folded in its order
                         worst = max(0, st["max_bound_violation"])
+                        if fixed is not None:
+                            worst = max(worst, fixed["bound_violation"])
                         if self.nb_equality_constraints() > 0:
-                            worst = max(worst, st["max_violated_equality_rounded"])
+                            worst = max(worst, st["max_violated_equality_full"])
                         if self.nb_inequality_constraints() > 0:
-                            worst = max(worst, st["max_violated_inequality"])
+                            worst = max(worst, st["max_violated_inequality_full"])
                         self.max_violated_constraint.append(worst)
                         self.max_violated_equality.append(st["max_violated_equality"])
                         self.max_violated_inequality.append(st["max_violated_inequality"])

@@ -58,6 +58,7 @@ class Stats(C.Structure):
         ("best_integer_energy", C.c_double), ("frac_zero_xbar", C.c_double),
         ("max_bound_violation", C.c_double), ("distance_to_ground_truth", C.c_double),
         ("distance_to_ground_truth_rounded", C.c_double),
+        ("max_violated_equality_full", C.c_double), ("max_violated_inequality_full", C.c_double),
         ("feasible", C.c_int32), ("improved", C.c_int32), ("have_best_integer", C.c_int32),
         ("reserved", C.c_int32),
     ]
@@ -118,6 +119,7 @@ SYMBOLS = {
     "cpppd_set_vector": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "cpppd_get_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "cpppd_set_ground_truth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "cpppd_set_row_offsets": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cpppd_get_layout": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_void_p]),
     "cpppd_iteration_count": (C.c_int64, [C.c_void_p]),
 }

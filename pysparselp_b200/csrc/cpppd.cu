@@ -287,7 +287,7 @@ int cpppd_stats_step(cpppd_handle h, int32_t force_integer) {
   if (force_integer)
     if (int rc = long_pass(h, h->longA, xr, xr)) return rc;
   k_stats_rows<<<h->stat_blocks_r, kBlock, 0, h->stream>>>(view(h->A), h->x, h->dbuf, h->xbar, xr, h->vb, h->y, h->m,
-                                                          h->m_eq, force_integer, h->rowpart);
+                                                          h->m_eq, force_integer, h->row_off, h->rowpart);
   if (h->gt_local)
     k_stats_gt<<<h->stat_blocks_g, kBlock, 0, h->stream>>>(h->gt_idx, h->gt_val, h->gt_local, h->x, h->gtpart);
   k_stats_local<<<1, kBlock, 0, h->stream>>>(h->colpart, h->stat_blocks_c, h->rowpart, h->stat_blocks_r, h->gtpart,
@@ -442,6 +442,21 @@ int cpppd_set_ground_truth(cpppd_handle h, const int32_t *indices, const double 
     CK(cudaMemcpyAsync(h->gt_val, val.data(), sizeof(double) * val.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
+  return 0;
+}
+
+int cpppd_set_row_offsets(cpppd_handle h, const double *offsets) {
+  CHECK_HANDLE(h);
+  if (!offsets) {
+    h->row_off = nullptr;  // (the buffer, if any, stays allocated until the handle is destroyed)
+    return 0;
+  }
+  double *buf = nullptr;
+  if (int rc = alloc_array(h, &buf, h->m)) return rc;
+  Scratch tmp(h);
+  if (int rc = upload_local(h, tmp, offsets, h->m_glob, h->row_old, h->m, buf)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->row_off = buf;
   return 0;
 }
 

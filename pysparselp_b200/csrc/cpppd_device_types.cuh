@@ -14,7 +14,7 @@ constexpr int kSlice = 32;       // SELL slice height C (= warp size)
 constexpr int kBlock = 256;      // threads per CTA for the streaming kernels (8 slices)
 constexpr int kGraphChunk = 50;  // iterations captured per CUDA graph
 constexpr int kColQ = 5;         // column-pass partials per CTA: 4 sums + max bound violation
-constexpr int kRowQ = 7;         // row-pass partials per CTA: 4 sums + 3 maxima
+constexpr int kRowQ = 9;         // row-pass partials per CTA: 4 sums + 5 maxima (the last two with the row offsets)
 constexpr int kGtQ = 2;          // ground-truth pass: sum |gt - x|, sum |gt - round(x)|
 constexpr int kStatQ = kColQ + kRowQ + kGtQ;
 // entries of the per-rank stats vector that are folded with a (NaN-propagating) max instead of a sum

@@ -39,9 +39,9 @@ __global__ void __launch_bounds__(kBlock)
 k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict__ x4,
              const double *__restrict__ xbar, const double *__restrict__ xr, Vec b,
              const double *__restrict__ y, int64_t m, int64_t m_eq, int force_integer,
-             double *__restrict__ part) {
+             const double *__restrict__ row_off, double *__restrict__ part) {
   const double ninf = -INFINITY;
-  double v[kRowQ] = {0.0, 0.0, 0.0, 0.0, ninf, ninf, ninf};
+  double v[kRowQ] = {0.0, 0.0, 0.0, 0.0, ninf, ninf, ninf, ninf, ninf};
   const int lane = threadIdx.x & 31;
   for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; (i >> 5) < A.nslices;
        i += (int64_t)gridDim.x * kBlock) {
@@ -75,9 +75,13 @@ k_stats_rows(SellView A, const double *__restrict__ x, const double *__restrict_
         v[3] = __dadd_rn(v[3], t2);
         v[6] = nan_max(v[6], __dsub_rn(axr, bi));
       }
+      // residual of the caller's FULL LP (cpppd_set_row_offsets: variables eliminated before the solve shift every
+      // row by a constant), for SparseLP.max_constraint_violation (reference SparseLP.py:186-204)
+      const double full = __dsub_rn(__dsub_rn(axr, bi), row_off ? row_off[i] : 0.0);
+      if (i < m_eq) v[7] = nan_max(v[7], fabs(full)); else v[8] = nan_max(v[8], full);
     }
   }
-  block_reduce_write<kRowQ>(v, 0x70u, part + (int64_t)blockIdx.x * kRowQ);
+  block_reduce_write<kRowQ>(v, 0x1F0u, part + (int64_t)blockIdx.x * kRowQ);
 }
 
 // Ground-truth pass (solve()'s distance curves, reference SparseLP.py:1074-1082): for the entries of the
@@ -104,7 +108,7 @@ k_stats_local(const double *__restrict__ colpart, int nbc, const double *__restr
 #pragma unroll
     for (int q = 0; q < kGtQ; ++q) gv[q] = __dadd_rn(gv[q], gtpart[(int64_t)bi * kGtQ + q]);
   const double ninf = -INFINITY;
-  double rv[kRowQ] = {0.0, 0.0, 0.0, 0.0, ninf, ninf, ninf};
+  double rv[kRowQ] = {0.0, 0.0, 0.0, 0.0, ninf, ninf, ninf, ninf, ninf};
   for (int bi = threadIdx.x; bi < nbc; bi += kBlock) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) cv[q] = __dadd_rn(cv[q], colpart[(int64_t)bi * kColQ + q]);
@@ -119,7 +123,7 @@ k_stats_local(const double *__restrict__ colpart, int nbc, const double *__restr
   __shared__ double fin[kStatQ];
   block_reduce_write<kColQ>(cv, 0x10u, fin);
   __syncthreads();
-  block_reduce_write<kRowQ>(rv, 0x70u, fin + kColQ);
+  block_reduce_write<kRowQ>(rv, 0x1F0u, fin + kColQ);
   __syncthreads();
   block_reduce_write<kGtQ>(gv, 0u, fin + kColQ + kRowQ);
   __syncthreads();
@@ -153,6 +157,8 @@ __global__ void k_stats_final(const double *__restrict__ all, int world, int64_t
   s.max_violated_equality = has_eq ? fin[kColQ + 4] : 0.0;
   s.max_violated_equality_rounded = has_eq ? fin[kColQ + 5] : 0.0;
   s.max_violated_inequality = fin[kColQ + 6];  // -inf when there is no inequality row
+  s.max_violated_equality_full = has_eq ? fin[kColQ + 7] : 0.0;
+  s.max_violated_inequality_full = fin[kColQ + 8];
   s.energy_rounded = fin[2];
   s.frac_zero_xbar = n_glob > 0 ? fin[3] / (double)n_glob : 0.0;
   s.max_bound_violation = fin[4];

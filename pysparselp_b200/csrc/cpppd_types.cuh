@@ -185,6 +185,7 @@ struct cpppd_solver {
   int64_t x_len = 0, y_len = 0;  // allocated length of x-like / y-like vectors (owned + ghosts + long-row tails)
   double *c = nullptr, *T = nullptr, *lb = nullptr, *ub = nullptr, *x = nullptr, *xbar = nullptr;
   double *b = nullptr, *sigma = nullptr, *y = nullptr, *dbuf = nullptr, *best = nullptr;
+  double *row_off = nullptr;  // cpppd_set_row_offsets (m, local order) or nullptr
   Vec vc{nullptr, 0}, vT{nullptr, 0}, vlb{nullptr, 0}, vub{nullptr, 0}, vb{nullptr, 0}, vsigma{nullptr, 0};
   int const_mask = 0;               // bit0 b, bit1 sigma, bit2 lb, bit3 ub, bit4 c, bit5 T folded to scalars
   unsigned long long *dict = nullptr;  // sorted bit patterns of the distinct matrix values (dictionary mode)

@@ -30,7 +30,7 @@ def test_struct_layout_matches_header():
     from pysparselp_b200 import _cabi
 
     # spot checks of the C layout (x86-64 SysV): sizes computed by hand from include/cpppd.h
-    assert C.sizeof(_cabi.Stats) == 8 + 11 * 8 + 4 * 4
+    assert C.sizeof(_cabi.Stats) == 8 + 13 * 8 + 4 * 4
     # windows, in_use, ms, sectors, window bytes, dense_halo + reserved, shape, shape_ms
     banded = 2 * 4 + 2 * 4 + 2 * 4 + 2 * 4 + 8 + 2 * 4 + 2 * 4 + 2 * 8 * 4
     assert C.sizeof(_cabi.Info) == 9 * 8 + 6 * 4 + 9 * 8 + 2 * 4 + 2 * _cabi.KERNEL_VARIANTS * 4 + 3 * 8 + 2 * 4 + banded

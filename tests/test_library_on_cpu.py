@@ -448,3 +448,53 @@ def test_emulated_banded_kernel_shapes_give_the_same_bits(shape, name, window, m
         assert np.array_equal(solver.get_y(), np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g]))
     finally:
         solver.close()
+
+
+def test_solve_with_fixed_variables_keeps_x_on_the_device(monkeypatch):
+    """``SparseLP.solve`` eliminates fixed variables before the solve and records, at every callback, curves of the
+    FULL LP at the mapped-back point (reference SparseLP.py:632-674, :1064-1093).  With the per-row offsets of
+    ``cpppd_set_row_offsets`` and the constant terms of the eliminated entries these are evaluated on the device: x is
+    fetched once, at the end — and the curves equal the host-side evaluation (``device_curves=False``)."""
+    import pysparselp_b200.ChambollePockPPD as front
+    from emul.patch_plugin import _Adapter
+    from pysparselp_b200.SparseLP import SparseLP
+    from test_fuzz_on_cpu import random_lp
+
+    fetches = []
+
+    class Counting(_Adapter):
+        def get_x(self):
+            fetches.append(1)
+            return super().get_x()
+
+    monkeypatch.setattr(front, "CpPpdSolver", Counting)
+    args, _, _, rng = random_lp(412)
+    c, a_eq, b_eq, a_in, b_lo, b_up, lb, ub = args
+    n = c.size
+    lb = np.where(np.isfinite(lb), lb, -3.0)
+    ub = np.where(np.isfinite(ub), ub, 3.0)
+    fix = rng.random(n) < 0.35
+    ub = np.where(fix, lb, ub)
+    gt_idx = np.sort(rng.choice(n, size=n // 2, replace=False))
+    gt = np.round(rng.standard_normal(gt_idx.size), 1)
+    curves = {}
+    for device_curves in (True, False):
+        lp = SparseLP()
+        lp.add_variables_array(n, lower_bounds=lb, upper_bounds=ub, costs=c)
+        if a_eq is not None and a_eq.shape[0]:
+            lp.add_equality_constraints_sparse(a_eq, b_eq)
+        lp.add_inequality_constraints_sparse(a_in, b_lo if b_lo is not None else np.full(a_in.shape[0], -np.inf), b_up)
+        fetches.clear()
+        x, _ = lp.solve(method="chambolle_pock_ppd", nb_iter=60, nb_iter_plot=10, ground_truth=gt, ground_truth_indices=gt_idx,
+                        device_curves=device_curves)
+        assert len(fetches) == (1 if device_curves else 7)
+        curves[device_curves] = (x, {k: np.array(getattr(lp, k), dtype=float) for k in (
+            "distance_to_ground_truth", "distanceToGroundTruthAfterRounding", "max_violated_constraint",
+            "max_violated_equality", "max_violated_inequality", "pobj_curve", "dobj_curve")})
+    assert fix.sum() > 0 and np.array_equal(curves[True][0], curves[False][0])
+    for k, want in curves[False][1].items():
+        got = curves[True][1][k]
+        assert got.shape == want.shape == (6,)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)])
+        assert np.allclose(got[fin], want[fin], rtol=1e-9, atol=1e-12), k

@@ -35,10 +35,12 @@ def short(name):
     if m:
         t = [int(v.replace("(bool)", "").replace("(int)", "")) for v in m.group(2).split(",")]
         if m.group(1) == "k_primal":
-            write_d, dict_, chunk, minb, comm, rows, persist = (t + [1, 0])[:7] if len(t) >= 6 else (t + [1, 0])[:7]
+            t += {5: [1, 0], 6: [0]}.get(len(t), [])  # (kRows and kPersist have defaults: older captures lack them)
+            write_d, dict_, chunk, minb, comm, rows, persist = t[:7]
         else:
             write_d = 0
-            dict_, chunk, minb, comm, rows, persist = (t + [1, 0])[:6] if len(t) >= 5 else (t + [1, 0])[:6]
+            t += {4: [1, 0], 5: [0]}.get(len(t), [])
+            dict_, chunk, minb, comm, rows, persist = t[:6]
         table = STRIDE if persist else VARIANTS
         tags = [table.get((chunk, minb, rows), "chunk%d/%dcta/rows%d" % (chunk, minb, rows))]
         tags += ["dict"] * bool(dict_) + ["write_d"] * bool(write_d) + ["fused-halo"] * bool(comm)
