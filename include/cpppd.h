@@ -157,7 +157,7 @@ typedef struct {
   void *comm;           /* optional cpppd_comm created by cpppd_comm_create(): reused (and not destroyed) by
                            this solver instead of building a new communicator from comm_id */
   int64_t long_row_threshold; /* rows of A / columns of A with more entries than this are summed by a CTA per
-                           4096-entry segment instead of by one thread (skewed patterns: L1-SVM weight columns, dense
+                           16384-entry segment instead of by one thread (skewed patterns: L1-SVM weight columns, dense
                            budget rows).  0: default (2048); < 0: never.  LPs with such rows agree with the reference
                            to rounding (fixed summation tree) instead of bit for bit; others are unaffected. */
   int64_t band_window;  /* banded operands: elements of the gathered vector per window.  0: CPPPD_BAND_WINDOW_MB

@@ -10,7 +10,7 @@
 // A row longer than the threshold is therefore cut out of the SELL operand at setup.  It keeps `virt`
 // VIRTUAL entries with value 1.0 whose gather index points behind the ghosts of the gathered vector (the
 // "tail"): before the hot kernel runs, k_long_partial / k_long_finish compute the row's sum(s) with one CTA
-// per 4096-entry segment and store them in the tail, and the unchanged hot kernel picks them up as
+// per 16384-entry segment and store them in the tail, and the unchanged hot kernel picks them up as
 // 0 + 1.0 * sum.  A^T keeps two virtual entries per long column (equality part with kEqBit, inequality
 // part), A keeps one.
 //
@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int kLongSeg = 4096;               // entries per segment (one CTA)
+constexpr int kLongSeg = 16384;              // entries per segment (one CTA: 192 KB of entries — with 4096 the three dependent
+                                             // loads that locate a segment took longer than streaming it, ncu: 39 % of HBM)
 constexpr int64_t kLongDefault = 2048;       // default threshold: rows with more entries are long
 
 struct LongRows {
