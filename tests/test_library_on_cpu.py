@@ -235,7 +235,7 @@ def test_emulated_every_kernel_variant_gives_the_same_bits(kernel_variant, flags
 def test_emulated_bad_kernel_variant_is_refused():
     args, _ = case_args("sc105")
     with pytest.raises(_cabi.CpppdError, match="kernel_variant"):
-        make_emulated_solver(*args, kernel_variant=9)
+        make_emulated_solver(*args, kernel_variant=_cabi.KERNEL_VARIANTS + 1)
 
 
 def test_emulated_autotune_leaves_the_initial_state_untouched(monkeypatch):
