@@ -604,19 +604,27 @@ def run_b200(a):
     # ---- end to end through the public API with host buffers -----------------------------------
     h2d = lp_nbytes(lp)
     d2h = 8 * n + 96
-    e2e_value, e2e_error = None, None
+    e2e_value, e2e_error, e2e_calls = None, None, []
     if a.e2e_steps > 0:
         def one_call():
             x, best = chambolle_pock_ppd(*args, nb_max_iter=a.e2e_iters, nb_iter_plot=a.e2e_iters, flags=a.flags)
             return x
 
         try:  # (a failure here must not take the device-timed headline down with it; it is reported in the line)
-            one_call()  # warm-up (allocator pools, graph instantiation, kernel-variant timing of this operand shape)
+            # warm-up: allocator pools (device and pinned host), graph instantiation, kernel-variant timing of this
+            # operand shape.  Twice, and the previous result is dropped before every call: a call that has to create a
+            # fresh 400 MB pinned result buffer (cudaHostAlloc) because the last x is still referenced takes 0.1-0.5 s
+            # longer (seen as 1.56 / 1.17 s calls among 1.03 s ones)
+            one_call()
+            one_call()
             barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(a.e2e_steps):
+                x = None
+                t_call = time.perf_counter()
                 x = one_call()
+                e2e_calls.append(round(time.perf_counter() - t_call, 4))
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if dist is not None:
@@ -664,7 +672,7 @@ def run_b200(a):
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "variants": variants,
             "with_stats_block": with_stats, "latency_bound_configs": small, "secondary_workloads": secondary,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "iters_per_call": a.e2e_iters, "calls": a.e2e_steps, "error": e2e_error,
+                    "iters_per_call": a.e2e_iters, "calls": a.e2e_steps, "call_seconds": e2e_calls, "error": e2e_error,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
                             "preconditioners on device, iterate, read x back"},
             # k_primal + k_dual per iteration; with N > 1 also k_push + k_wait after each of them (peer memory)

@@ -20,15 +20,4 @@ echo "l1svm exit $?" | tee -a $log
 timeout 900 python bench.py --workload l1svm --size 100000 --steps 4 --iters-per-step 10 --e2e-steps 1 --e2e-iters 50 --no-cpu-baseline --small-configs 0 \
   > $out/${tag}_bench_l1svm.json 2> $out/${tag}_bench_l1svm.err
 echo "bench l1svm exit $?" | tee -a $log
-echo "== 4. ncu --set full: banded window kernels (random LP), grid-stride kernels (Potts, generic and compressed)" | tee -a $log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_primal_band|k_dual_band' --launch-skip 560 -c 9 \
-  -f -o $out/${tag}_band python tools/quick_bench.py --kind random --size 20000000 --iters 4 --reps 1 > $out/${tag}_ncu_band.log 2>&1
-echo "ncu band exit $?" | tee -a $log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_primal|k_dual' --launch-skip 44 -c 4 \
-  -f -o $out/${tag}_stride python tools/quick_bench.py --size 4096 --iters 10 --reps 1 --variant 8 > $out/${tag}_ncu_stride.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_primal|k_dual' --launch-skip 44 -c 4 \
-  -f -o $out/${tag}_stride_dict python tools/quick_bench.py --size 4096 --iters 10 --reps 1 --variant 8 --flags 11 > $out/${tag}_ncu_stride_dict.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_long_partial|k_long_finish' --launch-skip 20 -c 4 \
-  -f -o $out/${tag}_long python tools/quick_bench.py --kind l1svm --size 50000 --iters 4 --reps 1 > $out/${tag}_ncu_long.log 2>&1
-echo "ncu exit $?" | tee -a $log
 echo "== done" | tee -a $log
