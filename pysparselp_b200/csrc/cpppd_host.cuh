@@ -517,18 +517,26 @@ int exchange_p2p(cpppd_solver *h, int kind) {
   P2P &pp = h->p2p;
   Halo &H = kind ? h->hy : h->hx;
   const double *vec = kind ? h->y : h->xbar;
+  // CPPPD_SPLIT_HALO_WAIT=1: the wait as a launch of its own (k_wait) instead of the tail of the push kernel
+  static const bool split_wait = [] { const char *e = getenv("CPPPD_SPLIT_HALO_WAIT"); return e && atoi(e) != 0; }();
+  const unsigned long long *wait_flags = split_wait ? nullptr : pp.flags;
+  bool pushed = false;
   if (pp.dense[kind]) {
     DenseDst D;
     memcpy(D.base, pp.dense_dst[kind], sizeof D.base);
     // (a few CTAs per SM: every thread streams its share of the owned entries to all peers)
     const int grid = (int)std::min<int64_t>(grid_for(H.owned), (int64_t)h->sm_count * 16);
     k_push_dense<<<grid, kBlock, 0, h->stream>>>(vec, H.owned, pp.ptrs[kind], D, kind, h->world, h->rank, pp.send_mask[kind],
-                                                 pp.state);
-  } else if (H.send_total)
+                                                 wait_flags, pp.recv_mask[kind], pp.state);
+    pushed = true;
+  } else if (H.send_total) {
     k_push<<<grid_for(H.send_total), kBlock, 0, h->stream>>>(vec, H.send_idx, pp.push_dst[kind], pp.push_peer[kind],
                                                             H.send_total, pp.ptrs[kind], kind, h->world, h->rank,
-                                                            pp.send_mask[kind], pp.state);
-  if (pp.recv_mask[kind]) k_wait<<<1, kMaxWorld, 0, h->stream>>>(pp.flags, kind, h->world, pp.recv_mask[kind], pp.state);
+                                                            pp.send_mask[kind], wait_flags, pp.recv_mask[kind], pp.state);
+    pushed = true;
+  }
+  if (pp.recv_mask[kind] && (!pushed || split_wait))
+    k_wait<<<1, kMaxWorld, 0, h->stream>>>(pp.flags, kind, h->world, pp.recv_mask[kind], pp.state);
   return 0;
 }
 

@@ -190,15 +190,12 @@ __global__ void k_init_stats(StatsDev *st) {
 // push_dst[k] of that peer's vector (its ghost slot).  The last CTA to finish raises, on every
 // neighbour it sent to, the flag [kind * world + me] to the new stamp (release at system scope after
 // every CTA fenced its stores).
-__global__ void __launch_bounds__(kBlock)
-k_push(const double *__restrict__ vec, const int32_t *__restrict__ src, const int64_t *__restrict__ dst,
-       const int32_t *__restrict__ peer, int64_t count, PeerPtrs P, int kind, int world, int me,
-       unsigned long long send_mask, SyncState *st) {
-  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (k < count) P.vec[peer[k]][dst[k]] = vec[src[k]];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+// Tail of a push kernel, run by thread 0 of every CTA after the CTA's stores were fenced: the LAST CTA to arrive
+// publishes the new stamp to the neighbours and then — the wait of this exchange, merged into the same launch: one
+// kernel less per half-iteration, which counts when a rank's kernels take 100 us — spins until the neighbours' stamps
+// of this exchange arrived (`my_flags` != nullptr; with a time-out, see wait_for_stamp).
+__device__ __forceinline__ void push_finish(const PeerPtrs &P, int kind, int world, int me, unsigned long long send_mask,
+                                            const unsigned long long *my_flags, unsigned long long recv_mask, SyncState *st) {
   const unsigned int ticket = atomicAdd(&st->ticket[kind], 1u);
   if (ticket != gridDim.x - 1) return;
   __threadfence_system();
@@ -207,6 +204,25 @@ k_push(const double *__restrict__ vec, const int32_t *__restrict__ src, const in
   st->push_stamp[kind] = stamp;
   for (int t = 0; t < world; ++t)
     if ((send_mask >> t) & 1ull) st_release_sys(P.flags[t] + kind * world + me, stamp);
+  if (my_flags && recv_mask) {
+    const unsigned long long want = st->wait_stamp[kind] + 1;
+    for (int t = 0; t < world; ++t)
+      if ((recv_mask >> t) & 1ull) wait_for_stamp(my_flags + kind * world + t, want, st, 200);
+    st->wait_stamp[kind] = want;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+k_push(const double *__restrict__ vec, const int32_t *__restrict__ src, const int64_t *__restrict__ dst,
+       const int32_t *__restrict__ peer, int64_t count, PeerPtrs P, int kind, int world, int me,
+       unsigned long long send_mask, const unsigned long long *__restrict__ my_flags, unsigned long long recv_mask,
+       SyncState *st) {
+  const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (k < count) P.vec[peer[k]][dst[k]] = vec[src[k]];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  push_finish(P, kind, world, me, send_mask, my_flags, recv_mask, st);
 }
 
 // Dense halo (patterns without locality: every peer needs every owned entry, and its ghost slots for this rank are
@@ -217,7 +233,8 @@ struct DenseDst {
 };
 __global__ void __launch_bounds__(kBlock)
 k_push_dense(const double *__restrict__ vec, int64_t owned, PeerPtrs P, DenseDst D, int kind, int world, int me,
-             unsigned long long send_mask, SyncState *st) {
+             unsigned long long send_mask, const unsigned long long *__restrict__ my_flags, unsigned long long recv_mask,
+             SyncState *st) {
   for (int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x; k < owned; k += (int64_t)gridDim.x * kBlock) {
     const double v = vec[k];
     for (int t = 0; t < world; ++t)
@@ -226,17 +243,11 @@ k_push_dense(const double *__restrict__ vec, int64_t owned, PeerPtrs P, DenseDst
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const unsigned int ticket = atomicAdd(&st->ticket[kind], 1u);
-  if (ticket != gridDim.x - 1) return;
-  __threadfence_system();
-  st->ticket[kind] = 0;
-  const unsigned long long stamp = st->push_stamp[kind] + 1;
-  st->push_stamp[kind] = stamp;
-  for (int t = 0; t < world; ++t)
-    if ((send_mask >> t) & 1ull) st_release_sys(P.flags[t] + kind * world + me, stamp);
+  push_finish(P, kind, world, me, send_mask, my_flags, recv_mask, st);
 }
 
-// Wait until every neighbour this rank receives from has pushed its halo for this exchange.
+// Wait until every neighbour this rank receives from has pushed its halo for this exchange (a rank that receives
+// without sending anything; otherwise the wait is the tail of the push kernel).
 __global__ void k_wait(const unsigned long long *__restrict__ flags, int kind, int world,
                        unsigned long long recv_mask, SyncState *st) {
   const int t = threadIdx.x;
