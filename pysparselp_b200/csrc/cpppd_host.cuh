@@ -233,9 +233,13 @@ int split_long_rows(cpppd_solver *h, Scratch &tmp, const int64_t *rowptr, const 
   std::vector<int64_t> len(count), ptr(count + 1, 0), seg_ptr(count + 1, 0);
   CK(cudaMemcpyAsync(len.data(), len_dev, sizeof(int64_t) * count, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  int seg_len = kLongSeg;
+  if (const char *env = getenv("CPPPD_LONG_SEG"))
+    if (atoi(env) >= 256) seg_len = atoi(env);
+  L->seg_len = seg_len;
   for (int32_t r = 0; r < count; ++r) {
     ptr[r + 1] = ptr[r] + len[r];
-    seg_ptr[r + 1] = seg_ptr[r] + (len[r] + kLongSeg - 1) / kLongSeg;
+    seg_ptr[r + 1] = seg_ptr[r] + (len[r] + seg_len - 1) / seg_len;
   }
   L->nnz = ptr[count];
   L->nseg = seg_ptr[count];
@@ -243,15 +247,29 @@ int split_long_rows(cpppd_solver *h, Scratch &tmp, const int64_t *rowptr, const 
   std::vector<int32_t> seg_row(L->nseg);
   for (int32_t r = 0; r < count; ++r)
     for (int64_t q = seg_ptr[r]; q < seg_ptr[r + 1]; ++q) seg_row[q] = r;
+  // launch order: row-major, as stored; CPPPD_LONG_ORDER=1: by position inside the row, then by row (the CTAs resident
+  // at one time then gather from about the same window of the vector — measured on the L1-SVM LP: no gain, 0.83 vs
+  // 0.81 ms; what the kernel lacked was the software pipeline, profiles/r02p_long_sweep.jsonl)
+  std::vector<int32_t> seg_order(L->nseg);
+  for (int64_t q = 0; q < L->nseg; ++q) seg_order[q] = (int32_t)q;
+  const char *order_env = getenv("CPPPD_LONG_ORDER"), *shape_env = getenv("CPPPD_LONG_SHAPE");
+  const bool k_major = order_env && atoi(order_env) != 0;
+  L->shape = shape_env ? atoi(shape_env) : 0;
+  if (k_major)
+    std::stable_sort(seg_order.begin(), seg_order.end(), [&](int32_t a, int32_t b) {
+      return a - seg_ptr[seg_row[a]] < b - seg_ptr[seg_row[b]];
+    });
   if (int rc = alloc_array(h, &L->ptr, count + 1)) return rc;
   if (int rc = alloc_array(h, &L->seg_ptr, count + 1)) return rc;
   if (int rc = alloc_array(h, &L->seg_row, L->nseg)) return rc;
+  if (int rc = alloc_array(h, &L->seg_order, L->nseg)) return rc;
   if (int rc = alloc_array(h, &L->idx, L->nnz)) return rc;
   if (int rc = alloc_array(h, &L->val, L->nnz)) return rc;
   if (int rc = alloc_array(h, &L->partial, 2 * L->nseg)) return rc;
   CK(cudaMemcpyAsync(L->ptr, ptr.data(), sizeof(int64_t) * (count + 1), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(L->seg_ptr, seg_ptr.data(), sizeof(int64_t) * (count + 1), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(L->seg_row, seg_row.data(), sizeof(int32_t) * L->nseg, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(L->seg_order, seg_order.data(), sizeof(int32_t) * L->nseg, cudaMemcpyHostToDevice, st));
   k_long_copy<<<count, kBlock, 0, st>>>(rowptr, indices, values, L->row, L->ptr, L->idx, L->val);
   // the CSR that goes into SELL: short rows as they are, long rows reduced to their virtual entries
   int64_t *newlen = nullptr;
@@ -275,10 +293,26 @@ int split_long_rows(cpppd_solver *h, Scratch &tmp, const int64_t *rowptr, const 
   return 0;
 }
 
+// k_long_partial in the compiled shape CPPPD_LONG_SHAPE asks for (default 0; all shapes give the same bits)
+void launch_long_partial(cpppd_solver *h, const LongRows &L, const double *vec, double power) {
+  const int shape = L.shape;
+  const int grid = (int)L.nseg;
+#define CPPPD_LONG_ARGS L.ptr, L.seg_ptr, L.seg_row, L.seg_order, L.seg_len, L.idx, L.val, vec, power, L.partial
+  if (!vec)
+    k_long_partial<2, 4, false><<<grid, kBlock, 0, h->stream>>>(CPPPD_LONG_ARGS);
+  else if (shape == 1)
+    k_long_partial<4, 5, true><<<grid, kBlock, 0, h->stream>>>(CPPPD_LONG_ARGS);
+  else if (shape == 2)
+    k_long_partial<8, 3, true><<<grid, kBlock, 0, h->stream>>>(CPPPD_LONG_ARGS);
+  else
+    k_long_partial<6, 4, true><<<grid, kBlock, 0, h->stream>>>(CPPPD_LONG_ARGS);
+#undef CPPPD_LONG_ARGS
+}
+
 // sums of the long rows of L against `vec`, stored behind the ghosts of `out_vec` (its tail)
 int long_pass(cpppd_solver *h, const LongRows &L, const double *vec, double *out_vec) {
   if (L.count == 0) return 0;
-  k_long_partial<<<(int)L.nseg, kBlock, 0, h->stream>>>(L.ptr, L.seg_ptr, L.seg_row, L.idx, L.val, vec, 0.0, L.partial);
+  launch_long_partial(h, L, vec, 0.0);
   k_long_finish<<<grid_for(L.count * 32), kBlock, 0, h->stream>>>(L.seg_ptr, L.row, L.count, L.partial,
                                                                  L.virt == 2 ? kLongSumsAT : kLongSumsA, 1, 1,
                                                                  out_vec + L.tail_base);
@@ -289,7 +323,7 @@ int long_pass(cpppd_solver *h, const LongRows &L, const double *vec, double *out
 int long_precond(cpppd_solver *h, const LongRows &L, double power, double *out) {
   if (L.count == 0) return 0;
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-  k_long_partial<<<(int)L.nseg, kBlock, 0, h->stream>>>(L.ptr, L.seg_ptr, L.seg_row, L.idx, L.val, nullptr, power, L.partial);
+  launch_long_partial(h, L, nullptr, power);
   k_long_finish<<<grid_for(L.count * 32), kBlock, 0, h->stream>>>(L.seg_ptr, L.row, L.count, L.partial,
                                                                  L.virt == 2 ? kLongPrecondT : kLongPrecondSigma, has_eq,
                                                                  has_ineq, out);

@@ -24,8 +24,9 @@
 
 namespace {
 
-constexpr int kLongSeg = 16384;              // entries per segment (one CTA: 192 KB of entries — with 4096 the three dependent
-                                             // loads that locate a segment took longer than streaming it, ncu: 39 % of HBM)
+constexpr int kLongSeg = 16384;              // default entries per segment (one CTA: 192 KB of entries — with 4096 the three
+                                             // dependent loads that locate a segment took longer than streaming it, ncu: 39 %
+                                             // of HBM); CPPPD_LONG_SEG overrides (the segment length is part of the fixed tree)
 constexpr int64_t kLongDefault = 2048;       // default threshold: rows with more entries are long
 
 struct LongRows {
@@ -36,6 +37,9 @@ struct LongRows {
   int64_t *ptr = nullptr;        // [count+1] entry offsets
   int64_t *seg_ptr = nullptr;    // [count+1] first segment of each long row
   int32_t *seg_row = nullptr;    // [nseg]    long row of a segment
+  int32_t *seg_order = nullptr;  // [nseg]    launch order of the segments: by position inside their row, then by row
+  int seg_len = kLongSeg;        // entries per segment
+  int shape = 0;                 // compiled shape of k_long_partial (CPPPD_LONG_SHAPE)
   int32_t *idx = nullptr;        // entries in stored order (A^T: with kEqBit), plain values
   double *val = nullptr;
   double *partial = nullptr;     // [2 * nseg]
@@ -104,40 +108,61 @@ k_long_copy(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ indi
 }
 
 // One CTA per segment: partial[2 s] / partial[2 s + 1] = equality / other part of sum_k a_k * vec[idx_k] over the
-// segment (vec == nullptr: sum_k |a_k|^power, the preconditioner sums).  Thread t takes entries t, t + 256, ...
-__global__ void __launch_bounds__(kBlock, 4)
+// segment (kGather false: sum_k |a_k|^power, the preconditioner sums).  Thread t takes entries t, t + 256, ...
+// CTA b takes segment seg_order[b] (row-major by default; see split_long_rows).
+template <int kLongUnroll, int kMinCtas, bool kGather>
+__global__ void __launch_bounds__(kBlock, kMinCtas)
 k_long_partial(const int64_t *__restrict__ ptr, const int64_t *__restrict__ seg_ptr, const int32_t *__restrict__ seg_row,
-               const int32_t *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ vec,
-               double power, double *__restrict__ partial) {
-  const int64_t s = blockIdx.x;
+               const int32_t *__restrict__ seg_order, int seg_len, const int32_t *__restrict__ idx,
+               const double *__restrict__ val, const double *__restrict__ vec, double power,
+               double *__restrict__ partial) {
+  const int64_t s = seg_order[blockIdx.x];
   const int32_t r = seg_row[s];
-  const int64_t e0 = ptr[r] + (s - seg_ptr[r]) * kLongSeg;
-  const int64_t e1 = min(e0 + (int64_t)kLongSeg, ptr[r + 1]);
+  const int64_t e0 = ptr[r] + (s - seg_ptr[r]) * seg_len;
+  const int64_t e1 = min(e0 + (int64_t)seg_len, ptr[r + 1]);
   double v[2] = {0.0, 0.0};
-  // kLongUnroll entries of the thread at a time: all index / value loads, then all gathers, then the additions in
-  // the thread's entry order (the same fixed tree as a one-at-a-time loop, with six loads in flight instead of one:
-  // ncu had this kernel at 39 % of the DRAM bandwidth on the L1-SVM weight columns, bound by load latency)
-  constexpr int kLongUnroll = 6;
+  // kLongUnroll entries of the thread per trip, software-pipelined: the index / value loads of trip t + 1 are issued
+  // before the gathers of trip t are consumed, so the entry stream never drains while a trip waits for its gathers.
+  // The additions stay in the thread's entry order (the same fixed tree as a one-at-a-time loop).
+  int32_t w[kLongUnroll], wn[kLongUnroll];
+  double a[kLongUnroll], an[kLongUnroll], g[kLongUnroll];
+  constexpr int64_t kTrip = (int64_t)kBlock * kLongUnroll;
+  int64_t base = e0 + threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < kLongUnroll; ++u) {
+    const int64_t e = base + (int64_t)u * kBlock;
+    wn[u] = e < e1 ? __ldcs(idx + e) : 0;
+    an[u] = e < e1 ? __ldcs(val + e) : 0.0;
+  }
 #pragma unroll 1
-  for (int64_t base = e0 + threadIdx.x; base < e1; base += (int64_t)kBlock * kLongUnroll) {
-    int32_t w[kLongUnroll];
-    double a[kLongUnroll], g[kLongUnroll];
+  for (; base < e1; base += kTrip) {
 #pragma unroll
     for (int u = 0; u < kLongUnroll; ++u) {
-      const int64_t e = base + (int64_t)u * kBlock;
-      w[u] = e < e1 ? __ldcs(idx + e) : 0;
-      a[u] = e < e1 ? __ldcs(val + e) : 0.0;
+      w[u] = wn[u];
+      a[u] = an[u];
     }
 #pragma unroll
-    for (int u = 0; u < kLongUnroll; ++u) g[u] = (vec && base + (int64_t)u * kBlock < e1) ? __ldg(vec + (w[u] & kIdxMask)) : 0.0;
+    for (int u = 0; u < kLongUnroll; ++u) g[u] = (kGather && base + (int64_t)u * kBlock < e1) ? __ldg(vec + (w[u] & kIdxMask)) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kLongUnroll; ++u) {
+      const int64_t e = base + kTrip + (int64_t)u * kBlock;
+      wn[u] = e < e1 ? __ldcs(idx + e) : 0;
+      an[u] = e < e1 ? __ldcs(val + e) : 0.0;
+    }
 #pragma unroll
     for (int u = 0; u < kLongUnroll; ++u) {
       if (base + (int64_t)u * kBlock >= e1) break;
-      const double t = vec ? __dmul_rn(a[u], g[u]) : abs_pow(a[u], power);
+      const double t = kGather ? __dmul_rn(a[u], g[u]) : abs_pow(a[u], power);
       if (w[u] & kEqBit) v[0] = __dadd_rn(v[0], t); else v[1] = __dadd_rn(v[1], t);
     }
   }
   block_reduce_write<2>(v, 0u, partial + 2 * s);
+}
+
+// compiled shapes of k_long_partial (same bits): entries in flight per thread x resident CTAs per SM
+constexpr int kLongShapes = 3;
+inline const char *long_shape_name(int shape) {
+  return shape == 1 ? "pipe4/5cta" : shape == 2 ? "pipe8/3cta" : "pipe6/4cta";
 }
 
 enum { kLongSumsAT = 0, kLongSumsA = 1, kLongPrecondT = 2, kLongPrecondSigma = 3 };

@@ -7,7 +7,7 @@ from pysparselp_b200 import generators
 from pysparselp_b200.ChambollePockPPD import make_solver, chambolle_pock_ppd
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-lp, keep = build_workload(size, pinned=True)
+lp, keep = build_workload("potts", size, pinned=True)
 args = generators.lp_args(lp)
 for flags in (0, 8, 0, 8):
     torch.cuda.synchronize(); t0 = time.perf_counter()
