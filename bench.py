@@ -662,7 +662,8 @@ def run_b200(a):
                 secondary[kind] = {"error": repr(e)}
 
     if rank == 0:
-        launches_per_iteration = 2 if world == 1 or a.flags & 128 else (4 if a.flags & 32 else 6)
+        split_wait = os.environ.get("CPPPD_SPLIT_HALO_WAIT", "0") not in ("", "0")
+        launches_per_iteration = 2 if world == 1 or a.flags & 128 else (6 if split_wait and not a.flags & 32 else 4)
         if any(info["band_in_use"]):  # a banded half-iteration is one launch per window
             launches_per_iteration = sum(info["band_windows"][k] if info["band_in_use"][k] else 1 for k in (0, 1))
         line = {
@@ -675,8 +676,9 @@ def run_b200(a):
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps, "call_seconds": e2e_calls, "error": e2e_error,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
                             "preconditioners on device, iterate, read x back"},
-            # k_primal + k_dual per iteration; with N > 1 also k_push + k_wait after each of them (peer memory)
-            # or one k_pack before each NCCL send/recv group
+            # k_primal + k_dual per iteration; with N > 1 also one k_push after each of them (peer memory; it also waits
+            # for the incoming halo — a separate k_wait only with CPPPD_SPLIT_HALO_WAIT=1) or one k_pack before each
+            # NCCL send/recv group
             # ... or nothing more when the halo is fused into the two kernels (flag 128)
             "gpu_launches": launches_per_iteration * a.steps * a.iters_per_step,
             "kernel_variants": kernel_variants(info),
@@ -717,20 +719,24 @@ def small_configs(a, generators, make_solver):
             small["netlib_sc105"] = {"error": repr(e)}
         for name, sargs in small_lps.items():
             small[name] = {}
-            for label, sflags in (("cuda_graphs", 4096), ("persistent_cta", 0)):  # (4096: CPPPD_FLAG_NO_TINY_PERSISTENT)
+            # (4096: CPPPD_FLAG_NO_TINY_PERSISTENT; the default picks one persistent CTA (k_tiny_iterate) when the LP fits one
+            # SM, one persistent thread-block cluster of 16 CTAs (k_cluster_iterate) when it fits 16)
+            for label, sflags in (("cuda_graphs", 4096), ("persistent", 0)):
                 try:
                     ss = make_solver(*sargs, flags=sflags)
                     try:
                         ss.iterate(a.small_iters)
                         ss.sync()
                         ms_small = ss.time_iterations(a.small_iters)
-                        used = bool(ss.info()["tiny_persistent"])
+                        used = int(ss.info()["tiny_persistent"])
                     finally:
                         ss.close()
-                    if label == "persistent_cta" and not used:
-                        small[name][label] = None  # the LP does not fit one CTA: the flag is ignored
+                    if label == "persistent" and not used:
+                        small[name][label] = None  # the LP fits neither: graph path
                     else:
                         small[name][label] = {"iterations_per_s": a.small_iters / (ms_small * 1e-3)}
+                        if label == "persistent":
+                            small[name][label]["kernel"] = {1: "k_tiny_iterate (one CTA)", 2: "k_cluster_iterate (one cluster)"}[used]
                 except Exception as e:
                     small[name][label] = {"error": repr(e)}
     except Exception as e:

@@ -32,6 +32,7 @@
 #include "cpppd_types.cuh"
 #include "cpppd_setup_kernels.cuh"
 #include "cpppd_hot_kernels.cuh"
+#include "cpppd_cluster.cuh"
 #include "cpppd_stats_kernels.cuh"
 #include "cpppd_host.cuh"
 
@@ -498,7 +499,7 @@ int cpppd_get_info(cpppd_handle h, cpppd_info *out) {
     if (!((h->const_mask >> bit) & 1)) vec_bytes += 8 * per_elem[bit];
   out->balanced_split = h->balanced_split ? 1 : 0;
   out->dense_halo = h->dense_halo && h->world > 1 ? 1 : 0;
-  out->tiny_persistent = h->tiny ? 1 : 0;
+  out->tiny_persistent = h->tiny ? 1 : (h->cluster.on ? 2 : 0);
   out->long_rows = h->longA.count;
   out->long_cols = h->longAT.count;
   out->long_entries = h->longA.nnz + h->longAT.nnz;

@@ -187,6 +187,38 @@ int build_band(cpppd_solver *h, const int64_t *rowptr, const int32_t *indices, c
   return 0;
 }
 
+// Host -> device copy of an array that EVERY rank of a distributed solve holds (the LP is passed whole to each rank):
+// a rank copies only its 1/N slice over PCIe and the slices are all-gathered over NVLink — the eight ranks of a node
+// otherwise pull N copies of the LP through the host's memory system at the same time (measured on the 4.4 GB Potts
+// LP: 54 / 83 / 110-130 ms per rank at N = 2 / 4 / 8).  The destination must hold shared_upload_count() elements.
+// CPPPD_FULL_UPLOAD=1 keeps the plain copy.
+inline bool shared_upload_on(const cpppd_solver *h) {
+  static const bool full = [] { const char *e = getenv("CPPPD_FULL_UPLOAD"); return e && atoi(e) != 0; }();
+  return h->world > 1 && h->comm && !full;
+}
+inline int64_t shared_upload_chunk(const cpppd_solver *h, int64_t bytes) {  // bytes per rank, a multiple of 256
+  const int64_t per = (bytes + h->world - 1) / h->world;
+  return (per + 255) / 256 * 256;
+}
+inline int64_t shared_upload_count(const cpppd_solver *h, int64_t count, size_t elem) {
+  if (!shared_upload_on(h) || count == 0) return count;
+  return (shared_upload_chunk(h, count * (int64_t)elem) * h->world + (int64_t)elem - 1) / (int64_t)elem;
+}
+int upload_shared(cpppd_solver *h, void *dst, const void *src, int64_t count, size_t elem) {
+  if (count == 0) return 0;
+  const int64_t bytes = count * (int64_t)elem;
+  if (!shared_upload_on(h)) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+  }
+  const int64_t chunk = shared_upload_chunk(h, bytes);
+  const int64_t lo = std::min(bytes, chunk * h->rank), hi = std::min(bytes, lo + chunk);
+  if (hi > lo)
+    CK(cudaMemcpyAsync((char *)dst + lo, (const char *)src + lo, hi - lo, cudaMemcpyHostToDevice, h->stream));
+  NK(g_nccl.AllGather((const char *)dst + chunk * h->rank, dst, (size_t)chunk, ncclInt8, h->comm, h->stream));
+  return 0;
+}
+
 int upload_f64(cpppd_solver *h, double *dst, const double *src, int64_t count) {
   if (count == 0) return 0;
   CK(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
@@ -341,8 +373,8 @@ int upload_local(cpppd_solver *h, Scratch &tmp, const double *host_full, int64_t
                  int64_t local_count, double *dst) {
   if (h->identity_layout) return upload_f64(h, dst, host_full, local_count);
   double *full = nullptr;
-  if (int rc = tmp.get(&full, full_count)) return rc;
-  if (int rc = upload_f64(h, full, host_full, full_count)) return rc;
+  if (int rc = tmp.get(&full, shared_upload_count(h, full_count, sizeof(double)))) return rc;
+  if (int rc = upload_shared(h, full, host_full, full_count, sizeof(double))) return rc;
   if (local_count) k_gather_f64<<<grid_for(local_count), kBlock, 0, h->stream>>>(full, map, local_count, dst);
   CK(cudaStreamSynchronize(h->stream));
   tmp.release(full);
@@ -622,6 +654,78 @@ int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const s
   return 0;
 }
 
+// Can one thread-block cluster carry this LP (cpppd_cluster.cuh)?  Fills h->cluster.
+int plan_cluster(cpppd_solver *h) {
+  h->cluster = ClusterPlan();
+#ifdef __CUDACC__
+  static const bool off = [] { const char *e = getenv("CPPPD_NO_CLUSTER"); return e && atoi(e) != 0; }();
+  if (off || h->A.nslices == 0 || h->AT.nslices == 0) return 0;
+  if (h->A.padded > kClusterMaxEntries || h->AT.padded > kClusterMaxEntries) return 0;
+  std::vector<int64_t> sp[2];
+  const Sell *ops[2] = {&h->AT, &h->A};
+  for (int k = 0; k < 2; ++k) {
+    const Sell &S = *ops[k];
+    sp[k].resize(S.nslices + 1);
+    if (S.uniform_width >= 0) {
+      for (int64_t q = 0; q <= S.nslices; ++q) sp[k][q] = q * S.uniform_width * 32;
+    } else {
+      CK(cudaMemcpyAsync(sp[k].data(), S.slice_ptr, sizeof(int64_t) * (S.nslices + 1), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+    }
+  }
+  int max_smem = 0;
+  CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  auto kernel = k_cluster_iterate<0>;
+  for (int ctas : {kClusterMaxCtas, 8}) {
+    ClusterPlan P;
+    P.ctas = ctas;
+    P.spc_at = (int)((h->AT.nslices + ctas - 1) / ctas);
+    P.spc_a = (int)((h->A.nslices + ctas - 1) / ctas);
+    int64_t ent[2] = {0, 0};
+    for (int k = 0; k < 2; ++k) {
+      const int64_t ns = ops[k]->nslices, spc = k ? P.spc_a : P.spc_at;
+      for (int r = 0; r < ctas; ++r) {
+        const int64_t lo = std::min<int64_t>(r * spc, ns), hi = std::min<int64_t>(lo + spc, ns);
+        ent[k] = std::max(ent[k], sp[k][hi] - sp[k][lo]);
+      }
+    }
+    P.ent_at = (int)ent[0];
+    P.ent_a = (int)ent[1];
+    P.smem = cluster_smem_bytes(P.spc_at, P.spc_a, P.ent_at, P.ent_a);
+    if ((int64_t)P.smem > max_smem) continue;
+    bool attr_ok = true;
+    for (auto fn : {k_cluster_iterate<0>, k_cluster_iterate<1>})
+      attr_ok = attr_ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
+                (ctas <= 8 || cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess);
+    if (!attr_ok) {
+      cudaGetLastError();
+      continue;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kClusterBlock);
+    cfg.dynamicSmemBytes = P.smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = ctas;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&clusters, kernel, &cfg) != cudaSuccess || clusters < 1) {
+      cudaGetLastError();
+      continue;
+    }
+    P.on = true;
+    h->cluster = P;
+    break;
+  }
+#endif
+  return 0;
+}
+
 // CPPPD_SETUP_TIMING=1: wall-clock of the phases of setup() on stderr (after a stream synchronisation each)
 struct PhaseTimer {
   cudaStream_t st;
@@ -649,23 +753,21 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   int64_t *rowptr = nullptr;
   int32_t *indices = nullptr;
   double *values = nullptr;
-  if (int rc = tmp.get(&rowptr, m + 1)) return rc;
-  if (int rc = tmp.get(&indices, nnz)) return rc;
-  if (int rc = tmp.get(&values, nnz)) return rc;
+  if (int rc = tmp.get(&rowptr, shared_upload_count(h, m + 1, sizeof(int64_t)))) return rc;
+  if (int rc = tmp.get(&indices, shared_upload_count(h, nnz, sizeof(int32_t)))) return rc;
+  if (int rc = tmp.get(&values, shared_upload_count(h, nnz, sizeof(double)))) return rc;
   if (P->indptr_bits == 64) {
-    CK(cudaMemcpyAsync(rowptr, P->indptr, sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
+    if (int rc = upload_shared(h, rowptr, P->indptr, m + 1, sizeof(int64_t))) return rc;
   } else {
     int32_t *tmp32 = nullptr;
-    if (int rc = tmp.get(&tmp32, m + 1)) return rc;
-    CK(cudaMemcpyAsync(tmp32, P->indptr, sizeof(int32_t) * (m + 1), cudaMemcpyHostToDevice, st));
+    if (int rc = tmp.get(&tmp32, shared_upload_count(h, m + 1, sizeof(int32_t)))) return rc;
+    if (int rc = upload_shared(h, tmp32, P->indptr, m + 1, sizeof(int32_t))) return rc;
     k_widen_indptr<<<grid_for(m + 1), kBlock, 0, st>>>(tmp32, rowptr, m + 1);
     CK(cudaStreamSynchronize(st));
     tmp.release(tmp32);
   }
-  if (nnz) {
-    CK(cudaMemcpyAsync(indices, P->indices, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(values, P->values, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
-  }
+  if (int rc = upload_shared(h, indices, P->indices, nnz, sizeof(int32_t))) return rc;
+  if (int rc = upload_shared(h, values, P->values, nnz, sizeof(double))) return rc;
   {  // validation on the device: monotone row pointers, column indices in range
     int *flag = nullptr;
     if (int rc = tmp.get(&flag, 1)) return rc;
@@ -678,6 +780,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (host_flag & 1) return fail(h, CPPPD_ERR_INVALID, "indptr is not non-decreasing");
     if (host_flag & 2) return fail(h, CPPPD_ERR_INVALID, "column index outside [0, n)");
   }
+  phase.mark("upload + validation");
   if ((h->flags & CPPPD_FLAG_VALUE_DICT) && nnz)
     if (int rc = detect_dictionary(h, tmp, values, nnz)) return rc;
   uint32_t *row_of = nullptr, *entry_id = nullptr;
@@ -732,7 +835,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   }
 
   if (reorder) {
-    phase.mark("upload + validation");
+    phase.mark("row of entry + layout choice");
     // ---- locality keys -> buckets -> owners (oracle/partition_oracle.py restates this block)
     const int64_t G = h->granule > 0 ? h->granule : default_granule(n);
     h->granule = G;
@@ -766,6 +869,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
       col_share[owner_h[q]] += work_h[nb + q];
     }
     CK(cudaMemcpyAsync(owner_dev, owner_h.data(), sizeof(int32_t) * nb, cudaMemcpyHostToDevice, st));
+    phase.mark("  keys + bucket work");
     // A pattern without locality leaves some rank with far more than its share of the row entries or of the
     // column entries (every kernel then waits for that rank): fall back to the balanced split, where the owner
     // of a row / column follows from the entries in front of it (oracle/partition_oracle.py restates this).
@@ -802,6 +906,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
                                                        h->balanced_split ? rowptr : nullptr, nnz, N, keep_order, rk_a, ro_a, counts, counts + N);
     if (n) k_sort_keys<<<grid_for(n), kBlock, 0, st>>>(col_key, n, (int32_t)G, owner_dev, 0, 0, nullptr, col_len,
                                                        col_prefix, nnz, N, keep_order, ck_a, co_a, counts + 2 * N, nullptr);
+    phase.mark("  sort keys");
     const int end_bit = 44 + bits_for((uint64_t)2 * N + 1);
     cub::DoubleBuffer<uint64_t> rk(rk_a, rk_b), ck(ck_a, ck_b);
     cub::DoubleBuffer<uint32_t> rov(ro_a, ro_b), cov(co_a, co_b);
@@ -809,6 +914,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = sort_pairs(h, ck, cov, n, end_bit)) return rc;
     row_order = rov.Current();
     col_order = cov.Current();
+    phase.mark("  two radix sorts");
     std::vector<int32_t> counts_h(3 * N);
     if (int rc = read_i32(h, counts, counts_h.data(), 3 * N)) return rc;
     for (int r = 0; r < N; ++r) {
@@ -1159,6 +1265,19 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   h->tiny = !(h->flags & CPPPD_FLAG_NO_TINY_PERSISTENT) && !variant_forced && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
             !h->bandA.built && !h->bandAT.built &&
             std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
+  // ... a cluster of up to 16 CTAs when they fit the shared memory of 16 SMs (see k_cluster_iterate);
+  // CPPPD_FORCE_CLUSTER=1 (tests): also the LPs that would fit one CTA
+  // An LP that fits one CTA but needs more than one pass of its 1024 threads is faster on the cluster as well
+  // (Potts 24x24, 1 680 x 2 208: 131 000 it/s in one CTA, 177 000 through CUDA graphs, 575 000 in the cluster; SC105,
+  // 103 x 105: 801 000 in one CTA, 734 000 in the cluster — profiles/r02_kernels.md)
+  const bool was_tiny = h->tiny;
+  if (h->tiny && std::max(nloc, mloc) > kTinyBlock) h->tiny = false;
+  if (const char *e = getenv("CPPPD_FORCE_CLUSTER"))
+    if (atoi(e) != 0) h->tiny = false;
+  if (!h->tiny && !(h->flags & CPPPD_FLAG_NO_TINY_PERSISTENT) && !variant_forced && N == 1 && h->longA.count == 0 &&
+      h->longAT.count == 0 && !h->bandA.built && !h->bandAT.built)
+    if (int rc = plan_cluster(h)) return rc;
+  if (was_tiny && !h->cluster.on) h->tiny = true;
   phase.mark("stats plumbing");
   if (int rc = tune_kernels(h)) return rc;
   phase.mark("kernel timing");
@@ -1500,8 +1619,38 @@ int run_tiny(cpppd_solver *h, int64_t k) {
   return 0;
 }
 
+// small LPs: all k iterations in one launch of one thread-block cluster (k_cluster_iterate)
+int run_cluster(cpppd_solver *h, int64_t k) {
+#ifdef __CUDACC__
+  const ClusterPlan &P = h->cluster;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(P.ctas);
+  cfg.blockDim = dim3(kClusterBlock);
+  cfg.dynamicSmemBytes = P.smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = P.ctas;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
+  static const bool strict = [] { const char *e = getenv("CPPPD_CLUSTER_STRICT"); return e && atoi(e) != 0; }();
+  CK(cudaLaunchKernelEx(&cfg, strict ? k_cluster_iterate<1> : k_cluster_iterate<0>, view(h->AT), view(h->A), h->vc, h->vT, h->vlb, h->vub, h->vb, h->vsigma,
+                        h->x, h->xbar, h->y, h->n, h->m, h->m_eq, has_eq, has_ineq, h->theta, h->one_plus_theta, k, P.spc_at,
+                        P.spc_a, P.ent_at, P.ent_a));
+  h->niter += k;
+  return 0;
+#else
+  return fail(h, CPPPD_ERR_INVALID, "cluster kernel not available");
+#endif
+}
+
 int run_iterations(cpppd_solver *h, int64_t k) {
   if (h->tiny && k > 0) return run_tiny(h, k);
+  if (h->cluster.on && k > 0) return run_cluster(h, k);
   const bool use_graph = !(h->flags & CPPPD_FLAG_NO_GRAPH) && (h->world == 1 || h->p2p.active || (h->flags & CPPPD_FLAG_GRAPH_COMM));
   while (k > 0) {
     int64_t step = std::min<int64_t>(k, kGraphChunk);

@@ -84,21 +84,32 @@ __global__ void k_sort_keys(const int32_t *__restrict__ key, int64_t count, int3
                             const int64_t *__restrict__ prefix, int64_t total, int world, int keep_order,
                             uint64_t *__restrict__ out_key, uint32_t *__restrict__ out_id,
                             int32_t *__restrict__ count_per_owner, int32_t *__restrict__ eq_per_owner) {
+  // per-owner counts: one shared-memory histogram per CTA, then one global atomic per CTA and owner (a global
+  // atomicAdd per row on `world` addresses serialised 117 M updates of the 4096^2 Potts LP on 8 counters)
+  __shared__ int32_t hist[2 * kMaxWorld];
+  for (int t = threadIdx.x; t < 2 * kMaxWorld; t += blockDim.x) hist[t] = 0;
+  __syncthreads();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  int32_t q = key[i] / granule;
-  int32_t o = owner_of_bucket[q];
-  if (prefix) o = (int32_t)min((int64_t)world - 1, prefix[i] * world / total);
-  // inside a bucket, rows / columns of equal length sit together (SELL sigma-sorting: slices of
-  // 32 neighbours then have nearly equal widths and little padding)
-  int64_t len = rowptr ? rowptr[i + 1] - rowptr[i] : (int64_t)len32[i];
-  uint64_t len12 = (uint64_t)(len > 4095 ? 4095 : len);
-  uint64_t major = is_rows ? (uint64_t)o * 2 + (i >= m_eq ? 1 : 0) : (uint64_t)o;
-  // keep_order (banded operands on several GPUs): original order inside (owner, kind) — the sort is stable
-  out_key[i] = keep_order ? (major << 44) : ((major << 44) | ((uint64_t)(uint32_t)q << 12) | len12);
-  out_id[i] = (uint32_t)i;
-  atomicAdd(count_per_owner + o, 1);
-  if (is_rows && i < m_eq) atomicAdd(eq_per_owner + o, 1);
+  if (i < count) {
+    int32_t q = key[i] / granule;
+    int32_t o = owner_of_bucket[q];
+    if (prefix) o = (int32_t)min((int64_t)world - 1, prefix[i] * world / total);
+    // inside a bucket, rows / columns of equal length sit together (SELL sigma-sorting: slices of
+    // 32 neighbours then have nearly equal widths and little padding)
+    int64_t len = rowptr ? rowptr[i + 1] - rowptr[i] : (int64_t)len32[i];
+    uint64_t len12 = (uint64_t)(len > 4095 ? 4095 : len);
+    uint64_t major = is_rows ? (uint64_t)o * 2 + (i >= m_eq ? 1 : 0) : (uint64_t)o;
+    // keep_order (banded operands on several GPUs): original order inside (owner, kind) — the sort is stable
+    out_key[i] = keep_order ? (major << 44) : ((major << 44) | ((uint64_t)(uint32_t)q << 12) | len12);
+    out_id[i] = (uint32_t)i;
+    atomicAdd(hist + o, 1);
+    if (is_rows && i < m_eq) atomicAdd(hist + kMaxWorld + o, 1);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < world; t += blockDim.x) {
+    if (hist[t]) atomicAdd(count_per_owner + t, hist[t]);
+    if (eq_per_owner && hist[kMaxWorld + t]) atomicAdd(eq_per_owner + t, hist[kMaxWorld + t]);
+  }
 }
 
 __global__ void k_col_len(const int32_t *__restrict__ indices, int64_t nnz, int32_t *__restrict__ col_len) {

@@ -46,6 +46,15 @@ struct Sell {
   int idx_bits = 30, ndict = 0;
 };
 
+// One thread-block cluster carries all iterations of a small LP (cpppd_cluster.cuh)
+struct ClusterPlan {
+  bool on = false;
+  int ctas = 0;
+  int spc_at = 0, spc_a = 0;  // slices per CTA of A^T / A
+  int ent_at = 0, ent_a = 0;  // entries per CTA (max over the CTAs, multiples of 32)
+  size_t smem = 0;
+};
+
 // Window-major copy of an operand for patterns without locality (cpppd_banded.cuh)
 struct Band {
   bool built = false;   // the window-major arrays exist
@@ -161,6 +170,7 @@ struct cpppd_solver {
   int rank = 0, world = 1;
   bool identity_layout = true;  // local index == original index (one GPU, no reordering)
   bool tiny = false;            // iterations run in k_tiny_iterate (one persistent CTA)
+  ClusterPlan cluster;          // ... or in k_cluster_iterate (one persistent cluster of CTAs)
   bool balanced_split = false;  // ownership by prefix sums instead of locality buckets (see setup())
   bool dense_halo = false;      // patterns without locality: every rank keeps ghosts of ALL foreign columns / rows
   int32_t *col_old = nullptr;   // n + ghosts : original column id of a local column

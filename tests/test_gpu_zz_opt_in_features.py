@@ -1,4 +1,4 @@
-"""GPU: opt-in features that have not been measured on hardware yet (CPPPD_FLAG_TINY_PERSISTENT).
+"""GPU: the persistent kernels for small LPs (one CTA: k_tiny_iterate; one thread-block cluster: k_cluster_iterate).
 (Sorted last on purpose: with `-x` everything on the default path — golden cases, kernel variants, autotune, long rows,
 the full-size workloads — is checked first.)"""
 import numpy as np
@@ -39,6 +39,64 @@ def test_tiny_persistent_kernel_gives_the_same_bits(name):
             assert_curves_close(np.array(trace), g["trace_10"])
         finally:
             solver.close()
+
+
+@pytest.mark.parametrize("name", ["potts50", "sc105", "random_small", "random_small_alpha", "kb2", "afiro", "sc50a", "sc50b"])
+def test_cluster_persistent_kernel_gives_the_same_bits(name, monkeypatch):
+    """k_cluster_iterate (cpppd_cluster.cuh): all iterations between two stats blocks in one launch of one thread-block
+    cluster, operands and vectors in (distributed) shared memory.  Potts 50x50 takes this path by default; the
+    smaller goldens are forced onto it (CPPPD_FORCE_CLUSTER) instead of the one-CTA kernel."""
+    from pysparselp_b200 import _cabi
+    from pysparselp_b200.ChambollePockPPD import chambolle_pock_ppd
+    from test_gpu_parity import assert_curves_close
+
+    monkeypatch.setenv("CPPPD_FORCE_CLUSTER", "1")
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    for flags in (0, _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS | _cabi.FLAG_REORDER):
+        trace = []
+        x, best, solver = chambolle_pock_ppd(*args, nb_max_iter=100, nb_iter_plot=10, flags=flags, return_solver=True,
+                                             callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)),
+                                             **kw)
+        try:
+            info = solver.info()
+            assert info["tiny_persistent"] == 2 and solver.niter == 100
+            y = solver.get_y()
+            if "alpha" not in kw:
+                assert np.array_equal(x, g["x_100"]) and np.array_equal(y, gold_y(g))
+            else:
+                assert np.allclose(x, g["x_100"], rtol=1e-9, atol=0)
+            assert_curves_close(np.array(trace), g["trace_10"])
+        finally:
+            solver.close()
+
+
+def test_cluster_kernel_reproduces_the_potts50_regression_curve():
+    """reference tests/test_pott_segmentation.py through SparseLP.solve: the 55 golden curve points, with the
+    iterations between two callbacks in one launch of the cluster kernel, and against the CUDA-graph path."""
+    import json
+    import os
+    import time
+
+    from conftest import GOLDEN
+    from pysparselp_b200 import _cabi
+    from pysparselp_b200.examples.example_pott_segmentation import build_linear_program
+
+    with open(os.path.join(GOLDEN, "reference_curves.json")) as f:
+        ref = json.load(f)
+    curves, timings = {}, {}
+    for flags in (0, _cabi.FLAG_NO_TINY_PERSISTENT):
+        lp, gt, gti, _ = build_linear_program(50, 0.5, 500)
+        t0 = time.perf_counter()
+        lp.solve(method="chambolle_pock_ppd", get_timing=True, nb_iter=27500, max_time=150, ground_truth=gt,
+                 ground_truth_indices=gti, nb_iter_plot=500, flags=flags)
+        timings[flags] = time.perf_counter() - t0
+        curves[flags] = list(lp.distance_to_ground_truth)
+        assert len(curves[flags]) == 55
+        np.testing.assert_almost_equal(curves[flags], ref["potts50"][:55])
+    assert curves[0] == curves[_cabi.FLAG_NO_TINY_PERSISTENT]
+    print("Potts 50x50 regression, 27500 iterations: cluster kernel %.3f s, CUDA graphs %.3f s" % (
+        timings[0], timings[_cabi.FLAG_NO_TINY_PERSISTENT]))
 
 
 def test_tiny_persistent_kernel_reproduces_the_sc105_regression_curve():
