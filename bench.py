@@ -631,6 +631,9 @@ def run_b200(a):
                 t = torch.tensor([dt], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
+                per_rank = [None] * world
+                dist.all_gather_object(per_rank, e2e_calls)
+                e2e_calls = per_rank  # [rank][call]: one slow rank holds every other one at the next collective
             if not np.all(np.isfinite(x)):
                 raise FloatingPointError("end-to-end x holds non-finite entries")
             e2e_value = a.e2e_steps * a.e2e_iters / dt

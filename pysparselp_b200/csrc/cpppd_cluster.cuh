@@ -7,7 +7,7 @@
 // cluster owns a contiguous range of slices of A^T (columns) and of A (rows) and keeps, for the whole launch, in its
 // own shared memory: its entries of both operands, c / T / lb / ub / x / xbar of its columns, b / sigma / y of its
 // rows.  A gather of y[i] or xbar[j] is a load from the OWNER's shared memory (distributed shared memory: the index
-// words are translated once, at staging, into [owner CTA][offset]); the two halves of an iteration are separated by
+// words are translated once, at staging, into shared::cluster addresses); the two halves of an iteration are separated by
 // the hardware cluster barrier (barrier.cluster arrive.release / wait.acquire) instead of a kernel boundary.
 // Nothing touches L2 / HBM between staging and the final write-back of x, xbar, y.
 //
@@ -26,20 +26,21 @@ namespace {
 
 constexpr int kClusterBlock = 1024;
 constexpr int kClusterMaxCtas = 16;
-constexpr int64_t kClusterMaxEntries = 65536;  // padded entries per operand: beyond, a half-iteration is no longer
+constexpr int64_t kClusterMaxEntries = 131072;  // padded entries per operand: beyond, a half-iteration is no longer
                                                // latency-bound and the streaming kernels are the better shape
-constexpr int32_t kClOffMask = 0x03ffffff;     // translated entry word: [pad:1][eq:1][owner:4][offset:26]
-constexpr int kClOwnerShift = 26;
+constexpr int kClusterDefaultMode = 0;         // see cluster_barrier()
+constexpr int kClC = 4;                        // entries per chunk: gathers in flight per thread
 
 // layout of a CTA's dynamic shared memory (identical in every CTA: a remote address is the local one, mapped)
 struct ClusterSmem {
-  double *val_at, *val_a, *c, *T, *lb, *ub, *x, *xbar, *b, *sigma, *y;
-  int32_t *w_at, *w_a, *sp_at, *sp_a;
+  double *val_at, *val_a, *c, *T, *lb, *ub, *x, *xbar, *b, *sigma, *y, *zero;
+  uint32_t *w_at, *w_a;
+  int32_t *sp_at, *sp_a;
 };
 
 inline __host__ __device__ size_t cluster_smem_bytes(int spc_at, int spc_a, int ent_at, int ent_a) {
   const size_t cols = (size_t)spc_at * 32, rows = (size_t)spc_a * 32;
-  return 8 * ((size_t)ent_at + ent_a + 6 * cols + 3 * rows) + 4 * ((size_t)ent_at + ent_a + spc_at + spc_a + 2) + 16;
+  return 8 * ((size_t)ent_at + ent_a + 6 * cols + 3 * rows + 2) + 4 * ((size_t)ent_at + ent_a + spc_at + spc_a + 2) + 16;
 }
 
 #ifdef __CUDACC__
@@ -60,49 +61,89 @@ __device__ __forceinline__ ClusterSmem cluster_carve(unsigned char *base, int sp
   S.b = d; d += rows;
   S.sigma = d; d += rows;
   S.y = d; d += rows;
-  int32_t *w = reinterpret_cast<int32_t *>(d);
+  S.zero = d; d += 2;
+  uint32_t *w = reinterpret_cast<uint32_t *>(d);
   S.w_at = w; w += ent_at;
   S.w_a = w; w += ent_a;
-  S.sp_at = w; w += spc_at + 1;
-  S.sp_a = w;
+  int32_t *sp = reinterpret_cast<int32_t *>(w);
+  S.sp_at = sp; sp += spc_at + 1;
+  S.sp_a = sp;
   return S;
 }
 
-// entries of the slices [s_lo, s_hi) of S into shared memory: value, and the index word translated to
-// [pad][eq][owner CTA of the gathered element][offset inside the owner's vector]
-__device__ __forceinline__ void cluster_stage(const SellView &S, int64_t s_lo, int64_t s_hi, int spc_other, double *val,
-                                              int32_t *w, int32_t *sp) {
-  int64_t e_lo, e_hi, tmp;
-  slice_range(S, s_lo, e_lo, tmp);
-  if (s_hi > s_lo) slice_range(S, s_hi - 1, tmp, e_hi); else e_hi = e_lo;
-  for (int64_t s = s_lo + threadIdx.x; s <= s_hi; s += blockDim.x) {
-    int64_t p0, p1;
-    if (s < s_hi) slice_range(S, s, p0, p1); else p0 = e_hi;
-    sp[s - s_lo] = (int32_t)(p0 - e_lo);
-  }
-  const int32_t per_owner = spc_other * 32;
-  for (int64_t e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
-    const int32_t word = S.idx[e];
-    int32_t out = kPad;
-    double a = 0.0;
-    if (word >= 0) {
-      a = entry_value(S, e, word);
-      const int32_t i = word & S.idx_mask;
-      const int32_t owner = i / per_owner;
-      out = (word & kEqBit) | (owner << kClOwnerShift) | (i - owner * per_owner);
+// 32-bit shared::cluster address of `local` (an address in this CTA's shared window) inside CTA `rank`
+__device__ __forceinline__ uint32_t cluster_map(uint32_t local, int rank) {
+  uint32_t out;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(local), "r"(rank));
+  return out;
+}
+// generic address of a shared::cluster address: (shared window base, constant for the kernel) | 32-bit address
+__device__ __forceinline__ uint64_t cluster_generic_base(uint32_t some_cluster_addr) {
+  uint64_t gen;
+  asm("cvta.shared::cluster.u64 %0, %1;" : "=l"(gen) : "l"((uint64_t)some_cluster_addr));
+  return gen & 0xffffffff00000000ull;
+}
+__device__ __forceinline__ double cluster_load(uint64_t base, uint32_t addr) {
+  double v;
+  asm volatile("ld.f64 %0, [%1];" : "=d"(v) : "l"(base | addr) : "memory");
+  return v;
+}
+
+// Entries of the slices [s_lo, s_hi) of S into shared memory: the value, and the index word translated ONCE into
+// the shared::cluster address of the gathered element inside its owner CTA (mapa) — a gather in the loop is then
+// one load, no owner / offset arithmetic.  The addresses are 8-byte aligned: bit 0 carries the equality flag.
+// Every slice is staged with its width rounded up to a whole number of chunks of kClC entries, and every padding
+// entry (the SELL padding of shorter rows and the chunk padding) becomes value 0.0 x the address of a zero in this
+// CTA's own shared memory: the loops then need no bounds or validity tests, and the iterates keep their bits — a
+// partial sum starts at +0.0 and can never become -0.0, so adding the +0.0 of a padding entry changes nothing.
+__device__ __forceinline__ void cluster_stage(const SellView &S, int64_t s_lo, int64_t s_hi, int spc_other,
+                                              const double *gathered_vec, const double *zero, int me, double *val,
+                                              uint32_t *w, int32_t *sp) {
+  if (threadIdx.x == 0) {  // local offsets of the padded slices (at most a few dozen per CTA)
+    int32_t off = 0;
+    for (int64_t s = s_lo; s < s_hi; ++s) {
+      int64_t p0, p1;
+      slice_range(S, s, p0, p1);
+      sp[s - s_lo] = off;
+      off += (int32_t)(((p1 - p0) / 32 + kClC - 1) / kClC * kClC * 32);
     }
-    val[e - e_lo] = a;
-    w[e - e_lo] = out;
+    sp[s_hi - s_lo] = off;
+  }
+  __syncthreads();
+  const int32_t per_owner = spc_other * 32;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(gathered_vec);
+  const uint32_t pad_word = cluster_map((uint32_t)__cvta_generic_to_shared(zero), me);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int64_t s = s_lo + warp; s < s_hi; s += nwarps) {
+    int64_t p0, p1;
+    slice_range(S, s, p0, p1);
+    const int width = (int)((p1 - p0) >> 5), padded = (sp[s - s_lo + 1] - sp[s - s_lo]) >> 5;
+    for (int k = 0; k < padded; ++k) {
+      uint32_t out = pad_word;
+      double a = 0.0;
+      if (k < width) {
+        const int64_t e = p0 + (int64_t)k * 32 + lane;
+        const int32_t word = S.idx[e];
+        if (word >= 0) {
+          a = entry_value(S, e, word);
+          const int32_t i = word & S.idx_mask;
+          const int32_t owner = i / per_owner;
+          out = cluster_map(base + 8u * (uint32_t)(i - owner * per_owner), owner) | ((word & kEqBit) ? 1u : 0u);
+        }
+      }
+      val[sp[s - s_lo] + k * 32 + lane] = a;
+      w[sp[s - s_lo] + k * 32 + lane] = out;
+    }
   }
 }
 
 // The barrier between the two halves of an iteration.  What has to be ordered is: my st.shared of xbar / y, then the
 // other CTAs' loads of it from my shared memory after the barrier.  barrier.cluster.arrive.release compiles to
 // MEMBAR.ALL.GPU + UCGABAR_ARV (cuobjdump): a GPU-scope fence, twice per iteration, for data that never leaves shared
-// memory — measured 3.3 us per iteration of the Potts 50x50 LP.  kStrict == 0 uses membar.cta + the RELAXED arrive
-// instead: shared memory has one physical copy (no cache in front of it), so once the store is performed at CTA
-// scope a later load through the cluster network reads it; the wait keeps its acquire form, the loads after it are
-// issued in program order.  kStrict == 1 (CPPPD_CLUSTER_STRICT=1) keeps release / acquire.
+// memory (measured: 10 % of the iteration time of the Potts 50x50 LP).  kStrict == 0 uses membar.cta + the RELAXED
+// arrive instead: shared memory has one physical copy (no cache in front of it), so once the store is performed at
+// CTA scope a later load through the cluster network reads it; the wait keeps its acquire form, the loads after it
+// are issued in program order.  kStrict == 1 (CPPPD_CLUSTER_MODE=1) keeps release / acquire.
 template <int kStrict>
 __device__ __forceinline__ void cluster_barrier() {
   if (kStrict) {
@@ -114,14 +155,80 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
-// element `word & kClOffMask` of the owner's copy of `vec`: own shared memory when this CTA is the owner
-__device__ __forceinline__ double cluster_gather(cg::cluster_group &cluster, double *vec, int me, int32_t word) {
-  const int owner = (word >> kClOwnerShift) & 15;
-  const int off = word & kClOffMask;
-  return owner == me ? vec[off] : cluster.map_shared_rank(vec, owner)[off];
+// per-column / per-row constants and state of one thread
+struct ClusterCol { double c, T, lb, ub, x; int q0, width; bool live; };   // width: padded, a multiple of kClC
+struct ClusterRow { double b, sigma, y; int q0, width; bool live, ineq; };
+
+// primal half for one column (:198-228): same operations, same order as primal_rows / primal_sums<_, 0>
+// (kEq false: the LP has no equality row, no entry carries the flag)
+template <bool kEq>
+__device__ __forceinline__ void cluster_primal(const ClusterSmem &S, uint64_t gbase, ClusterCol &C, int jl, int has_eq,
+                                               int has_ineq, double theta, double one_plus_theta) {
+  double s_eq = 0.0, s_in = 0.0;
+#pragma unroll 1
+  for (int k0 = 0; k0 < C.width; k0 += kClC) {
+    uint32_t w[kClC];
+    double a[kClC], g[kClC];
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) w[u] = S.w_at[C.q0 + (k0 + u) * 32];
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) g[u] = cluster_load(gbase, kEq ? (w[u] & ~1u) : w[u]);
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) a[u] = S.val_at[C.q0 + (k0 + u) * 32];
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) {
+      const double t = __dmul_rn(a[u], g[u]);
+      if (kEq && (w[u] & 1u)) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
+    }
+  }
+  if (!C.live) return;
+  double d = C.c;
+  if (has_eq) d = __dadd_rn(d, s_eq);
+  if (has_ineq) d = __dadd_rn(d, s_in);
+  double x2 = __dsub_rn(C.x, __dmul_rn(C.T, d));
+  x2 = (C.lb > x2) ? C.lb : x2;
+  x2 = (C.ub < x2) ? C.ub : x2;
+  S.xbar[jl] = __dsub_rn(__dmul_rn(one_plus_theta, x2), __dmul_rn(theta, C.x));
+  C.x = x2;
 }
 
-template <int kStrict>
+// dual half for one row (:231-240, :333-341): same operations, same order as dual_rows / dual_sum<_, 0>
+__device__ __forceinline__ void cluster_dual(const ClusterSmem &S, uint64_t gbase, ClusterRow &R, int il) {
+  double acc = 0.0;
+#pragma unroll 1
+  for (int k0 = 0; k0 < R.width; k0 += kClC) {
+    uint32_t w[kClC];
+    double a[kClC], g[kClC];
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) w[u] = S.w_a[R.q0 + (k0 + u) * 32];
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) g[u] = cluster_load(gbase, w[u]);
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) a[u] = S.val_a[R.q0 + (k0 + u) * 32];
+#pragma unroll
+    for (int u = 0; u < kClC; ++u) acc = __dadd_rn(acc, __dmul_rn(a[u], g[u]));
+  }
+  if (!R.live) return;
+  const double r = __dsub_rn(acc, R.b);
+  double yn = __dadd_rn(R.y, __dmul_rn(R.sigma, r));
+  if (R.ineq) yn = (yn < 0.0) ? 0.0 : yn;
+  R.y = yn;
+  S.y[il] = yn;
+}
+
+__device__ __forceinline__ ClusterCol cluster_col(const ClusterSmem &S, int sl, int lane, bool live) {
+  const int jl = sl * 32 + lane;
+  return ClusterCol{S.c[jl], S.T[jl], S.lb[jl], S.ub[jl], S.x[jl], S.sp_at[sl] + lane, (S.sp_at[sl + 1] - S.sp_at[sl]) >> 5, live};
+}
+__device__ __forceinline__ ClusterRow cluster_row(const ClusterSmem &S, int sl, int lane, bool live, bool ineq) {
+  const int il = sl * 32 + lane;
+  return ClusterRow{S.b[il], S.sigma[il], S.y[il], S.sp_a[sl] + lane, (S.sp_a[sl + 1] - S.sp_a[sl]) >> 5, live, ineq};
+}
+
+// kOnePass: every CTA has at most one slice of A^T and one of A per warp — a thread keeps its column and its row
+// (constants, x, y, entry offsets) in registers for the whole launch.  Otherwise the warps stride over the slices and
+// reload them from shared memory every iteration.
+template <int kStrict, bool kOnePass>
 __global__ void __launch_bounds__(kClusterBlock, 1)
 k_cluster_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, Vec sigma, double *x, double *xbar, double *y,
                   int64_t n, int64_t m, int64_t m_eq, int has_eq, int has_ineq, double theta, double one_plus_theta,
@@ -136,8 +243,10 @@ k_cluster_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, 
   const int64_t r_lo = min((int64_t)me * spc_a, A.nslices), r_hi = min(r_lo + spc_a, A.nslices);
   const int ncs = (int)(c_hi - c_lo), nrs = (int)(r_hi - r_lo);
   // ---- staging
-  cluster_stage(AT, c_lo, c_hi, spc_a, S.val_at, S.w_at, S.sp_at);   // A^T gathers y: owners by row slices
-  cluster_stage(A, r_lo, r_hi, spc_at, S.val_a, S.w_a, S.sp_a);      // A gathers xbar: owners by column slices
+  if (threadIdx.x < 2) S.zero[threadIdx.x] = 0.0;
+  cluster_stage(AT, c_lo, c_hi, spc_a, S.y, S.zero, me, S.val_at, S.w_at, S.sp_at);    // A^T gathers y: owners by row slices
+  cluster_stage(A, r_lo, r_hi, spc_at, S.xbar, S.zero, me, S.val_a, S.w_a, S.sp_a);    // A gathers xbar: owners by column slices
+  const uint64_t gbase = cluster_generic_base(cluster_map((uint32_t)__cvta_generic_to_shared(S.zero), me));
   for (int t = threadIdx.x; t < spc_at * 32; t += blockDim.x) {
     const int64_t j = c_lo * 32 + t;
     const bool live = t < ncs * 32 && j < n;
@@ -156,72 +265,38 @@ k_cluster_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, 
     S.y[t] = live ? y[i] : 0.0;
   }
   cluster.sync();
-  // gathers in flight per thread: a whole pixel column of the Potts LP (8 entries) / a whole row (3) in one round trip
-  constexpr int kCP = 8, kCD = 4;
-  for (int64_t it = 0; it < iters; ++it) {
-    // ---- primal half (:198-228): column sums of A against y (remote shared memory), fused epilogue
-    for (int sl = warp; sl < ncs; sl += nwarps) {
-      const int q0 = S.sp_at[sl] + lane, width = (S.sp_at[sl + 1] - S.sp_at[sl]) >> 5;
-      double s_eq = 0.0, s_in = 0.0;
-#pragma unroll 1
-      for (int k0 = 0; k0 < width; k0 += kCP) {
-        int32_t w[kCP];
-        double g[kCP];
-#pragma unroll
-        for (int u = 0; u < kCP; ++u) w[u] = k0 + u < width ? S.w_at[q0 + (k0 + u) * 32] : kPad;
-#pragma unroll
-        for (int u = 0; u < kCP; ++u) g[u] = w[u] >= 0 ? cluster_gather(cluster, S.y, me, w[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < kCP; ++u)
-          if (w[u] >= 0) {
-            const double t = __dmul_rn(S.val_at[q0 + (k0 + u) * 32], g[u]);
-            if (w[u] & kEqBit) s_eq = __dadd_rn(s_eq, t); else s_in = __dadd_rn(s_in, t);
-          }
-      }
-      const int jl = sl * 32 + lane;
-      if (c_lo * 32 + jl < n) {
-        const double xo = S.x[jl];
-        double d = S.c[jl];
-        if (has_eq) d = __dadd_rn(d, s_eq);
-        if (has_ineq) d = __dadd_rn(d, s_in);
-        const double l = S.lb[jl], u = S.ub[jl];
-        double x2 = __dsub_rn(xo, __dmul_rn(S.T[jl], d));
-        x2 = (l > x2) ? l : x2;
-        x2 = (u < x2) ? u : x2;
-        S.xbar[jl] = __dsub_rn(__dmul_rn(one_plus_theta, x2), __dmul_rn(theta, xo));
-        S.x[jl] = x2;
-      }
+  if (kOnePass) {
+    const bool has_col = warp < ncs, has_row = warp < nrs;
+    ClusterCol C = cluster_col(S, has_col ? warp : 0, lane, has_col && c_lo * 32 + warp * 32 + lane < n);
+    ClusterRow R = cluster_row(S, has_row ? warp : 0, lane, has_row && r_lo * 32 + warp * 32 + lane < m,
+                               r_lo * 32 + warp * 32 + lane >= m_eq);
+    if (!has_col) C.width = 0;
+    if (!has_row) R.width = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+      if (has_eq) cluster_primal<true>(S, gbase, C, warp * 32 + lane, has_eq, has_ineq, theta, one_plus_theta);
+      else cluster_primal<false>(S, gbase, C, warp * 32 + lane, has_eq, has_ineq, theta, one_plus_theta);
+      cluster_barrier<kStrict>();
+      cluster_dual(S, gbase, R, warp * 32 + lane);
+      cluster_barrier<kStrict>();
     }
-    cluster_barrier<kStrict>();
-    // ---- dual half (:231-240, :333-341): row sums of A against xbar, fused epilogue
-    for (int sl = warp; sl < nrs; sl += nwarps) {
-      const int q0 = S.sp_a[sl] + lane, width = (S.sp_a[sl + 1] - S.sp_a[sl]) >> 5;
-      double acc = 0.0;
-#pragma unroll 1
-      for (int k0 = 0; k0 < width; k0 += kCD) {
-        int32_t w[kCD];
-        double a[kCD], g[kCD];
-#pragma unroll
-        for (int u = 0; u < kCD; ++u) w[u] = k0 + u < width ? S.w_a[q0 + (k0 + u) * 32] : kPad;
-#pragma unroll
-        for (int u = 0; u < kCD; ++u) g[u] = w[u] >= 0 ? cluster_gather(cluster, S.xbar, me, w[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < kCD; ++u) a[u] = k0 + u < width ? S.val_a[q0 + (k0 + u) * 32] : 0.0;
-#pragma unroll
-        for (int u = 0; u < kCD; ++u)
-          if (w[u] >= 0) acc = __dadd_rn(acc, __dmul_rn(a[u], g[u]));
+    if (C.live) S.x[warp * 32 + lane] = C.x;
+  } else {
+    for (int64_t it = 0; it < iters; ++it) {
+      for (int sl = warp; sl < ncs; sl += nwarps) {
+        ClusterCol C = cluster_col(S, sl, lane, c_lo * 32 + sl * 32 + lane < n);
+        if (has_eq) cluster_primal<true>(S, gbase, C, sl * 32 + lane, has_eq, has_ineq, theta, one_plus_theta);
+        else cluster_primal<false>(S, gbase, C, sl * 32 + lane, has_eq, has_ineq, theta, one_plus_theta);
+        if (C.live) S.x[sl * 32 + lane] = C.x;
       }
-      const int il = sl * 32 + lane;
-      const int64_t i = r_lo * 32 + il;
-      if (i < m) {
-        const double r = __dsub_rn(acc, S.b[il]);
-        double yn = __dadd_rn(S.y[il], __dmul_rn(S.sigma[il], r));
-        if (i >= m_eq) yn = (yn < 0.0) ? 0.0 : yn;
-        S.y[il] = yn;
+      cluster_barrier<kStrict>();
+      for (int sl = warp; sl < nrs; sl += nwarps) {
+        ClusterRow R = cluster_row(S, sl, lane, r_lo * 32 + sl * 32 + lane < m, r_lo * 32 + sl * 32 + lane >= m_eq);
+        cluster_dual(S, gbase, R, sl * 32 + lane);
       }
+      cluster_barrier<kStrict>();
     }
-    cluster_barrier<kStrict>();
   }
+  __syncthreads();
   // ---- write-back
   for (int t = threadIdx.x; t < ncs * 32; t += blockDim.x) {
     const int64_t j = c_lo * 32 + t;

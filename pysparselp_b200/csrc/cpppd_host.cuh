@@ -654,6 +654,13 @@ int setup_fused(cpppd_solver *h, const std::vector<int64_t> &dst_base_x, const s
   return 0;
 }
 
+#ifdef __CUDACC__
+inline auto cluster_kernel(bool strict, bool one_pass) {
+  if (strict) return one_pass ? k_cluster_iterate<1, true> : k_cluster_iterate<1, false>;
+  return one_pass ? k_cluster_iterate<0, true> : k_cluster_iterate<0, false>;
+}
+#endif
+
 // Can one thread-block cluster carry this LP (cpppd_cluster.cuh)?  Fills h->cluster.
 int plan_cluster(cpppd_solver *h) {
   h->cluster = ClusterPlan();
@@ -675,7 +682,7 @@ int plan_cluster(cpppd_solver *h) {
   }
   int max_smem = 0;
   CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-  auto kernel = k_cluster_iterate<0>;
+  auto kernel = cluster_kernel(false, false);
   for (int ctas : {kClusterMaxCtas, 8}) {
     ClusterPlan P;
     P.ctas = ctas;
@@ -686,7 +693,9 @@ int plan_cluster(cpppd_solver *h) {
       const int64_t ns = ops[k]->nslices, spc = k ? P.spc_a : P.spc_at;
       for (int r = 0; r < ctas; ++r) {
         const int64_t lo = std::min<int64_t>(r * spc, ns), hi = std::min<int64_t>(lo + spc, ns);
-        ent[k] = std::max(ent[k], sp[k][hi] - sp[k][lo]);
+        int64_t padded = 0;  // every slice is staged with its width rounded up to whole chunks of kClC entries
+        for (int64_t q = lo; q < hi; ++q) padded += ((sp[k][q + 1] - sp[k][q]) / 32 + kClC - 1) / kClC * kClC * 32;
+        ent[k] = std::max(ent[k], padded);
       }
     }
     P.ent_at = (int)ent[0];
@@ -694,7 +703,7 @@ int plan_cluster(cpppd_solver *h) {
     P.smem = cluster_smem_bytes(P.spc_at, P.spc_a, P.ent_at, P.ent_a);
     if ((int64_t)P.smem > max_smem) continue;
     bool attr_ok = true;
-    for (auto fn : {k_cluster_iterate<0>, k_cluster_iterate<1>})
+    for (auto fn : {cluster_kernel(false, false), cluster_kernel(false, true), cluster_kernel(true, false), cluster_kernel(true, true)})
       attr_ok = attr_ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
                 (ctas <= 8 || cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess);
     if (!attr_ok) {
@@ -789,6 +798,18 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   if (nnz) k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, entry_id);
 
   bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
+#ifdef __CUDACC__
+  // Small LPs that may run in one thread-block cluster (cpppd_cluster.cuh) are renumbered by locality: a CTA of the
+  // cluster then owns rows AND the columns they touch, most gathers stay in its own shared memory, and the cluster
+  // network — which bounds the kernel otherwise — carries a fraction of them (Potts 50x50: 404 000 -> 794 000 it/s).
+  {
+    static const bool no_cluster = [] { const char *e = getenv("CPPPD_NO_CLUSTER"); return e && atoi(e) != 0; }();
+    const bool forced = h->variant_request != 0 || (getenv("CPPPD_KERNEL_VARIANT") && atoi(getenv("CPPPD_KERNEL_VARIANT")));
+    if (N == 1 && nnz > 0 && nnz <= kClusterMaxEntries && !no_cluster && !forced &&
+        !(h->flags & (CPPPD_FLAG_NO_REORDER | CPPPD_FLAG_NO_TINY_PERSISTENT | CPPPD_FLAG_BANDED)))
+      reorder = true;
+  }
+#endif
   // Banded operands (cpppd_banded.cuh) keep the caller's numbering: the window order along a row is what keeps
   // the sums bit-exact.  Candidates: forced by flag, or a pattern without locality over vectors of several windows.
   // With more than one GPU they need the balanced split in original order (decided below): windows are ranges of
@@ -1267,13 +1288,11 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
             std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
   // ... a cluster of up to 16 CTAs when they fit the shared memory of 16 SMs (see k_cluster_iterate);
   // CPPPD_FORCE_CLUSTER=1 (tests): also the LPs that would fit one CTA
-  // An LP that fits one CTA but needs more than one pass of its 1024 threads is faster on the cluster as well
-  // (Potts 24x24, 1 680 x 2 208: 131 000 it/s in one CTA, 177 000 through CUDA graphs, 575 000 in the cluster; SC105,
-  // 103 x 105: 801 000 in one CTA, 734 000 in the cluster — profiles/r02_kernels.md)
+  // The cluster kernel is the faster one whenever it can be launched (SC105, 103 x 105: 801 000 it/s in one CTA,
+  // 1 116 000 in the cluster; Potts 24x24: 131 000 / 961 000 — profiles/r02_kernels.md): the one-CTA kernel remains for
+  // devices / LPs where the cluster launch is refused and for an explicit CPPPD_FLAG_TINY_PERSISTENT.
   const bool was_tiny = h->tiny;
-  if (h->tiny && std::max(nloc, mloc) > kTinyBlock) h->tiny = false;
-  if (const char *e = getenv("CPPPD_FORCE_CLUSTER"))
-    if (atoi(e) != 0) h->tiny = false;
+  if (!(h->flags & CPPPD_FLAG_TINY_PERSISTENT)) h->tiny = false;
   if (!h->tiny && !(h->flags & CPPPD_FLAG_NO_TINY_PERSISTENT) && !variant_forced && N == 1 && h->longA.count == 0 &&
       h->longAT.count == 0 && !h->bandA.built && !h->bandAT.built)
     if (int rc = plan_cluster(h)) return rc;
@@ -1637,8 +1656,11 @@ int run_cluster(cpppd_solver *h, int64_t k) {
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   const int has_eq = h->m_eq_glob > 0, has_ineq = h->m_ineq_glob > 0;
-  static const bool strict = [] { const char *e = getenv("CPPPD_CLUSTER_STRICT"); return e && atoi(e) != 0; }();
-  CK(cudaLaunchKernelEx(&cfg, strict ? k_cluster_iterate<1> : k_cluster_iterate<0>, view(h->AT), view(h->A), h->vc, h->vT, h->vlb, h->vub, h->vb, h->vsigma,
+  const char *mode_env = getenv("CPPPD_CLUSTER_MODE");  // 0: relaxed barrier arrive, 1: release / acquire
+  const int mode = mode_env ? atoi(mode_env) : kClusterDefaultMode;
+  const bool one_pass = std::max(P.spc_at, P.spc_a) <= kClusterBlock / 32;
+  auto kernel = cluster_kernel(mode != 0, one_pass);
+  CK(cudaLaunchKernelEx(&cfg, kernel, view(h->AT), view(h->A), h->vc, h->vT, h->vlb, h->vub, h->vb, h->vsigma,
                         h->x, h->xbar, h->y, h->n, h->m, h->m_eq, has_eq, has_ineq, h->theta, h->one_plus_theta, k, P.spc_at,
                         P.spc_a, P.ent_at, P.ent_a));
   h->niter += k;

@@ -10,7 +10,7 @@ echo "pytest exit $?"; tail -4 $out/${tag}_pytest_gpu.log
 timeout 300 python tools/small_bench.py > $out/${tag}_small.jsonl 2> $out/${tag}_small.err
 echo "small exit $?"; cat $out/${tag}_small.jsonl | cut -c1-420; tail -3 $out/${tag}_small.err
 echo "-- strict barrier"
-CPPPD_CLUSTER_STRICT=1 timeout 300 python tools/small_bench.py 5000 2>&1 | tail -5 | tee $out/${tag}_small_strict.jsonl
+CPPPD_CLUSTER_MODE=1 timeout 300 python tools/small_bench.py 5000 2>&1 | tail -5 | tee $out/${tag}_small_strict.jsonl
 echo "-- cluster forced"
 CPPPD_FORCE_CLUSTER=1 timeout 300 python tools/small_bench.py 5000 2>&1 | tail -7 | cut -c1-420 | tee $out/${tag}_small_forced.jsonl
 echo "-- setup phases (flags 8: reordered layout on one GPU)"

@@ -49,7 +49,7 @@ def short(name):
     if m:
         return "%s<%s>" % (m.group(1), m.group(2).replace(" ", "").replace("(bool)", ""))
     for k in ("k_stats_rows", "k_stats_cols", "k_stats_final", "k_precond", "k_fill_sell", "k_push", "k_wait", "k_long_partial",
-              "k_long_finish", "k_tiny_iterate"):
+              "k_long_finish", "k_tiny_iterate", "k_cluster_iterate"):
         if k in name:
             return k
     return name.split("(")[0][-60:]

@@ -11,7 +11,7 @@ for _ in range(2):
     print(json.dumps(bench.small_configs(a, generators, make_solver)), flush=True)
 for size in (24, 50, 64, 72, 96):
     out = {"potts": size}
-    for label, flags in (("cuda_graphs", 4096), ("persistent", 0)):
+    for label, flags in (("cuda_graphs", 4096), ("persistent", 0), ("persistent_reorder", 8)):
         s = make_solver(*generators.lp_args(generators.potts_lp(size)), flags=flags)
         s.iterate(2000); s.sync()
         out[label] = round(5000 / (s.time_iterations(5000) * 1e-3))
