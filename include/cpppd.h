@@ -94,7 +94,8 @@ enum {
   CPPPD_FLAG_FUSED_HALO = 1u << 7,
   /* never time the kernel variants at creation: use variant 1 (see cpppd_problem.kernel_variant) */
   CPPPD_FLAG_NO_AUTOTUNE = 1u << 8,
-  /* (accepted for compatibility: this is the default now, see CPPPD_FLAG_NO_TINY_PERSISTENT) */
+  /* small LPs: prefer the one-CTA persistent kernel (k_tiny_iterate) over the thread-block-cluster kernel when the LP
+   * fits one SM (see CPPPD_FLAG_NO_TINY_PERSISTENT for what runs by default) */
   CPPPD_FLAG_TINY_PERSISTENT = 1u << 9,
   /* one GPU, caller's numbering: store A and A^T window-major ("banded") and run one launch per window of the
    * gathered vector, so that the gathers of a launch stay inside a window that fits the L2 (cpppd_banded.cuh).
@@ -105,11 +106,14 @@ enum {
   CPPPD_FLAG_BANDED = 1u << 10,
   /* never build the banded copies */
   CPPPD_FLAG_NO_BANDED = 1u << 11,
-  /* One GPU, LPs whose operands fit the L1 of one SM (n, m <= 4096 and <= 16384 stored entries in A and A^T together,
-   * e.g. netlib SC105) and no forced kernel variant: cpppd_iterate(k) runs all k iterations in ONE launch of one CTA
-   * (k_tiny_iterate) instead of 2k graph nodes — such LPs are bound by launch latency, not bandwidth (SC105 on a B200:
-   * 800 000 iterations/s against 189 000 through CUDA graphs).  Same per-row code, same bits.  This flag keeps the
-   * graph path. */
+  /* One GPU, small LPs, no forced kernel variant: cpppd_iterate(k) runs all k iterations in ONE launch instead of 2k
+   * graph nodes — such LPs are bound by launch latency, not bandwidth.  LPs whose operands and vectors fit the shared
+   * memory of 16 SMs (<= 131072 stored entries per operand) run in one thread-block cluster of 16 CTAs, gathers
+   * through distributed shared memory, the hardware cluster barrier between the two halves of an iteration
+   * (k_cluster_iterate, csrc/cpppd_cluster.cuh: Potts 50x50 793 000 iterations/s against 144 000 through CUDA graphs,
+   * netlib SC105 1 130 000 against 211 000); such LPs are renumbered by locality like CPPPD_FLAG_REORDER.  Where the
+   * cluster launch is refused, LPs that fit one SM (n, m <= 4096, <= 16384 stored entries) run in one CTA
+   * (k_tiny_iterate).  Same per-row arithmetic, same bits.  This flag keeps the graph path. */
   CPPPD_FLAG_NO_TINY_PERSISTENT = 1u << 12,
   /* world_size > 1, patterns without locality (balanced split + banded operands): keep only the ghosts the pattern
    * really touches and push them through index lists, instead of the dense halo (every foreign column / row is a
@@ -219,7 +223,8 @@ typedef struct {
   int64_t long_entries;         /* their entries */
   int32_t balanced_split;       /* world_size > 1: the locality buckets left some rank with more than 1.5x its share of
                                    the row or column entries, so rows / columns were dealt out by prefix sums instead */
-  int32_t tiny_persistent;      /* iterations run in one persistent CTA (CPPPD_FLAG_TINY_PERSISTENT and a tiny LP) */
+  int32_t tiny_persistent;      /* iterations run in a persistent kernel: 1 one CTA (k_tiny_iterate), 2 one thread-block
+                                   cluster (k_cluster_iterate); 0: CUDA graphs of k_primal / k_dual */
   /* banded operands (CPPPD_FLAG_BANDED; [0]: A, used by the dual half, [1]: A^T, used by the primal half) */
   int32_t band_windows[2];      /* windows of the gathered vector (= launches per half-iteration); 0: not built */
   int32_t band_in_use[2];       /* the half-iteration runs the banded kernels */
