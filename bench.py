@@ -7,8 +7,9 @@ Headline workload (N = 1 and N > 1 alike): the synthetic 4096x4096 Potts-segment
 BASELINE.json configs[4] (n = 50 323 456, m = 67 092 480, nnz = 201 277 440), fp64.
 ``--workload random`` makes BASELINE configs[3] the headline instead (randomLP.py family: 20 M variables, 40 M
 inequality rows, exactly 8 entries per row, 320 M entries), ``--workload l1svm`` the configs[2] family (``--size``
-samples x 1 000 features).  On one GPU the default run also measures the random LP after the headline and reports it
-under ``secondary_workloads`` (device-resident iterations/s, per-half-iteration times, roofline, storage chosen).
+samples x 1 000 features).  The default run also measures, after the headline, the random LP (any N: with N > 1 its
+distributed solve) and — one GPU — the L1-SVM LP with 100 000 samples, and reports them under ``secondary_workloads``
+(device-resident iterations/s, per-half-iteration times, roofline, storage chosen, parity verdict).
 A *step* is ``--iters-per-step`` (default 50) solver iterations — one pass of the hot path
 (A^T y + primal update, A xbar + dual update) over the whole LP per iteration.
 
@@ -21,7 +22,8 @@ A *step* is ``--iters-per-step`` (default 50) solver iterations — one pass of 
 * ``with_stats_block``: iterations/s of the same resident loop with the reference's stats block every
                 ``--stats-interval`` (500) iterations.
 * ``latency_bound_configs``: iterations/s of BASELINE.json's two small configs (Potts 50x50, netlib SC105), which fit
-                the caches and are bound by launch latency, not bandwidth (extra information, N = 1).
+                the caches and are bound by launch latency, not bandwidth (extra information, N = 1): CUDA graphs
+                against the persistent kernel (one thread-block cluster).
 * ``roofline``: algorithmic bytes of the dominant kernel / its CUDA-event time,
                 against MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s).
 * ``parity``  : x and y of a fresh solver after 6 iterations, sha256, against the digest the plain-C oracle port
@@ -466,8 +468,11 @@ def storage_summary(info, t_build, t_setup):
                        "sectors_per_gather": info["band_sectors_per_gather"]}}
 
 
-def secondary_workload(kind, size, a, torch, local_rank, make_solver, chambolle_pock_ppd, peak, peak_src):
-    """Device-resident measurement of another BASELINE config on one GPU (after the headline, own roofline)."""
+def secondary_workload(kind, size, a, torch, local_rank, make_solver, chambolle_pock_ppd, peak, peak_src, dist=None,
+                       world=1):
+    """Device-resident measurement of another BASELINE config (after the headline, own roofline).  One GPU: also the
+    SELL kernels beside the banded ones (random LP) and one end-to-end call.  N GPUs (every rank calls this): the
+    distributed solve of the same LP, device-timed as the max over ranks, with its parity verdict."""
     from pysparselp_b200 import generators
 
     t0 = time.perf_counter()
@@ -481,19 +486,25 @@ def secondary_workload(kind, size, a, torch, local_rank, make_solver, chambolle_
     try:
         info = solver.info()
         steps = max(2, a.steps // 4)
-        ms, clocks = time_resident(solver, a, torch, None, local_rank, steps, 3)
+        ms, clocks = time_resident(solver, a, torch, dist, local_rank, steps, 3)
         its = steps * a.iters_per_step / (ms * 1e-3)
-        out.update({"value": its, "unit": UNIT, "steps": steps, "warmup": 3, "ms_per_step": ms / steps, "clocks": clocks,
-                    "roofline": roofline_block(solver, info, its, 1, peak, peak_src),
+        out.update({"value": its, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": ms / steps,
+                    "clocks": clocks, "roofline": roofline_block(solver, info, its, world, peak, peak_src),
                     "kernel_variants": kernel_variants(info), "problem": storage_summary(info, t_build, t_setup)})
     finally:
         solver.close()
     out["parity"] = parity_check(make_solver, args, workload_name(kind, size), a.flags)
+    if world > 1:
+        out["partition"] = {k: info[k] for k in ("n_local", "m_local", "n_ghost", "m_ghost", "halo_send_bytes_per_iteration",
+                                                 "balanced_split")}
+        del lp, keep
+        return out
     # the SELL kernels on the same LP (what ran before the banded operands existed)
-    try:
-        out["sell_kernels"] = time_variant(make_solver, args, a.flags | 2048, a.iters_per_step // 2, peak)
-    except Exception as e:
-        out["sell_kernels"] = {"error": repr(e)}
+    if kind == "random":
+        try:
+            out["sell_kernels"] = time_variant(make_solver, args, a.flags | 2048, a.iters_per_step // 2, peak)
+        except Exception as e:
+            out["sell_kernels"] = {"error": repr(e)}
     # end to end, one call: upload from pinned host memory, build both operand forms, iterate, read x back
     try:
         iters = max(100, a.e2e_iters // 2)
@@ -649,19 +660,24 @@ def run_b200(a):
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": "failed: %r" % (e,)}
 
-    # ---- BASELINE configs[3] beside the headline (one GPU, default run)
+    # ---- BASELINE configs[3] (random sparse LP) and the configs[2] family (L1-SVM) beside the headline, default run.
+    #      N > 1: the random LP only — the distributed solve (balanced split, banded operands, dense halo over peer memory)
     secondary = None
-    if world == 1 and a.secondary and a.workload == "potts":
+    if a.secondary and a.workload == "potts":
         del lp, keep, args
         torch.cuda.empty_cache()
         secondary = {}
-        for kind in a.secondary.split(","):
-            kind = kind.strip()
+        for item in a.secondary.split(","):
+            kind, _, own_size = item.strip().partition(":")
+            if world > 1 and kind != "random":
+                continue
+            size2 = int(own_size) if own_size else (a.secondary_size or DEFAULT_SIZE[kind])
             try:
-                size2 = DEFAULT_SIZE[kind] if not a.secondary_size else a.secondary_size
                 secondary[workload_name(kind, size2)] = secondary_workload(kind, size2, a, torch, local_rank, make_solver,
-                                                                           chambolle_pock_ppd, peak, peak_src)
+                                                                           chambolle_pock_ppd, peak, peak_src, dist, world)
             except Exception as e:
+                if world > 1:
+                    raise  # the other ranks are inside collectives: fail together
                 secondary[kind] = {"error": repr(e)}
 
     if rank == 0:
@@ -785,8 +801,9 @@ def main():
                     help="headline LP: potts (BASELINE configs[4]), random (configs[3]) or l1svm (configs[2] family)")
     ap.add_argument("--size", type=int, default=0, help="Potts image side (4096) / random-LP variables (20 M; rows = 2x) / "
                                                          "L1-SVM samples (x 1000 features); 0: the workload's default")
-    ap.add_argument("--secondary", default="random", help="N = 1, --workload potts: also measure these workloads "
-                                                          "(comma separated, '' for none) under secondary_workloads")
+    ap.add_argument("--secondary", default="random,l1svm",
+                    help="--workload potts: also measure these workloads (comma separated, kind or kind:size, '' for none) "
+                         "under secondary_workloads; with N > 1 only the random LP")
     ap.add_argument("--secondary-size", type=int, default=0)
     ap.add_argument("--iters-per-step", type=int, default=50)
     ap.add_argument("--ref-iters-per-step", type=int, default=1)

@@ -106,7 +106,7 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     torch.cuda.empty_cache()  # (a no-op without a device; the script calls it between the workloads)
     a = argparse.Namespace(gpus=1, steps=2, warmup=3, impl="b200", workload="potts", size=24, iters_per_step=3,
                            ref_iters_per_step=1, ref_numpy_iters=1, e2e_iters=7, e2e_steps=2, no_cpu_baseline=False,
-                           variants=1, flags=0, stats_interval=5, small_configs=2, small_iters=30, secondary="random",
+                           variants=1, flags=0, stats_interval=5, small_configs=2, small_iters=30, secondary="random,l1svm:60",
                            secondary_size=2000)
     bench.run_b200(a)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
@@ -124,6 +124,8 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     sec = d["secondary_workloads"]["random_sparse_lp_2000x4000_8_per_row"]
     assert sec["value"] > 0 and sec["parity"]["status"] == "ok" and sec["roofline"]["frac"] > 0
     assert sec["e2e"]["value"] > 0 and sec["e2e"]["finite"] and "error" not in sec["sell_kernels"]
+    svm = d["secondary_workloads"]["l1svm_lp_60_samples_x_1000_features"]  # (no digest committed for this size)
+    assert svm["value"] > 0 and svm["roofline"]["frac"] > 0 and svm["e2e"]["finite"] and "sell_kernels" not in svm
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["achieved"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     e = d["e2e"]
