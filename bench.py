@@ -617,8 +617,13 @@ def run_b200(a):
     d2h = 8 * n + 96
     e2e_value, e2e_error, e2e_calls = None, None, []
     if a.e2e_steps > 0:
+        e2e_phases = []
+
         def one_call():
-            x, best = chambolle_pock_ppd(*args, nb_max_iter=a.e2e_iters, nb_iter_plot=a.e2e_iters, flags=a.flags)
+            phases = {}
+            x, best = chambolle_pock_ppd(*args, nb_max_iter=a.e2e_iters, nb_iter_plot=a.e2e_iters, flags=a.flags,
+                                         timings=phases)
+            e2e_phases.append({k: round(v, 4) for k, v in phases.items()})
             return x
 
         try:  # (a failure here must not take the device-timed headline down with it; it is reported in the line)
@@ -693,6 +698,7 @@ def run_b200(a):
             "with_stats_block": with_stats, "latency_bound_configs": small, "secondary_workloads": secondary,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "iters_per_call": a.e2e_iters, "calls": a.e2e_steps, "call_seconds": e2e_calls, "error": e2e_error,
+                    "call_phases_rank0": e2e_phases[-a.e2e_steps:] if a.e2e_steps > 0 else None,
                     "note": "each call: upload LP from pinned host memory, build SELL operators + transpose + "
                             "preconditioners on device, iterate, read x back"},
             # k_primal + k_dual per iteration; with N > 1 also one k_push after each of them (peer memory; it also waits

@@ -570,6 +570,7 @@ def chambolle_pock_ppd(
     long_row_threshold=0,
     n_gpus=None,
     y0=None,
+    timings=None,
 ):
     """minimise ``c.x``  s.t.  ``a_eq x = beq``, ``b_lower <= a_ineq x <= b_upper``, ``lb <= x <= ub``.
 
@@ -587,6 +588,9 @@ def chambolle_pock_ppd(
       the extrapolated point (``:269``);
     * returns ``(x, best_integer_solution)`` (``:344-346``); with neither equality nor
       inequality rows the reference returns the bare closed-form x (``:147-151``), so does this.
+
+    ``timings`` (keyword-only extension): a dict that receives the wall-clock seconds of the phases of this call
+    (``setup``: upload + operator build, ``iterate``: the schedule incl. the final read-back of x, ``close``).
     """
     start = time.perf_counter()
     c = np.ascontiguousarray(c, dtype=np.float64)
@@ -615,6 +619,10 @@ def chambolle_pock_ppd(
     solver = make_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=x0, alpha=alpha, theta=theta,
                          device=device, flags=flags, distributed=distributed, partition_granule=partition_granule,
                          kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
+    if timings is not None:
+        if solver is not None:
+            solver.sync()
+        timings["setup"] = time.perf_counter() - start
     if solver is not None and y0 is not None:
         # dual warm start (extension: the reference always starts from y = 0, :166,:177).  y0 = [y_eq; y_ineq] in the
         # row order of the ONE-SIDED system (finite uppers, then negated finite lowers, :74-88)
@@ -633,8 +641,12 @@ def chambolle_pock_ppd(
     except BaseException:
         solver.close()
         raise
+    if timings is not None:
+        timings["iterate"] = time.perf_counter() - start - timings["setup"]
     if return_solver:
         return x[:n], best, solver
     solver.close()
+    if timings is not None:
+        timings["close"] = time.perf_counter() - start - timings["setup"] - timings["iterate"]
     return x[:n], best
 

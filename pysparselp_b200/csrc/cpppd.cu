@@ -117,6 +117,8 @@ int cpppd_comm_create(const void *id128, int32_t rank, int32_t world_size, int32
 
 int cpppd_comm_destroy(cpppd_comm comm) {
   if (!comm) return 0;
+  cudaSetDevice(comm->device);
+  pool_release(comm->pool);
   if (comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm->comm);
   delete comm;
   return 0;
@@ -200,6 +202,7 @@ int cpppd_create(const cpppd_problem *P, cpppd_handle *out) {
       }
       h->comm = shared->comm;
       h->own_comm = false;
+      h->shared = shared;
     } else if (world > 1) {
       if (const char *e = load_nccl()) {
         rc = fail(h, CPPPD_ERR_COMM, "%s", e);
@@ -236,6 +239,7 @@ int cpppd_destroy(cpppd_handle h) {
   }
   for (void *p : h->p2p.opened) cudaIpcCloseMemHandle(p);
   for (void *p : h->p2p.own) cudaFree(p);
+  if (h->pooled && h->shared) h->shared->pool.busy = false;  // (the buffers stay mapped for the next solve)
   if (h->comm && h->own_comm) g_nccl.CommDestroy(h->comm);
   for (void *p : h->owned) dev_free(h, p);
   if (h->stats_host) cudaFreeHost(h->stats_host);

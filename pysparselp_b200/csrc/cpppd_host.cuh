@@ -460,6 +460,118 @@ int check_halo_timeout(cpppd_solver *h) {
   return 0;
 }
 
+// unmap the peers' buffers and free this rank's (communicator tear-down, or before the pool grows)
+void pool_release(PeerPool &pl) {
+  if (!pl.valid) return;
+  for (int t = 0; t < kMaxWorld; ++t) {
+    for (void *p : {(void *)pl.peer_x[t], (void *)pl.peer_y[t], (void *)pl.peer_flags[t]})
+      if (p) cudaIpcCloseMemHandle(p);
+    pl.peer_x[t] = pl.peer_y[t] = nullptr;
+    pl.peer_flags[t] = nullptr;
+  }
+  for (void *p : {(void *)pl.xbar, (void *)pl.y, (void *)pl.flags, (void *)pl.state})
+    if (p) cudaFree(p);
+  cudaGetLastError();
+  pl = PeerPool();
+}
+
+// The two peer-written vectors of this solve, from the communicator's pool when every rank can take them there
+// (collective: every rank of the solve calls this with its own lengths).  The pool is (re)built — cudaMalloc, export,
+// all-gather of the handles, cudaIpcOpenMemHandle of every peer — when some rank needs more than it holds; a second
+// solver alive on the same communicator, or a solver with a communicator of its own, gets private buffers as before
+// (h->pooled stays false, setup() allocates).  CPPPD_NO_P2P_POOL=1 switches the pool off.
+struct PoolHandles {
+  cudaIpcMemHandle_t xbar, y, flags;
+};
+int pool_acquire(cpppd_solver *h, int64_t x_len, int64_t y_len) {
+  static const bool off = [] { const char *e = getenv("CPPPD_NO_P2P_POOL"); return e && atoi(e) != 0; }();
+  h->pooled = false;
+  if (off || !h->shared) return 0;
+  const int N = h->world, me = h->rank;
+  PeerPool &pl = h->shared->pool;
+  cudaStream_t st = h->stream;
+  const size_t need_x = sizeof(double) * (size_t)std::max<int64_t>(x_len, 1), need_y = sizeof(double) * (size_t)std::max<int64_t>(y_len, 1);
+  Scratch tmp(h);
+  signed char *votes = nullptr;  // [0]: ranks whose pool is busy, [1]: ranks that cannot reuse theirs
+  if (int rc = tmp.get(&votes, 2)) return rc;
+  signed char mine[2] = {(signed char)(pl.busy ? 1 : 0),
+                         (signed char)((pl.valid && pl.world == N && pl.cap_x >= need_x && pl.cap_y >= need_y) ? 0 : 1)};
+  CK(cudaMemcpyAsync(votes, mine, 2, cudaMemcpyHostToDevice, st));
+  NK(g_nccl.AllReduce(votes, votes, 2, ncclInt8, ncclSum, h->comm, st));
+  CK(cudaMemcpyAsync(mine, votes, 2, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (mine[0]) {  // another solver of this communicator is alive: private buffers
+    if (getenv("CPPPD_POOL_TRACE")) fprintf(stderr, "[cpppd pool rank %d] busy: private buffers\n", me);
+    return 0;
+  }
+  if (mine[1]) {
+    // every rank agreed to rebuild (the all-reduce above is the rendezvous: no solver is alive, nobody stores into
+    // the old buffers any more)
+    pool_release(pl);
+    size_t round = (size_t)2 << 20;  // capacity granule (CPPPD_POOL_GRANULE: tests make it small to see the pool grow)
+    if (const char *e = getenv("CPPPD_POOL_GRANULE"))
+      if (atoll(e) >= 8) round = (size_t)atoll(e);
+    pl.cap_x = (need_x + round - 1) / round * round;
+    pl.cap_y = (need_y + round - 1) / round * round;
+    pl.world = N;
+    pl.valid = true;  // (from here on pool_release undoes whatever exists)
+    CK(cudaMalloc(&pl.xbar, pl.cap_x));
+    CK(cudaMalloc(&pl.y, pl.cap_y));
+    CK(cudaMalloc(&pl.flags, sizeof(unsigned long long) * 2 * kMaxWorld));
+    CK(cudaMalloc(&pl.state, sizeof(SyncState)));
+    PoolHandles own;
+    memset(&own, 0, sizeof own);
+    CK(cudaIpcGetMemHandle(&own.xbar, pl.xbar));
+    CK(cudaIpcGetMemHandle(&own.y, pl.y));
+    CK(cudaIpcGetMemHandle(&own.flags, pl.flags));
+    char *send = nullptr, *recv = nullptr;
+    if (int rc = tmp.get(&send, (int64_t)sizeof(PoolHandles))) return rc;
+    if (int rc = tmp.get(&recv, (int64_t)sizeof(PoolHandles) * N)) return rc;
+    CK(cudaMemcpyAsync(send, &own, sizeof own, cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllGather(send, recv, sizeof(PoolHandles), ncclInt8, h->comm, st));
+    std::vector<PoolHandles> all(N);
+    CK(cudaMemcpyAsync(all.data(), recv, sizeof(PoolHandles) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int failed = 0;
+    for (int t = 0; t < N && !failed; ++t) {
+      if (t == me) continue;
+      void *px = nullptr, *py = nullptr, *pf = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&px, all[t].xbar, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&py, all[t].y, cudaIpcMemLazyEnablePeerAccess);
+      if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pf, all[t].flags, cudaIpcMemLazyEnablePeerAccess);
+      pl.peer_x[t] = (double *)px;
+      pl.peer_y[t] = (double *)py;
+      pl.peer_flags[t] = (unsigned long long *)pf;
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        failed = 1;
+        fail(h, CPPPD_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (use CPPPD_FLAG_NO_P2P for the NCCL path)", t,
+             cudaGetErrorString(e));
+      }
+    }
+    // success is agreed on collectively (a rank that returned alone would leave its peers in a later collective)
+    signed char any = (signed char)failed;
+    CK(cudaMemcpyAsync(votes, &any, 1, cudaMemcpyHostToDevice, st));
+    NK(g_nccl.AllReduce(votes, votes, 1, ncclInt8, ncclSum, h->comm, st));
+    CK(cudaMemcpyAsync(&any, votes, 1, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (any) {
+      pool_release(pl);
+      if (!failed) fail(h, CPPPD_ERR_COMM, "a peer rank could not map this rank's halo buffers (cudaIpcOpenMemHandle); "
+                                           "use CPPPD_FLAG_NO_P2P for the NCCL path");
+      return CPPPD_ERR_COMM;
+    }
+  }
+  if (getenv("CPPPD_POOL_TRACE"))
+    fprintf(stderr, "[cpppd pool rank %d] %s (%zu + %zu bytes needed, %zu + %zu held)\n", me, mine[1] ? "built" : "reused",
+            need_x, need_y, pl.cap_x, pl.cap_y);
+  pl.busy = true;
+  h->pooled = true;
+  h->xbar = pl.xbar;
+  h->y = pl.y;
+  return 0;
+}
+
 // What every rank publishes so that its neighbours can write into its ghost slots.
 struct PeerRecord {
   cudaIpcMemHandle_t xbar, y, flags;
@@ -471,10 +583,15 @@ int setup_p2p(cpppd_solver *h) {
   const int N = h->world, me = h->rank;
   P2P &pp = h->p2p;
   cudaStream_t st = h->stream;
-  CK(cudaMalloc(&pp.flags, sizeof(unsigned long long) * 2 * N));
-  pp.own.push_back(pp.flags);
-  CK(cudaMalloc(&pp.state, sizeof(SyncState)));
-  pp.own.push_back(pp.state);
+  if (h->pooled) {
+    pp.flags = h->shared->pool.flags;
+    pp.state = h->shared->pool.state;
+  } else {
+    CK(cudaMalloc(&pp.flags, sizeof(unsigned long long) * 2 * N));
+    pp.own.push_back(pp.flags);
+    CK(cudaMalloc(&pp.state, sizeof(SyncState)));
+    pp.own.push_back(pp.state);
+  }
   CK(cudaMemsetAsync(pp.flags, 0, sizeof(unsigned long long) * 2 * N, st));
   {
     SyncState init;
@@ -485,9 +602,11 @@ int setup_p2p(cpppd_solver *h) {
   }
   PeerRecord mine;
   memset(&mine, 0, sizeof mine);
-  CK(cudaIpcGetMemHandle(&mine.xbar, h->xbar));
-  CK(cudaIpcGetMemHandle(&mine.y, h->y));
-  CK(cudaIpcGetMemHandle(&mine.flags, pp.flags));
+  if (!h->pooled) {
+    CK(cudaIpcGetMemHandle(&mine.xbar, h->xbar));
+    CK(cudaIpcGetMemHandle(&mine.y, h->y));
+    CK(cudaIpcGetMemHandle(&mine.flags, pp.flags));
+  }
   mine.owned_x = h->hx.owned;
   mine.owned_y = h->hy.owned;
   for (int t = 0; t < N; ++t) {
@@ -511,6 +630,12 @@ int setup_p2p(cpppd_solver *h) {
     if (t == me) continue;
     const bool nb = h->hx.send_count[t] || h->hx.recv_count[t] || h->hy.send_count[t] || h->hy.recv_count[t];
     if (!nb) continue;
+    if (h->pooled) {  // mapped when the pool was built
+      pp.ptrs[0].vec[t] = h->shared->pool.peer_x[t];
+      pp.ptrs[1].vec[t] = h->shared->pool.peer_y[t];
+      pp.ptrs[0].flags[t] = pp.ptrs[1].flags[t] = h->shared->pool.peer_flags[t];
+      continue;
+    }
     void *px = nullptr, *py = nullptr, *pf = nullptr;
     cudaError_t e1 = cudaIpcOpenMemHandle(&px, all[t].xbar, cudaIpcMemLazyEnablePeerAccess);
     cudaError_t e2 = e1 == cudaSuccess ? cudaIpcOpenMemHandle(&py, all[t].y, cudaIpcMemLazyEnablePeerAccess) : e1;
@@ -1212,7 +1337,11 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
     if (int rc = alloc_array(h, v, x_len)) return rc;
   for (double **v : {&h->b, &h->sigma})
     if (int rc = alloc_array(h, v, mloc)) return rc;
-  if (want_p2p) {  // the two vectors with peer-written ghost tails: plain cudaMalloc, exportable by IPC
+  if (want_p2p)    // ... from the communicator's pool of mapped peer memory when there is one
+    if (int rc = pool_acquire(h, x_len, y_len)) return rc;
+  if (h->pooled) {
+    h->device_bytes += 8 * (x_len + y_len);
+  } else if (want_p2p) {  // the two vectors with peer-written ghost tails: plain cudaMalloc, exportable by IPC
     CK(cudaMalloc(&h->xbar, sizeof(double) * std::max<int64_t>(x_len, 1)));
     h->p2p.own.push_back(h->xbar);
     CK(cudaMalloc(&h->y, sizeof(double) * std::max<int64_t>(y_len, 1)));

@@ -154,9 +154,24 @@ const char *load_nccl() {
 
 }  // namespace
 
+// Peer-memory buffers of a communicator, kept between solves (cpppd_host.cuh: pool_acquire).  A solve used to
+// cudaMalloc xbar / y / the stamps, export them, map those of its neighbours (cudaIpcOpenMemHandle) and undo all of
+// it in cpppd_destroy — measured on 2 GPUs: 0.12-0.62 s per end-to-end call in the unmap + cudaFree alone.
+struct PeerPool {
+  bool valid = false, busy = false;
+  int world = 0;
+  size_t cap_x = 0, cap_y = 0;  // bytes of this rank's two vectors
+  double *xbar = nullptr, *y = nullptr;
+  unsigned long long *flags = nullptr;
+  SyncState *state = nullptr;
+  double *peer_x[kMaxWorld] = {}, *peer_y[kMaxWorld] = {};
+  unsigned long long *peer_flags[kMaxWorld] = {};
+};
+
 struct cpppd_comm_s {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, device = 0;
+  PeerPool pool;
 };
 
 struct cpppd_solver {
@@ -178,6 +193,8 @@ struct cpppd_solver {
   Halo hx, hy;                  // xbar-like vectors (columns) / y-like vectors (rows)
   ncclComm_t comm = nullptr;
   bool own_comm = true;         // false: borrowed from a cpppd_comm (cpppd_problem.comm)
+  cpppd_comm_s *shared = nullptr;  // that cpppd_comm (owner of the peer-memory pool)
+  bool pooled = false;          // xbar / y / stamps / peer mappings belong to shared->pool
   P2P p2p;
   double alpha = 1, theta = 1, one_plus_theta = 2;
   uint32_t flags = 0;

@@ -34,7 +34,7 @@ def emulated_library():
 
 class EmulatedSolver(SolverHandle):
     def __init__(self, c, a, m_eq, b, lb, ub, x0=None, alpha=1, theta=1, flags=0, partition_granule=0,
-                 rank=0, world=1, comm_id=None, kernel_variant=0, long_row_threshold=0):
+                 rank=0, world=1, comm_id=None, kernel_variant=0, long_row_threshold=0, comm=None):
         self.lib = emulated_library()
         p, keep = prepare_problem(c, a, m_eq, b, lb, ub, x0, alpha, theta, flags, partition_granule, kernel_variant,
                                   long_row_threshold)
@@ -45,6 +45,7 @@ class EmulatedSolver(SolverHandle):
         p.free = C.cast(None, _cabi.FREE_FN)
         p.rank, p.world_size = rank, world
         p.comm_id = None if comm_id is None else comm_id.ctypes.data
+        p.comm = comm  # a cpppd_comm kept between solves (emulated_comm): owner of the peer-memory pool
         handle = C.c_void_p()
         _cabi.check(self.lib, None, self.lib.cpppd_create(C.byref(p), C.byref(handle)))
         del keep
@@ -52,14 +53,23 @@ class EmulatedSolver(SolverHandle):
 
 
 def make_emulated_solver(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1, flags=0,
-                         partition_granule=0, rank=0, world=1, comm_id=None, kernel_variant=0, long_row_threshold=0):
+                         partition_granule=0, rank=0, world=1, comm_id=None, kernel_variant=0, long_row_threshold=0,
+                         comm=None):
     if a_eq is not None and a_eq.shape[0] == 0:
         a_eq, beq = None, None
     a_ineq, b_ineq = one_sided_rows(a_ineq, b_lower, b_upper)
     a, b, m_eq = stack_operator(a_eq, beq, a_ineq, b_ineq, np.size(c))
     return EmulatedSolver(c, a, m_eq, b, lb, ub, x0=x0, alpha=alpha, theta=theta, flags=flags,
                           partition_granule=partition_granule, rank=rank, world=world, comm_id=comm_id,
-                          kernel_variant=kernel_variant, long_row_threshold=long_row_threshold)
+                          kernel_variant=kernel_variant, long_row_threshold=long_row_threshold, comm=comm)
+
+
+def emulated_comm(comm_id, rank, world):
+    """cpppd_comm_create on the emulated library: a communicator that outlives the solves made on it."""
+    comm = C.c_void_p()
+    _cabi.check(emulated_library(), None, emulated_library().cpppd_comm_create(comm_id.ctypes.data, rank, world, 0,
+                                                                                C.byref(comm)))
+    return comm
 
 
 def emulated_chambolle_pock_ppd(c, a_eq, beq, a_ineq, b_lower, b_upper, lb, ub, x0=None, alpha=1, theta=1,

@@ -263,3 +263,49 @@ def test_multi_rank_sparse_halo_of_banded_operands(monkeypatch):
     for r in res:
         assert r["info"]["dense_halo"] == 0 and r["info"]["band_in_use"] == [1, 1]
         assert np.array_equal(r["x"], g["x_100"]) and np.array_equal(r["y"], y_gold)
+
+
+@pytest.mark.timeout(600)
+def test_peer_memory_pool_of_a_kept_communicator(monkeypatch, capfd):
+    """Solves made on one cpppd_comm (what the Python layer does) take xbar / y / stamps and the peer mappings from the
+    communicator's pool: built by the first solve, reused by the second, rebuilt when a larger LP arrives, bypassed
+    (private buffers) while another solver of the communicator is alive.  Same bits every time."""
+    from emul.cabi_driver import emulated_comm, emulated_library
+
+    monkeypatch.setenv("CPPPD_POOL_GRANULE", "256")  # (default 2 MB: every golden LP would fit the first pool)
+    monkeypatch.setenv("CPPPD_POOL_TRACE", "1")
+    small, g_small = case_args("sc105")
+    large, g_large = case_args("potts50")
+
+    def body(rank, world, comm_id):
+        comm = emulated_comm(comm_id, rank, world)
+        out = []
+        try:
+            for args in (small, small, large, small):
+                solver = make_emulated_solver(*args, partition_granule=32, rank=rank, world=world, comm=comm)
+                solver.iterate(100)
+                out.append((solver.get_x(), solver.get_y()))
+                solver.close()
+            # two solvers alive at once: the second one must not touch the buffers of the first
+            first = make_emulated_solver(*large, partition_granule=32, rank=rank, world=world, comm=comm)
+            second = make_emulated_solver(*small, partition_granule=32, rank=rank, world=world, comm=comm)
+            first.iterate(50)
+            second.iterate(100)
+            first.iterate(50)
+            out.append((first.get_x(), first.get_y()))
+            out.append((second.get_x(), second.get_y()))
+            second.close()
+            first.close()
+        finally:
+            emulated_library().cpppd_comm_destroy(comm)
+        return out
+
+    def gold_y(g):
+        return np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+
+    for world in (2, 3):
+        for out in run_ranks(world, body):
+            for (x, y), g in zip(out, (g_small, g_small, g_large, g_small, g_large, g_small)):
+                assert np.array_equal(x, g["x_100"]) and np.array_equal(y, gold_y(g))
+        trace = [l.split("] ")[1].split(" ")[0] for l in capfd.readouterr().err.splitlines() if "[cpppd pool rank 0]" in l]
+        assert trace == ["built", "reused", "built", "reused", "reused", "busy:"], trace
