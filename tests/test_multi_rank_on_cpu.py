@@ -309,3 +309,49 @@ def test_peer_memory_pool_of_a_kept_communicator(monkeypatch, capfd):
                 assert np.array_equal(x, g["x_100"]) and np.array_equal(y, gold_y(g))
         trace = [l.split("] ")[1].split(" ")[0] for l in capfd.readouterr().err.splitlines() if "[cpppd pool rank 0]" in l]
         assert trace == ["built", "reused", "built", "reused", "reused", "busy:"], trace
+
+
+@pytest.mark.timeout(300)
+def test_time_out_is_one_decision_for_all_ranks():
+    """run_schedule with max_time on two ranks whose clocks disagree (reference :243-247, the schedule of
+    pysparselp_b200/ChambollePockPPD.py): rank 0's verdict is the verdict of every rank, so the ranks keep issuing the
+    same collectives — a rank that broke out alone would call get_x (a collective) while the other one is inside the
+    stats exchange, and both would hang."""
+    import threading
+    import time
+
+    args, g = case_args("potts50")
+
+    class Agreement:
+        """agree() of the product's solver (one broadcast / all-reduce through torch.distributed) over two threads"""
+
+        def __init__(self, world):
+            self.barrier = threading.Barrier(world)
+            self.votes = [False] * world
+
+        def bind(self, solver, rank):
+            def agree(flag, any_rank=False):
+                self.votes[rank] = bool(flag)
+                self.barrier.wait(timeout=60)
+                verdict = any(self.votes) if any_rank else self.votes[0]
+                self.barrier.wait(timeout=60)
+                return verdict
+
+            solver.agree, solver.world = agree, 2
+
+    for late_rank, want_iterations in ((1, 40), (0, 0)):
+        shared = Agreement(2)
+
+        def body(rank, world, comm_id):
+            solver = make_emulated_solver(*args, partition_granule=32, rank=rank, world=world, comm_id=comm_id)
+            shared.bind(solver, rank)
+            # the late rank believes the solve started 1000 s ago: on its own clock max_time = 500 s has passed
+            start = time.perf_counter() - (1000.0 if rank == late_rank else 0.0)
+            x, best = run_schedule(solver, 40, None, 500.0, False, 10, False, start)
+            niter = solver.niter
+            solver.close()
+            return x, niter
+
+        results = run_ranks(2, body)
+        assert results[0][1] == results[1][1] == want_iterations
+        assert np.array_equal(results[0][0], results[1][0])
