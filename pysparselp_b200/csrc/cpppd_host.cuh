@@ -1415,8 +1415,7 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   h->tiny = !(h->flags & CPPPD_FLAG_NO_TINY_PERSISTENT) && !variant_forced && N == 1 && h->longA.count == 0 && h->longAT.count == 0 &&
             !h->bandA.built && !h->bandAT.built &&
             std::max(nloc, mloc) <= 4096 && h->A.padded + h->AT.padded <= 16384;
-  // ... a cluster of up to 16 CTAs when they fit the shared memory of 16 SMs (see k_cluster_iterate);
-  // CPPPD_FORCE_CLUSTER=1 (tests): also the LPs that would fit one CTA
+  // ... a cluster of up to 16 CTAs when they fit the shared memory of 16 SMs (see k_cluster_iterate).
   // The cluster kernel is the faster one whenever it can be launched (SC105, 103 x 105: 801 000 it/s in one CTA,
   // 1 116 000 in the cluster; Potts 24x24: 131 000 / 961 000 — profiles/r02_kernels.md): the one-CTA kernel remains for
   // devices / LPs where the cluster launch is refused and for an explicit CPPPD_FLAG_TINY_PERSISTENT.

@@ -45,13 +45,11 @@ def test_tiny_persistent_kernel_gives_the_same_bits(name):
 @pytest.mark.parametrize("name", ["potts50", "sc105", "random_small", "random_small_alpha", "kb2", "afiro", "sc50a", "sc50b"])
 def test_cluster_persistent_kernel_gives_the_same_bits(name, mode, monkeypatch):
     """k_cluster_iterate (cpppd_cluster.cuh): all iterations between two stats blocks in one launch of one thread-block
-    cluster, operands and vectors in (distributed) shared memory.  Potts 50x50 takes this path by default; the
-    smaller goldens are forced onto it (CPPPD_FORCE_CLUSTER) instead of the one-CTA kernel."""
+    cluster, operands and vectors in (distributed) shared memory: the default for every LP that fits 16 SMs."""
     from pysparselp_b200 import _cabi
     from pysparselp_b200.ChambollePockPPD import chambolle_pock_ppd
     from test_gpu_parity import assert_curves_close
 
-    monkeypatch.setenv("CPPPD_FORCE_CLUSTER", "1")
     # 0: relaxed cluster barrier arrive (after membar.cta); 1: release / acquire
     monkeypatch.setenv("CPPPD_CLUSTER_MODE", str(mode))
     args, g = case_args(name)
