@@ -460,20 +460,27 @@ int check_halo_timeout(cpppd_solver *h) {
   return 0;
 }
 
-// unmap the peers' buffers and free this rank's (communicator tear-down, or before the pool grows)
-void pool_release(PeerPool &pl) {
-  if (!pl.valid) return;
+// Unmap the peers' buffers and free this rank's (communicator tear-down, or before the pool grows).  CUDA leaves
+// cudaFree of an exported region undefined while an importer still has it open: `between` runs after all imports of
+// this rank are closed and before its own exports are freed — the pool rebuild passes a collective there, so that no
+// rank frees what a slower peer still maps (at tear-down there is nobody left to wait for).
+template <typename Between>
+int pool_release(PeerPool &pl, Between between) {
+  if (!pl.valid) return between();
   for (int t = 0; t < kMaxWorld; ++t) {
     for (void *p : {(void *)pl.peer_x[t], (void *)pl.peer_y[t], (void *)pl.peer_flags[t]})
       if (p) cudaIpcCloseMemHandle(p);
     pl.peer_x[t] = pl.peer_y[t] = nullptr;
     pl.peer_flags[t] = nullptr;
   }
+  const int rc = between();
   for (void *p : {(void *)pl.xbar, (void *)pl.y, (void *)pl.flags, (void *)pl.state})
     if (p) cudaFree(p);
   cudaGetLastError();
   pl = PeerPool();
+  return rc;
 }
+inline void pool_release(PeerPool &pl) { pool_release(pl, [] { return 0; }); }
 
 // The two peer-written vectors of this solve, from the communicator's pool when every rank can take them there
 // (collective: every rank of the solve calls this with its own lengths).  The pool is (re)built — cudaMalloc, export,
@@ -506,8 +513,13 @@ int pool_acquire(cpppd_solver *h, int64_t x_len, int64_t y_len) {
   }
   if (mine[1]) {
     // every rank agreed to rebuild (the all-reduce above is the rendezvous: no solver is alive, nobody stores into
-    // the old buffers any more)
-    pool_release(pl);
+    // the old buffers any more); a second one separates "every rank has closed its imports" from "free the exports"
+    if (int rc = pool_release(pl, [&]() -> int {
+          NK(g_nccl.AllReduce(votes, votes, 1, ncclInt8, ncclSum, h->comm, st));
+          CK(cudaStreamSynchronize(st));
+          return 0;
+        }))
+      return rc;
     size_t round = (size_t)2 << 20;  // capacity granule (CPPPD_POOL_GRANULE: tests make it small to see the pool grow)
     if (const char *e = getenv("CPPPD_POOL_GRANULE"))
       if (atoll(e) >= 8) round = (size_t)atoll(e);
