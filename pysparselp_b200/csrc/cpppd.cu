@@ -342,18 +342,15 @@ int cpppd_time_iterations(cpppd_handle h, int64_t k, float *elapsed_ms) {
   CHECK_HANDLE(h);
   if (!elapsed_ms || k < 0) return fail(h, CPPPD_ERR_INVALID, "bad argument");
   if (h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "cpppd_dual_step must close the open iteration first");
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, h->stream));
+  Events ev(2);
+  CK(ev.create());
+  CK(cudaEventRecord(ev[0], h->stream));
   int rc = run_iterations(h, k);
   if (!rc) {
-    CK(cudaEventRecord(e1, h->stream));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaEventElapsedTime(elapsed_ms, e0, e1));
+    CK(cudaEventRecord(ev[1], h->stream));
+    CK(cudaEventSynchronize(ev[1]));
+    CK(cudaEventElapsedTime(elapsed_ms, ev[0], ev[1]));
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return rc ? rc : check_halo_timeout(h);
 }
 
@@ -362,8 +359,8 @@ int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_
   if (!primal_ms || !dual_ms || k < 0 || k > 64) return fail(h, CPPPD_ERR_INVALID, "bad argument (k must be in [0, 64])");
   if (h->mid_iteration) return fail(h, CPPPD_ERR_STATE, "cpppd_dual_step must close the open iteration first");
   // the halo exchanges (world > 1) fall inside the brackets of the kernel that produces the data
-  std::vector<cudaEvent_t> ev(2 * k + 1);
-  for (auto &e : ev) CK(cudaEventCreate(&e));
+  Events ev(2 * k + 1);
+  CK(ev.create());
   CK(cudaEventRecord(ev[0], h->stream));
   for (int64_t i = 0; i < k; ++i) {
     if (int rc = launch_primal(h, false)) return rc;
@@ -381,7 +378,6 @@ int cpppd_time_kernels(cpppd_handle h, int64_t k, float *primal_ms, float *dual_
     *primal_ms += a;
     *dual_ms += b;
   }
-  for (auto &e : ev) cudaEventDestroy(e);
   return 0;
 }
 

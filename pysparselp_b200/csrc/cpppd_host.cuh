@@ -1652,9 +1652,9 @@ int tune_kernels(cpppd_solver *h) {
   double *x_saved = nullptr;
   if (int rc = tmp.get(&x_saved, nx)) return rc;
   CK(cudaMemcpyAsync(x_saved, h->x, sizeof(double) * nx, cudaMemcpyDeviceToDevice, st));
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
+  Events tune_ev(2);  // (destroyed on every way out, also the early returns of CK)
+  CK(tune_ev.create());
+  const cudaEvent_t e0 = tune_ev[0], e1 = tune_ev[1];
   int rc = 0;
   for (int kind = 0; kind < 2 && !rc; ++kind) {
     // pass 0 runs every variant once untimed (caches, clocks); passes 1 and 2 time two launches of each variant
@@ -1707,8 +1707,6 @@ int tune_kernels(cpppd_solver *h) {
       band.in_use = (h->flags & CPPPD_FLAG_BANDED) || (!rc && band.ms < 0.98f * h->variant_ms[kind][best]);
     }
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   if (rc) return rc;
   h->autotuned = true;
   if (use_cache) {

@@ -339,6 +339,22 @@ struct Scratch {
   }
 };
 
+// CUDA events that are destroyed on every way out of a function (the CK / NK macros return early)
+struct Events {
+  std::vector<cudaEvent_t> ev;
+  explicit Events(size_t count) : ev(count, nullptr) {}
+  ~Events() {
+    for (cudaEvent_t e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+  cudaError_t create() {
+    for (auto &e : ev)
+      if (cudaError_t err = cudaEventCreate(&e)) return err;
+    return cudaSuccess;
+  }
+  cudaEvent_t operator[](size_t i) const { return ev[i]; }
+};
+
 inline int grid_for(int64_t items, int block = kBlock) { return (int)std::max<int64_t>(1, (items + block - 1) / block); }
 
 }  // namespace
