@@ -15,7 +15,10 @@
 // in stored entry order, equality / inequality parts apart, the same epilogues) — the iterates are the same bits;
 // tests/test_gpu_parity.py compares them with the goldens minted from the reference.
 //
-// Not compiled for the CPU emulation (tests/emul runs one CTA at a time): there the LP stays on the graph path.
+// CPU emulation (tests/emul runs one CTA at a time): the staging and the per-row code below are compiled for the host
+// as they are and driven phase by phase — one emulated launch per half-iteration instead of the cluster barrier, a
+// host buffer per CTA instead of its shared memory (see the `#else` branches); what only hardware shows (the barrier,
+// distributed shared memory, the one-pass register form of the kernel) stays with the -m gpu tests.
 #pragma once
 
 #ifdef __CUDACC__
@@ -45,6 +48,7 @@ inline __host__ __device__ size_t cluster_smem_bytes(int spc_at, int spc_a, int 
 
 #ifdef __CUDACC__
 namespace cg = cooperative_groups;
+#endif
 
 __device__ __forceinline__ ClusterSmem cluster_carve(unsigned char *base, int spc_at, int spc_a, int ent_at, int ent_a) {
   ClusterSmem S;
@@ -71,6 +75,7 @@ __device__ __forceinline__ ClusterSmem cluster_carve(unsigned char *base, int sp
   return S;
 }
 
+#ifdef __CUDACC__
 // 32-bit shared::cluster address of `local` (an address in this CTA's shared window) inside CTA `rank`
 __device__ __forceinline__ uint32_t cluster_map(uint32_t local, int rank) {
   uint32_t out;
@@ -88,6 +93,20 @@ __device__ __forceinline__ double cluster_load(uint64_t base, uint32_t addr) {
   asm volatile("ld.f64 %0, [%1];" : "=d"(v) : "l"(base | addr) : "memory");
   return v;
 }
+
+#else
+// ---- CPU emulation (tests/emul): one host buffer per CTA stands for its shared memory; a shared::cluster address is
+//      [CTA rank : 6][offset inside the buffer : 26], the "generic base" is 0, mapa / cvta / ld are arithmetic on that.
+inline thread_local unsigned char *g_emul_cluster_smem[kClusterMaxCtas] = {};
+inline size_t __cvta_generic_to_shared(const void *p) {
+  return (size_t)(static_cast<const unsigned char *>(p) - g_emul_cluster_smem[blockIdx.x]);
+}
+inline uint32_t cluster_map(uint32_t local, int rank) { return ((uint32_t)rank << 26) | local; }
+inline uint64_t cluster_generic_base(uint32_t) { return 0; }
+inline double cluster_load(uint64_t, uint32_t addr) {
+  return *reinterpret_cast<const double *>(g_emul_cluster_smem[addr >> 26] + (addr & 0x03fffff8u));
+}
+#endif
 
 // Entries of the slices [s_lo, s_hi) of S into shared memory: the value, and the index word translated ONCE into
 // the shared::cluster address of the gathered element inside its owner CTA (mapa) — a gather in the loop is then
@@ -137,6 +156,7 @@ __device__ __forceinline__ void cluster_stage(const SellView &S, int64_t s_lo, i
   }
 }
 
+#ifdef __CUDACC__
 // The barrier between the two halves of an iteration.  What has to be ordered is: my st.shared of xbar / y, then the
 // other CTAs' loads of it from my shared memory after the barrier.  barrier.cluster.arrive.release compiles to
 // MEMBAR.ALL.GPU + UCGABAR_ARV (cuobjdump): a GPU-scope fence, twice per iteration, for data that never leaves shared
@@ -154,6 +174,8 @@ __device__ __forceinline__ void cluster_barrier() {
   }
   asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
+
+#endif
 
 // per-column / per-row constants and state of one thread
 struct ClusterCol { double c, T, lb, ub, x; int q0, width; bool live; };   // width: padded, a multiple of kClC
@@ -225,6 +247,7 @@ __device__ __forceinline__ ClusterRow cluster_row(const ClusterSmem &S, int sl, 
   return ClusterRow{S.b[il], S.sigma[il], S.y[il], S.sp_a[sl] + lane, (S.sp_a[sl + 1] - S.sp_a[sl]) >> 5, live, ineq};
 }
 
+#ifdef __CUDACC__
 // kOnePass: every CTA has at most one slice of A^T and one of A per warp — a thread keeps its column and its row
 // (constants, x, y, entry offsets) in registers for the whole launch.  Otherwise the warps stride over the slices and
 // reload them from shared memory every iteration.
@@ -308,6 +331,92 @@ k_cluster_iterate(SellView AT, SellView A, Vec c, Vec T, Vec lb, Vec ub, Vec b, 
   for (int t = threadIdx.x; t < nrs * 32; t += blockDim.x) {
     const int64_t i = r_lo * 32 + t;
     if (i < m) y[i] = S.y[t];
+  }
+}
+#else  // ---- CPU emulation of the cluster kernel: the same staging and per-row code, one emulated launch per phase
+// (the kernel boundary stands for the cluster barrier; CTAs run one after the other, a remote gather is a read of the
+// other CTA's host buffer).  Per-thread state is reloaded from "shared memory" in every phase (the kOnePass = false form).
+struct EmulClusterArgs {
+  SellView AT, A;
+  Vec c, T, lb, ub, b, sigma;
+  double *x, *xbar, *y;
+  int64_t n, m, m_eq;
+  int has_eq, has_ineq;
+  double theta, one_plus_theta;
+  int spc_at, spc_a, ent_at, ent_a;
+};
+struct EmulClusterCta {
+  ClusterSmem S;
+  int me, lane, warp, nwarps, ncs, nrs;
+  int64_t c_lo, r_lo;
+};
+inline EmulClusterCta emul_cluster_cta(const EmulClusterArgs &a) {
+  EmulClusterCta q;
+  q.me = (int)blockIdx.x;
+  q.S = cluster_carve(g_emul_cluster_smem[q.me], a.spc_at, a.spc_a, a.ent_at, a.ent_a);
+  q.lane = threadIdx.x & 31;
+  q.warp = threadIdx.x >> 5;
+  q.nwarps = blockDim.x >> 5;
+  q.c_lo = std::min((int64_t)q.me * a.spc_at, a.AT.nslices);
+  q.r_lo = std::min((int64_t)q.me * a.spc_a, a.A.nslices);
+  q.ncs = (int)(std::min(q.c_lo + a.spc_at, a.AT.nslices) - q.c_lo);
+  q.nrs = (int)(std::min(q.r_lo + a.spc_a, a.A.nslices) - q.r_lo);
+  return q;
+}
+__global__ void k_emul_cluster_stage(EmulClusterArgs a) {
+  const EmulClusterCta q = emul_cluster_cta(a);
+  const ClusterSmem &S = q.S;
+  if (threadIdx.x < 2) S.zero[threadIdx.x] = 0.0;
+  cluster_stage(a.AT, q.c_lo, q.c_lo + q.ncs, a.spc_a, S.y, S.zero, q.me, S.val_at, S.w_at, S.sp_at);
+  cluster_stage(a.A, q.r_lo, q.r_lo + q.nrs, a.spc_at, S.xbar, S.zero, q.me, S.val_a, S.w_a, S.sp_a);
+  for (int t = threadIdx.x; t < a.spc_at * 32; t += blockDim.x) {
+    const int64_t j = q.c_lo * 32 + t;
+    const bool live = t < q.ncs * 32 && j < a.n;
+    S.c[t] = live ? (a.c.p ? a.c.p[j] : a.c.c) : 0.0;
+    S.T[t] = live ? (a.T.p ? a.T.p[j] : a.T.c) : 0.0;
+    S.lb[t] = live ? (a.lb.p ? a.lb.p[j] : a.lb.c) : 0.0;
+    S.ub[t] = live ? (a.ub.p ? a.ub.p[j] : a.ub.c) : 0.0;
+    S.x[t] = live ? a.x[j] : 0.0;
+    S.xbar[t] = live ? a.xbar[j] : 0.0;
+  }
+  for (int t = threadIdx.x; t < a.spc_a * 32; t += blockDim.x) {
+    const int64_t i = q.r_lo * 32 + t;
+    const bool live = t < q.nrs * 32 && i < a.m;
+    S.b[t] = live ? (a.b.p ? a.b.p[i] : a.b.c) : 0.0;
+    S.sigma[t] = live ? (a.sigma.p ? a.sigma.p[i] : a.sigma.c) : 0.0;
+    S.y[t] = live ? a.y[i] : 0.0;
+  }
+}
+__global__ void k_emul_cluster_primal(EmulClusterArgs a) {
+  const EmulClusterCta q = emul_cluster_cta(a);
+  const uint64_t gbase = cluster_generic_base(0);
+  for (int sl = q.warp; sl < q.ncs; sl += q.nwarps) {
+    ClusterCol C = cluster_col(q.S, sl, q.lane, q.c_lo * 32 + sl * 32 + q.lane < a.n);
+    if (a.has_eq) cluster_primal<true>(q.S, gbase, C, sl * 32 + q.lane, a.has_eq, a.has_ineq, a.theta, a.one_plus_theta);
+    else cluster_primal<false>(q.S, gbase, C, sl * 32 + q.lane, a.has_eq, a.has_ineq, a.theta, a.one_plus_theta);
+    if (C.live) q.S.x[sl * 32 + q.lane] = C.x;
+  }
+}
+__global__ void k_emul_cluster_dual(EmulClusterArgs a) {
+  const EmulClusterCta q = emul_cluster_cta(a);
+  const uint64_t gbase = cluster_generic_base(0);
+  for (int sl = q.warp; sl < q.nrs; sl += q.nwarps) {
+    ClusterRow R = cluster_row(q.S, sl, q.lane, q.r_lo * 32 + sl * 32 + q.lane < a.m, q.r_lo * 32 + sl * 32 + q.lane >= a.m_eq);
+    cluster_dual(q.S, gbase, R, sl * 32 + q.lane);
+  }
+}
+__global__ void k_emul_cluster_writeback(EmulClusterArgs a) {
+  const EmulClusterCta q = emul_cluster_cta(a);
+  for (int t = threadIdx.x; t < q.ncs * 32; t += blockDim.x) {
+    const int64_t j = q.c_lo * 32 + t;
+    if (j < a.n) {
+      a.x[j] = q.S.x[t];
+      a.xbar[j] = q.S.xbar[t];
+    }
+  }
+  for (int t = threadIdx.x; t < q.nrs * 32; t += blockDim.x) {
+    const int64_t i = q.r_lo * 32 + t;
+    if (i < a.m) a.y[i] = q.S.y[t];
   }
 }
 #endif  // __CUDACC__

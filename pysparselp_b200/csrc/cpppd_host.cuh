@@ -801,7 +801,6 @@ inline auto cluster_kernel(bool strict, bool one_pass) {
 // Can one thread-block cluster carry this LP (cpppd_cluster.cuh)?  Fills h->cluster.
 int plan_cluster(cpppd_solver *h) {
   h->cluster = ClusterPlan();
-#ifdef __CUDACC__
   static const bool off = [] { const char *e = getenv("CPPPD_NO_CLUSTER"); return e && atoi(e) != 0; }();
   if (off || h->A.nslices == 0 || h->AT.nslices == 0) return 0;
   if (h->A.padded > kClusterMaxEntries || h->AT.padded > kClusterMaxEntries) return 0;
@@ -817,9 +816,13 @@ int plan_cluster(cpppd_solver *h) {
       CK(cudaStreamSynchronize(h->stream));
     }
   }
+#ifdef __CUDACC__
   int max_smem = 0;
   CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   auto kernel = cluster_kernel(false, false);
+#else
+  const int max_smem = 232448;  // (CPU emulation: the 227 KB per CTA of sm_100)
+#endif
   for (int ctas : {kClusterMaxCtas, 8}) {
     ClusterPlan P;
     P.ctas = ctas;
@@ -839,6 +842,7 @@ int plan_cluster(cpppd_solver *h) {
     P.ent_a = (int)ent[1];
     P.smem = cluster_smem_bytes(P.spc_at, P.spc_a, P.ent_at, P.ent_a);
     if ((int64_t)P.smem > max_smem) continue;
+#ifdef __CUDACC__
     bool attr_ok = true;
     for (auto fn : {cluster_kernel(false, false), cluster_kernel(false, true), cluster_kernel(true, false), cluster_kernel(true, true)})
       attr_ok = attr_ok && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
@@ -864,11 +868,11 @@ int plan_cluster(cpppd_solver *h) {
       cudaGetLastError();
       continue;
     }
+#endif
     P.on = true;
     h->cluster = P;
     break;
   }
-#endif
   return 0;
 }
 
@@ -935,7 +939,6 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
   if (nnz) k_row_of_entry<<<grid_for(nnz), kBlock, 0, st>>>(rowptr, m, nnz, row_of, entry_id);
 
   bool reorder = N > 1 || (h->flags & CPPPD_FLAG_REORDER);
-#ifdef __CUDACC__
   // Small LPs that may run in one thread-block cluster (cpppd_cluster.cuh) are renumbered by locality: a CTA of the
   // cluster then owns rows AND the columns they touch, most gathers stay in its own shared memory, and the cluster
   // network — which bounds the kernel otherwise — carries a fraction of them (Potts 50x50: 404 000 -> 794 000 it/s).
@@ -946,7 +949,6 @@ int setup(cpppd_solver *h, const cpppd_problem *P) {
         !(h->flags & (CPPPD_FLAG_NO_REORDER | CPPPD_FLAG_NO_TINY_PERSISTENT | CPPPD_FLAG_BANDED)))
       reorder = true;
   }
-#endif
   // Banded operands (cpppd_banded.cuh) keep the caller's numbering: the window order along a row is what keeps
   // the sums bit-exact.  Candidates: forced by flag, or a pattern without locality over vectors of several windows.
   // With more than one GPU they need the balanced split in original order (decided below): windows are ranges of
@@ -1804,7 +1806,25 @@ int run_cluster(cpppd_solver *h, int64_t k) {
   h->niter += k;
   return 0;
 #else
-  return fail(h, CPPPD_ERR_INVALID, "cluster kernel not available");
+  // CPU emulation: a host buffer per CTA, one emulated launch per phase (cpppd_cluster.cuh)
+  const ClusterPlan &P = h->cluster;
+  std::vector<std::vector<unsigned char>> smem(P.ctas, std::vector<unsigned char>(P.smem + 16, (unsigned char)0xA5));
+  for (int r = 0; r < P.ctas; ++r) {
+    unsigned char *base = smem[r].data();
+    g_emul_cluster_smem[r] = base + ((16 - reinterpret_cast<uintptr_t>(base) % 16) % 16);
+  }
+  EmulClusterArgs a{view(h->AT), view(h->A), h->vc, h->vT, h->vlb, h->vub, h->vb, h->vsigma, h->x, h->xbar, h->y, h->n, h->m,
+                    h->m_eq, h->m_eq_glob > 0, h->m_ineq_glob > 0, h->theta, h->one_plus_theta, P.spc_at, P.spc_a, P.ent_at,
+                    P.ent_a};
+  k_emul_cluster_stage<<<P.ctas, kClusterBlock, 0, h->stream>>>(a);
+  for (int64_t it = 0; it < k; ++it) {
+    k_emul_cluster_primal<<<P.ctas, kClusterBlock, 0, h->stream>>>(a);
+    k_emul_cluster_dual<<<P.ctas, kClusterBlock, 0, h->stream>>>(a);
+  }
+  k_emul_cluster_writeback<<<P.ctas, kClusterBlock, 0, h->stream>>>(a);
+  for (int r = 0; r < P.ctas; ++r) g_emul_cluster_smem[r] = nullptr;
+  h->niter += k;
+  return 0;
 #endif
 }
 

@@ -382,11 +382,45 @@ def test_emulated_tiny_persistent_kernel(name, flags):
         curves_close(np.array(trace), g["trace_10"])
     finally:
         solver.close()
-    # too large for one CTA: the flag is ignored
+    # too large for one CTA: the cluster kernel takes it; with CPPPD_FLAG_NO_TINY_PERSISTENT the graph path
     args, g = case_args("potts50")
-    x, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=20, nb_iter_plot=10, flags=_cabi.FLAG_TINY_PERSISTENT)
-    assert solver.info()["tiny_persistent"] == 0
-    solver.close()
+    for flag, want in ((_cabi.FLAG_TINY_PERSISTENT, 2), (_cabi.FLAG_NO_TINY_PERSISTENT, 0)):
+        x, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=20, nb_iter_plot=10, flags=flag)
+        assert solver.info()["tiny_persistent"] == want
+        solver.close()
+
+
+@pytest.mark.parametrize("name", ["potts50", "sc105", "random_small", "random_small_alpha", "kb2", "afiro", "sc50a", "sc50b"])
+@pytest.mark.parametrize("flags", [0, _cabi.FLAG_VALUE_DICT | _cabi.FLAG_CONST_VECTORS | _cabi.FLAG_REORDER])
+def test_emulated_cluster_kernel(name, flags):
+    """k_cluster_iterate (csrc/cpppd_cluster.cuh), the default for small LPs: its staging (index words translated into
+    [owner CTA][offset], slices padded to whole chunks with value-0 entries) and its per-row code compiled for the host
+    and driven phase by phase over one buffer per CTA — what the hardware cluster does between two cluster barriers.
+    Same bits as the goldens; the one-CTA kernel and the graph path give the same x, y."""
+    args, g = case_args(name)
+    kw = CASE_PARAMS.get(name, {})
+    trace = []
+    x, best, solver = emulated_chambolle_pock_ppd(
+        *args, nb_max_iter=100, nb_iter_plot=10, flags=flags,
+        callback_func=lambda k, xx, e1, e2, el, a, b: trace.append((k, e1, e2, a, b)), **kw)
+    try:
+        assert solver.info()["tiny_persistent"] == 2 and solver.niter == 100
+        y = solver.get_y()
+        y_gold = np.concatenate([g[k] for k in ("y_eq", "y_ineq") if k in g])
+        if "alpha" not in kw:
+            assert np.array_equal(x, g["x_100"]) and np.array_equal(y, y_gold)
+        else:
+            assert rel_inf(x, g["x_100"]) <= 1e-9 and rel_inf(y, y_gold) <= 1e-9
+        curves_close(np.array(trace), g["trace_10"])
+    finally:
+        solver.close()
+    x0, _, solver = emulated_chambolle_pock_ppd(*args, nb_max_iter=100, nb_iter_plot=10,
+                                                flags=flags | _cabi.FLAG_NO_TINY_PERSISTENT, **kw)
+    try:
+        assert solver.info()["tiny_persistent"] == 0
+        assert np.array_equal(x0, x) and np.array_equal(solver.get_y(), y)
+    finally:
+        solver.close()
 
 
 @pytest.mark.parametrize("window", ["small", "single"])
