@@ -3,7 +3,9 @@
 # for the CPU by make_emul.py) under AddressSanitizer and UndefinedBehaviorSanitizer: an out-of-bounds load or
 # store of a kernel, which a GPU may tolerate silently, aborts the run here.
 #
-#   bash tests/emul/sanitize.sh            (about 15 minutes; run from the repo root)
+#   bash tests/emul/sanitize.sh            (about an hour since the cluster kernel is emulated phase by phase; run from
+#                                           the repo root.  The two deselected regression curves — 27 500 iterations
+#                                           against a 150 s time-out — are too slow for the emulation.)
 #
 # Covers tests/test_library_on_cpu.py, tests/test_multi_rank_on_cpu.py and the dry run of the `-m gpu` tests.
 set -e
@@ -17,7 +19,8 @@ LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest tests/test_librar
 env $small CPPPD_EMULATE_GPU_TESTS=1 PYTHONPATH=.:tests LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
   python -m pytest tests -m gpu -p emul.patch_plugin -x -q \
   --deselect tests/test_gpu_variants.py::test_autotune_is_on_by_default_for_large_operands \
-  --deselect tests/test_gpu_parity.py::test_reference_golden_curves_through_solve
+  --deselect tests/test_gpu_parity.py::test_reference_golden_curves_through_solve \
+  --deselect tests/test_gpu_zz_opt_in_features.py::test_cluster_kernel_reproduces_the_potts50_regression_curve
 
 rebuild "-fsanitize=undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer"
 python -m pytest tests/test_library_on_cpu.py tests/test_multi_rank_on_cpu.py tests/test_fuzz_on_cpu.py -x -q
