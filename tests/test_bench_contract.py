@@ -130,6 +130,8 @@ def test_b200_arm_dry_run_on_the_emulated_library(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0 and d["cpu_baseline"]["cores"] >= 1
     e = d["e2e"]
     assert e["error"] is None and e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert len(e["call_seconds"]) == 2 and len(e["call_phases_rank0"]) == 2
+    assert all(set(ph) == {"setup", "iterate", "close"} and min(ph.values()) >= 0 for ph in e["call_phases_rank0"])
     assert d["gpu_launches"] == 2 * 2 * 3
     assert d["with_stats_block"]["iterations"] == 10 and d["with_stats_block"]["iterations_per_s"] > 0
     small = d["latency_bound_configs"]
